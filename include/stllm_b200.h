@@ -1,0 +1,105 @@
+/* stllm_b200 - C ABI of the B200-native ST-LLM video-token hot path.
+ *
+ * The reference (TencentARC/ST-LLM) has no FFI/operator layer of its own: its hot path is Python calling
+ * torch/cuBLAS/cuDNN ops.  This header is the drop-in boundary *under* the reference's Python
+ * model API: every entry point replaces the library call(s) the reference makes at the cited file:line.
+ * The Python classes in stllm_b200/ (same names/attributes/state-dict keys as stllm/models/*.py) bind these
+ * with ctypes; INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - All pointers are BORROWED device pointers (the caller - torch - owns memory; nothing is allocated here).
+ *   - fp16 = IEEE binary16 ("half"); matrices are row-major; ld* are row strides in ELEMENTS.
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on it; no internal sync.
+ *   - Return value: 0 on success, negative on error (never throws); stllm_last_error() describes the failure.
+ *   - Thread-safe for distinct streams.  There is NO CPU fallback: without a CUDA device every call fails.
+ */
+#ifndef STLLM_B200_H
+#define STLLM_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define STLLM_OK 0
+#define STLLM_ERR_BAD_ARG (-1)
+#define STLLM_ERR_CUDA (-2)
+#define STLLM_ERR_UNSUPPORTED (-3)
+#define STLLM_ERR_DRIVER (-4)
+
+/* GEMM epilogues */
+#define STLLM_EPI_NONE 0   /* C = A W^T (+bias) (+residual) */
+#define STLLM_EPI_GELU 1   /* C = gelu_erf(A W^T + bias) (+residual)                 eva_vit.py:55-57, Qformer.py:359 */
+#define STLLM_EPI_SWIGLU 2 /* W rows interleaved (gate_j, up_j): C[:,j] = silu(g_j) * u_j   modeling_llama_mem.py:143 */
+#define STLLM_EPI_RELU 3   /* C = relu(A W^T + bias)                                 st_llm.py:242,475 */
+
+int stllm_abi_version(void);
+const char* stllm_last_error(void);
+int stllm_device_sm_count(void);
+
+/* C[M,N] = epi(A[M,K] * W[N,K]^T + bias[N]) (+ residual[M,N]); fp16 operands, fp32 accumulate (tcgen05/TMEM).
+ * Replaces F.linear / nn.Linear / nn.Conv2d-as-GEMM at eva_vit.py:124,146,55-59,196; Qformer.py:186-208,285,
+ * 357,371; st_llm.py:368 (llama_proj), :38 (mvm head), :108,122 (lm_head); modeling_llama_mem.py:160-163,
+ * 139-143 (q/k/v/o, gate/up/down).  K, lda, ldw multiples of 8; A, W 16-byte aligned.
+ * For STLLM_EPI_SWIGLU the output has N/2 columns.  out_f32: 0 -> fp16 C, 1 -> fp32 C.
+ * tile_n: 0 = auto, or 128 / 256. */
+int stllm_gemm_f16(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N,
+                   int K, const void* bias, const void* residual, long long ldr, int epilogue, int out_f32,
+                   int tile_n, void* stream);
+
+/* out[b,s,h,:] = softmax(scale * q k^T + mask) v   (flash-style, fp32 softmax).  Strides: {batch, seq, head} in
+ * elements, multiples of 8.  q_prescale != 0: q <- fp16(q * q_prescale) first (eva_vit.py:128).
+ * key_mask: optional uint8 [B,Skv], 0 = masked -> additive mask_value (Qformer.py:801 -10000; HF Llama fp16 min).
+ * causal: key j visible to query i iff j <= i + (Skv - Sq).  D in {64, 88, 128}.
+ * Replaces eva_vit.py:128-145, Qformer.py:210-268, modeling_llama_mem.py:205-244. */
+int stllm_attention_f16(const void* q, const void* k, const void* v, void* out, int B, int H, int Sq, int Skv, int D,
+                        const long long* q_strides, const long long* k_strides, const long long* v_strides,
+                        const long long* o_strides, float scale, float q_prescale, int causal,
+                        const void* key_mask, float mask_value, void* stream);
+
+/* y = LayerNorm(x) with fp32 statistics; gamma/beta fp32.  eva_vit.py:157,163; blip2.py:103-109; Qformer.py:65,
+ * 282,366; st_llm.py:39. */
+int stllm_layernorm_f16(const void* x, long long ldx, void* y, long long ldy, const float* gamma, const float* beta,
+                        int rows, int cols, float eps, void* stream);
+
+/* y = w * fp16(x * rsqrt(mean(x^2) + eps)).  modeling_llama_mem.py:61-78. */
+int stllm_rmsnorm_f16(const void* x, long long ldx, void* y, long long ldy, const void* weight, int rows, int cols,
+                      float eps, void* stream);
+
+/* frames [n,C,H,W] (fp16, or fp32 when img_is_f32) -> patch matrix [n*(H/P)*(W/P), kpad] fp16, column =
+ * c*P*P + py*P + px (the flattening of Conv2d weight [D,C,P,P]); columns >= C*P*P are zero.  eva_vit.py:196,203. */
+int stllm_im2col_patch(const void* img, int img_is_f32, void* out, int n_img, int C, int H, int W, int P, int kpad,
+                       void* stream);
+
+/* x[n,0,:] = cls + pos[0]; x[n,1+p,:] = patches[n*NP+p,:] + pos[1+p].  eva_vit.py:328-332. */
+int stllm_vit_assemble_f16(const void* patches, long long ldp, const void* cls, const void* pos, void* x, int n_img,
+                           int n_patches, int dim, void* stream);
+
+/* in-place rotate-half RoPE on nheads consecutive heads per row; cos/sin fp32 [max_pos, head_dim/2].
+ * modeling_llama_mem.py:81-127. */
+int stllm_rope_f16(void* x, long long ldx, const int* pos, const float* cos_t, const float* sin_t, int rows,
+                   int nheads, int head_dim, int max_pos, void* stream);
+
+/* dst[i,:] = src[idx[i],:] (int64 idx).  st_llm.py:491 (img_embeds[~mask]) and nn.Embedding lookups.
+ * err_flag (optional, device int): set to 1 on an out-of-range index. */
+int stllm_gather_rows_f16(const void* src, long long lds, long long src_rows, const long long* idx, void* dst,
+                          long long ldd, int n_rows, int cols, int* err_flag, void* stream);
+
+/* y[b,:] = mean_t x[b,t,:] (fp32 accumulate).  st_llm.py:466,470. */
+int stllm_mean_frames_f16(const void* x, void* y, int B, int T, long long inner, void* stream);
+
+/* out[b,r,:] = x[b,idx[r],:] + g[b,:].  st_llm.py:472-476 (global-local merge). */
+int stllm_residual_merge_f16(const void* x, const void* g, const long long* idx, void* out, int B, int T, int R,
+                             long long inner, void* stream);
+
+/* out_sum[0] = mean_rows(2 - 2 cos(a_row, b_row)).  st_llm.py:89-91. */
+int stllm_cosine_loss_f16(const void* a, long long lda, const void* b, long long ldb, int rows, int cols,
+                          float* out_sum, void* stream);
+
+/* out[0] = sum of CE over rows with label != ignore_index, out[1] = number of such rows.  st_llm.py:124-138. */
+int stllm_cross_entropy_f16(const void* logits, long long ldl, const long long* labels, int rows, int V,
+                            long long ignore_index, float* out_sum_count, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* STLLM_B200_H */

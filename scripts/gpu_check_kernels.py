@@ -1,0 +1,249 @@
+"""Kernel-level bring-up check on a B200: every C-ABI op against a plain torch fp32 reference, all cases run
+(no stop at first failure), plus quick CUDA-event timings of the GEMM.  Usage: python scripts/gpu_check_kernels.py"""
+import math
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+from stllm_b200 import ops
+
+torch.manual_seed(0)
+dev = "cuda"
+fails = []
+
+
+def report(name, got, ref, atol, rtol):
+    got = got.float()
+    ref = ref.float()
+    err = (got - ref).abs()
+    tol = atol + rtol * ref.abs()
+    bad = (err > tol).sum().item()
+    finite = torch.isfinite(got).all().item()
+    ok = bad == 0 and finite
+    print(f"{'OK  ' if ok else 'FAIL'} {name:60s} max_abs={err.max().item():.3e} ref_max={ref.abs().max().item():.3e} "
+          f"bad={bad}/{err.numel()} finite={finite}", flush=True)
+    if not ok:
+        fails.append(name)
+        # error pattern: which rows / cols are wrong (helps debugging descriptor problems)
+        if err.dim() == 2:
+            rows = (err > tol).any(dim=1).nonzero().flatten()
+            cols = (err > tol).any(dim=0).nonzero().flatten()
+            print(f"     bad rows: n={rows.numel()} first={rows[:8].tolist()} last={rows[-4:].tolist()}  "
+                  f"bad cols: n={cols.numel()} first={cols[:8].tolist()} last={cols[-4:].tolist()}")
+            print("     got[0,:8]", got[0, :8].tolist())
+            print("     ref[0,:8]", ref[0, :8].tolist())
+    return ok
+
+
+def gemm_case(M, N, K, epi=ops.EPI_NONE, bias=False, residual=False, tile_n=0, out_f32=False, lda_pad=0):
+    a_full = torch.randn(M, K + lda_pad, device=dev, dtype=torch.float16) * 0.5
+    a = a_full[:, :K]
+    w = torch.randn(N, K, device=dev, dtype=torch.float16) * 0.05
+    b = (torch.randn(N, device=dev, dtype=torch.float16) * 0.5) if bias else None
+    n_out = N // 2 if epi == ops.EPI_SWIGLU else N
+    r = (torch.randn(M, n_out, device=dev, dtype=torch.float16)) if residual else None
+    ref = a.float() @ w.float().t()
+    if bias:
+        ref = ref + b.float()
+    if epi == ops.EPI_GELU:
+        ref = torch.nn.functional.gelu(ref)
+    elif epi == ops.EPI_RELU:
+        ref = torch.relu(ref)
+    elif epi == ops.EPI_SWIGLU:
+        ref = torch.nn.functional.silu(ref[:, 0::2]) * ref[:, 1::2]
+    if residual:
+        ref = ref + r.float()
+    out = ops.gemm(a, w, bias=b, residual=r, epilogue=epi, tile_n=tile_n,
+                   out_dtype=torch.float32 if out_f32 else torch.float16)
+    torch.cuda.synchronize()
+    name = f"gemm M={M} N={N} K={K} epi={epi} bias={int(bias)} res={int(residual)} tn={tile_n} f32={int(out_f32)} pad={lda_pad}"
+    return report(name, out, ref, atol=2e-2 if not out_f32 else 5e-3, rtol=1e-2)
+
+
+def attn_ref(q, k, v, scale, causal, key_mask, mask_value, q_prescale):
+    qf, kf, vf = q.float(), k.float(), v.float()
+    if q_prescale:
+        qf = (qf * q_prescale).half().float()
+    s = torch.einsum("bqhd,bkhd->bhqk", qf, kf) * scale
+    if key_mask is not None:
+        s = s + (1 - key_mask.float())[:, None, None, :] * mask_value
+    if causal:
+        Sq, Skv = q.shape[1], k.shape[1]
+        i = torch.arange(Sq, device=q.device)[:, None]
+        j = torch.arange(Skv, device=q.device)[None, :]
+        s = s.masked_fill(j > i + (Skv - Sq), float("-inf"))
+    p = torch.softmax(s, dim=-1)
+    return torch.einsum("bhqk,bkhd->bqhd", p, vf)
+
+
+def attn_case(B, H, Sq, Skv, D, causal=False, mask=False, prescale=False, packed=False):
+    if packed:  # q,k,v as slices of one [B, S, 3, H, D] buffer (the ViT / Llama qkv layout)
+        assert Sq == Skv
+        qkv = torch.randn(B, Sq, 3, H, D, device=dev, dtype=torch.float16)
+        q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+    else:
+        q = torch.randn(B, Sq, H, D, device=dev, dtype=torch.float16)
+        k = torch.randn(B, Skv, H, D, device=dev, dtype=torch.float16)
+        v = torch.randn(B, Skv, H, D, device=dev, dtype=torch.float16)
+    km = None
+    if mask:
+        lens = torch.randint(1, Skv + 1, (B,), device=dev)
+        km = (torch.arange(Skv, device=dev)[None, :] < lens[:, None]).to(torch.uint8)
+    scale = D ** -0.5
+    mv = -10000.0
+    ref = attn_ref(q, k, v, 1.0 if prescale else scale, causal, km, mv, scale if prescale else 0.0)
+    out = ops.attention(q, k, v, 1.0 if prescale else scale, causal=causal, key_mask=km, mask_value=mv,
+                        q_prescale=scale if prescale else 0.0)
+    torch.cuda.synchronize()
+    name = f"attn B={B} H={H} Sq={Sq} Skv={Skv} D={D} causal={int(causal)} mask={int(mask)} pre={int(prescale)} packed={int(packed)}"
+    return report(name, out.reshape(-1, D), ref.reshape(-1, D), atol=4e-3, rtol=1e-2)
+
+
+def time_gemm(M, N, K, epi=ops.EPI_NONE, tile_n=0, iters=20):
+    a = torch.randn(M, K, device=dev, dtype=torch.float16)
+    w = torch.randn(N, K, device=dev, dtype=torch.float16) * 0.02
+    n_out = N // 2 if epi == ops.EPI_SWIGLU else N
+    out = torch.empty(M, n_out, device=dev, dtype=torch.float16)
+    for _ in range(3):
+        ops.gemm(a, w, epilogue=epi, out=out, tile_n=tile_n)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        ops.gemm(a, w, epilogue=epi, out=out, tile_n=tile_n)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    tf = 2.0 * M * N * K / ms / 1e9
+    # cuBLAS bar (not on the product path)
+    for _ in range(3):
+        torch.matmul(a, w.t())
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(iters):
+        torch.matmul(a, w.t())
+    e1.record()
+    torch.cuda.synchronize()
+    ms_cb = e0.elapsed_time(e1) / iters
+    print(f"TIME gemm M={M} N={N} K={K} epi={epi} tn={tile_n}: {ms*1e3:.1f} us  {tf:.1f} TFLOP/s   "
+          f"(cuBLAS {ms_cb*1e3:.1f} us {2.0*M*N*K/ms_cb/1e9:.1f} TFLOP/s)", flush=True)
+
+
+def main():
+    print(torch.cuda.get_device_name(0), "SMs:", torch.cuda.get_device_properties(0).multi_processor_count)
+    t0 = time.time()
+    # --- GEMM: start tiny so a descriptor bug shows on the simplest case ---
+    gemm_case(128, 128, 64, tile_n=128)
+    gemm_case(128, 256, 64, tile_n=256)
+    gemm_case(128, 128, 128, tile_n=128)
+    gemm_case(128, 128, 512, tile_n=128)
+    gemm_case(256, 512, 256, tile_n=128)
+    gemm_case(256, 512, 256, tile_n=256)
+    gemm_case(100, 200, 72, tile_n=128)           # ragged M, N, K
+    gemm_case(100, 200, 72, tile_n=256)
+    gemm_case(4112, 4224, 1408, bias=True)         # ViT qkv
+    gemm_case(4112, 1408, 1408, bias=True, residual=True)
+    gemm_case(4112, 6144, 1408, epi=ops.EPI_GELU, bias=True)
+    gemm_case(4112, 1408, 6144, bias=True, residual=True)
+    gemm_case(4096, 1408, 640, bias=True)          # patch embed (K padded 588 -> 640)
+    gemm_case(576, 12288, 4096)                    # llama qkv
+    gemm_case(576, 22016, 4096, epi=ops.EPI_SWIGLU)
+    gemm_case(576, 4096, 11008, residual=True)
+    gemm_case(576, 32000, 4096)
+    gemm_case(64, 32001, 4096, out_f32=True)       # odd N -> scalar tail path
+    gemm_case(512, 4096, 768, bias=True)           # llama_proj
+    gemm_case(32, 1024, 4096, epi=ops.EPI_RELU, bias=True)
+    gemm_case(1, 4096, 4096)                       # decode-like M=1
+    gemm_case(300, 768, 768, bias=True, lda_pad=8) # strided A (ld != K)
+    # --- attention ---
+    attn_case(2, 16, 257, 257, 88, prescale=True, packed=True)   # ViT
+    attn_case(3, 12, 32, 32, 64)                                  # Q-Former self (no text)
+    attn_case(3, 12, 44, 44, 64, mask=True)                       # Q-Former self with text + padding mask
+    attn_case(3, 12, 32, 257, 64)                                 # Q-Former cross
+    attn_case(1, 32, 576, 576, 128, causal=True, packed=True)     # Llama prefill
+    attn_case(2, 32, 320, 320, 128, causal=True, mask=True)       # Llama prefill with right padding
+    attn_case(2, 32, 1, 300, 128, causal=True)                    # decode step
+    attn_case(1, 4, 130, 130, 128, causal=True)
+    # --- norms ---
+    x = torch.randn(4112, 1408, device=dev, dtype=torch.float16) * 3 + 0.5
+    g = torch.randn(1408, device=dev) * 0.2 + 1
+    b = torch.randn(1408, device=dev) * 0.1
+    report("layernorm 4112x1408 eps1e-6", ops.layernorm(x, g, b, 1e-6),
+           torch.nn.functional.layer_norm(x.float(), (1408,), g, b, 1e-6), 2e-3, 2e-3)
+    x = torch.randn(333, 768, device=dev, dtype=torch.float16)
+    g = torch.randn(768, device=dev) * 0.2 + 1
+    b = torch.randn(768, device=dev) * 0.1
+    report("layernorm 333x768 eps1e-12", ops.layernorm(x, g, b, 1e-12),
+           torch.nn.functional.layer_norm(x.float(), (768,), g, b, 1e-12), 2e-3, 2e-3)
+    x = torch.randn(576, 4096, device=dev, dtype=torch.float16) * 2
+    w = (torch.randn(4096, device=dev) * 0.2 + 1).half()
+    ref = (x.float() * torch.rsqrt(x.float().pow(2).mean(-1, keepdim=True) + 1e-6)).half().float() * w.float()
+    report("rmsnorm 576x4096", ops.rmsnorm(x, w, 1e-6), ref, 2e-3, 2e-3)
+    # --- im2col + assemble ---
+    img = torch.randn(3, 3, 224, 224, device=dev)
+    cols = ops.im2col_patch(img, 14, 640)
+    ref = torch.nn.functional.unfold(img, kernel_size=14, stride=14).transpose(1, 2).reshape(-1, 588)
+    report("im2col fp32 in", cols[:, :588], ref.half(), 0, 0)
+    report("im2col pad zero", cols[:, 588:], torch.zeros_like(cols[:, 588:]), 0, 0)
+    cols16 = ops.im2col_patch(img.half(), 14, 640)
+    report("im2col fp16 in", cols16[:, :588], ref.half(), 0, 0)
+    patches = torch.randn(3 * 256, 1408, device=dev, dtype=torch.float16)
+    cls = torch.randn(1408, device=dev, dtype=torch.float16)
+    pos = torch.randn(257, 1408, device=dev, dtype=torch.float16)
+    xa = ops.vit_assemble(patches, cls, pos, 3, 256)
+    ref = torch.cat([cls.expand(3, 1, 1408), patches.view(3, 256, 1408)], 1) + pos
+    report("vit_assemble", xa.reshape(-1, 1408), ref.reshape(-1, 1408), 0, 0)
+    # --- rope ---
+    S, H, D = 70, 32, 128
+    qkv = torch.randn(S, 3 * H * D, device=dev, dtype=torch.float16)
+    cos_t, sin_t = ops.rope_tables(D, 2048)
+    pos_ids = torch.arange(S, device=dev, dtype=torch.int32) + 5
+    qk = qkv[:, :2 * H * D].float().view(S, 2 * H, D)
+    c = torch.cat([cos_t, cos_t], -1)[pos_ids.long()][:, None, :]
+    s_ = torch.cat([sin_t, sin_t], -1)[pos_ids.long()][:, None, :]
+    rot = torch.cat([-qk[..., D // 2:], qk[..., :D // 2]], -1)
+    ref = (qk * c + rot * s_).reshape(S, 2 * H * D)
+    vref = qkv[:, 2 * H * D:].clone()
+    ops.rope_(qkv, pos_ids, cos_t, sin_t, 2 * H, D)
+    report("rope q,k", qkv[:, :2 * H * D], ref, 2e-3, 2e-3)
+    report("rope leaves v", qkv[:, 2 * H * D:], vref, 0, 0)
+    # --- gather / mean / merge / losses ---
+    src = torch.randn(1000, 4096, device=dev, dtype=torch.float16)
+    idx = torch.randint(0, 1000, (777,), device=dev)
+    report("gather_rows", ops.gather_rows(src, idx), src[idx], 0, 0)
+    x = torch.randn(2, 16, 32, 4096, device=dev, dtype=torch.float16)
+    report("mean_frames", ops.mean_frames(x).reshape(-1, 4096), x.float().mean(1).reshape(-1, 4096), 1e-3, 1e-3)
+    gl = torch.randn(2, 32, 4096, device=dev, dtype=torch.float16)
+    ridx = torch.tensor([2, 6, 10, 14], device=dev)
+    report("residual_merge", ops.residual_merge(x, gl, ridx).reshape(-1, 4096),
+           (x[:, ridx] + gl[:, None]).reshape(-1, 4096), 0, 0)
+    a = torch.randn(512, 4096, device=dev, dtype=torch.float16)
+    bb = torch.randn(512, 4096, device=dev, dtype=torch.float16)
+    an, bn = a.float() / a.float().norm(dim=-1, keepdim=True), bb.float() / bb.float().norm(dim=-1, keepdim=True)
+    report("cosine_loss", ops.cosine_loss(a, bb).view(1, 1), (2 - 2 * (an * bn).sum(-1)).mean().view(1, 1), 1e-4, 1e-4)
+    logits = torch.randn(100, 32000, device=dev, dtype=torch.float16) * 3
+    labels = torch.randint(0, 32000, (100,), device=dev)
+    labels[::3] = -100
+    report("cross_entropy", ops.cross_entropy(logits, labels).view(1, 1),
+           torch.nn.functional.cross_entropy(logits.float(), labels, ignore_index=-100).view(1, 1), 1e-3, 1e-3)
+    print(f"checks done in {time.time()-t0:.1f}s; failures: {len(fails)}")
+    for f in fails:
+        print("  FAILED:", f)
+    # --- timings ---
+    if "--no-time" not in sys.argv:
+        for tn in (128, 256):
+            time_gemm(4112, 6144, 1408, ops.EPI_GELU, tn)
+            time_gemm(4112, 4224, 1408, ops.EPI_NONE, tn)
+            time_gemm(4112, 1408, 6144, ops.EPI_NONE, tn)
+            time_gemm(576, 22016, 4096, ops.EPI_SWIGLU, tn)
+            time_gemm(576, 4096, 11008, ops.EPI_NONE, tn)
+            time_gemm(576, 12288, 4096, ops.EPI_NONE, tn)
+            time_gemm(8192, 8192, 8192, ops.EPI_NONE, tn)
+    return 1 if fails else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,23 @@
+// C-ABI glue: error string, version, device queries.  See include/stllm_b200.h.
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+static thread_local char g_last_error[1024] = "";
+
+void stllm_set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" const char* stllm_last_error(void) { return g_last_error; }
+extern "C" int stllm_abi_version(void) { return 1; }
+extern "C" int stllm_device_sm_count(void) {
+  int dev = 0, n = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return STLLM_ERR_CUDA;
+  if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return STLLM_ERR_CUDA;
+  return n;
+}

@@ -1,0 +1,295 @@
+// HBM-bound data-movement kernels of the video-token path (coalesced, 16-byte vectors where the layout allows).
+//   im2col            eva_vit.py:196,203   Conv2d(3, D, k=14, s=14) == GEMM over 14x14x3 patches
+//   vit_assemble      eva_vit.py:328-332   [cls ; patches] + pos_embed
+//   rope              modeling_llama_mem.py:81-127  rotate-half RoPE on q,k (positions 0..S-1)
+//   gather_rows       st_llm.py:491 (img_embeds[~mask]), nn.Embedding lookups (st_llm.py:392-393,510)
+//   mean_frames       st_llm.py:466,470   mean over T
+//   residual_merge    st_llm.py:472-476   local[:, idx] + global (global-local long-video path)
+//   cosine_loss       st_llm.py:89-91     MVM loss  mean(2 - 2 cos)
+//   cross_entropy     st_llm.py:124-138   shifted CE, ignore_index -100
+#include "common.cuh"
+
+namespace {
+
+template <typename TIN>
+__global__ void im2col_patch_kernel(const TIN* __restrict__ img, __half* __restrict__ out, int n_img, int C, int H,
+                                    int W, int P, int kpad) {
+  const int gw = W / P, gh = H / P;
+  const int kreal = C * P * P;
+  const long long total = (long long)n_img * gh * gw * kpad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int col = (int)(i % kpad);
+    const long long rowi = i / kpad;
+    float v = 0.f;
+    if (col < kreal) {
+      const int px = col % P, py = (col / P) % P, c = col / (P * P);
+      const int gx = (int)(rowi % gw), gy = (int)((rowi / gw) % gh);
+      const long long n = rowi / ((long long)gw * gh);
+      v = (float)img[((n * C + c) * H + (gy * P + py)) * (long long)W + gx * P + px];
+    }
+    out[i] = __float2half_rn(v);
+  }
+}
+
+// x[n,0,:] = cls + pos[0];  x[n,1+p,:] = patches[n*NP+p,:] + pos[1+p]   (fp16 add, one rounding)
+__global__ void vit_assemble_kernel(const __half* __restrict__ patches, long long ldp, const __half* __restrict__ cls,
+                                    const __half* __restrict__ pos, __half* __restrict__ x, int n_img, int np,
+                                    int dim) {
+  const int dv = dim >> 3;
+  const long long total = (long long)n_img * (np + 1) * dv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % dv);
+    const long long tok = i / dv;
+    const int t = (int)(tok % (np + 1));
+    const long long n = tok / (np + 1);
+    uint4 a = (t == 0) ? __ldg(reinterpret_cast<const uint4*>(cls) + c)
+                       : __ldg(reinterpret_cast<const uint4*>(patches + (n * np + t - 1) * ldp) + c);
+    uint4 b = __ldg(reinterpret_cast<const uint4*>(pos + (long long)t * dim) + c);
+    const __half2* ah = reinterpret_cast<const __half2*>(&a);
+    const __half2* bh = reinterpret_cast<const __half2*>(&b);
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) oh[j] = __hadd2(ah[j], bh[j]);
+    reinterpret_cast<uint4*>(x + tok * dim)[c] = o;
+  }
+}
+
+// in-place rotate-half RoPE on `nheads` consecutive heads of each row: x[row, h*D + j], j in [0,D)
+// cos/sin: fp32 tables [max_pos, D/2]; pos[row] int32 position ids
+__global__ void rope_kernel(__half* __restrict__ x, long long ldx, const int* __restrict__ pos,
+                            const float* __restrict__ cos_t, const float* __restrict__ sin_t, int rows, int nheads,
+                            int D) {
+  const int half_d = D >> 1;
+  const long long total = (long long)rows * nheads * (half_d >> 1);  // 2 pairs per thread (half2)
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(i % (half_d >> 1)) * 2;
+    const long long rh = i / (half_d >> 1);
+    const int h = (int)(rh % nheads);
+    const long long row = rh / nheads;
+    const int ppos = pos[row];
+    __half* base = x + row * ldx + (long long)h * D;
+    const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(base + j));
+    const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(base + j + half_d));
+    const float2 c = *reinterpret_cast<const float2*>(cos_t + (long long)ppos * half_d + j);
+    const float2 s = *reinterpret_cast<const float2*>(sin_t + (long long)ppos * half_d + j);
+    // out_lo = lo*cos - hi*sin ; out_hi = hi*cos + lo*sin   (cos/sin identical for j and j + D/2)
+    *reinterpret_cast<__half2*>(base + j) = __floats2half2_rn(lo.x * c.x - hi.x * s.x, lo.y * c.y - hi.y * s.y);
+    *reinterpret_cast<__half2*>(base + j + half_d) =
+        __floats2half2_rn(hi.x * c.x + lo.x * s.x, hi.y * c.y + lo.y * s.y);
+  }
+}
+
+__global__ void gather_rows_kernel(const __half* __restrict__ src, long long lds, const long long* __restrict__ idx,
+                                   __half* __restrict__ dst, long long ldd, int n_rows, int cols, long long src_rows,
+                                   int* __restrict__ err) {
+  const int cv = cols >> 3;
+  const long long total = (long long)n_rows * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv);
+    const long long r = i / cv;
+    const long long s = idx[r];
+    if (s < 0 || s >= src_rows) {
+      if (err != nullptr) *err = 1;
+      continue;
+    }
+    reinterpret_cast<uint4*>(dst + r * ldd)[c] = __ldg(reinterpret_cast<const uint4*>(src + s * lds) + c);
+  }
+}
+
+// x: [B, T, inner] -> y: [B, inner], mean over T with fp32 accumulation (torch.mean on fp16 does the same)
+__global__ void mean_frames_kernel(const __half* __restrict__ x, __half* __restrict__ y, int B, int T,
+                                   long long inner) {
+  const long long iv = inner >> 1;
+  const long long total = (long long)B * iv;
+  const float inv = 1.f / (float)T;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long c = i % iv, b = i / iv;
+    float2 acc = make_float2(0.f, 0.f);
+    for (int t = 0; t < T; ++t) {
+      const float2 f = __half22float2(*reinterpret_cast<const __half2*>(x + ((long long)b * T + t) * inner + 2 * c));
+      acc.x += f.x;
+      acc.y += f.y;
+    }
+    *reinterpret_cast<__half2*>(y + b * inner + 2 * c) = __floats2half2_rn(acc.x * inv, acc.y * inv);
+  }
+}
+
+// out[b, r, :] = x[b, idx[r], :] + g[b, :]      x: [B, T, inner], g: [B, inner], out: [B, R, inner]
+__global__ void residual_merge_kernel(const __half* __restrict__ x, const __half* __restrict__ g,
+                                      const long long* __restrict__ idx, __half* __restrict__ out, int B, int T,
+                                      int R, long long inner) {
+  const long long iv = inner >> 3;
+  const long long total = (long long)B * R * iv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long c = i % iv;
+    const long long br = i / iv;
+    const int r = (int)(br % R);
+    const long long b = br / R;
+    const long long t = idx[r];
+    uint4 a = __ldg(reinterpret_cast<const uint4*>(x + (b * T + t) * inner) + c);
+    uint4 gg = __ldg(reinterpret_cast<const uint4*>(g + b * inner) + c);
+    const __half2* ah = reinterpret_cast<const __half2*>(&a);
+    const __half2* gh = reinterpret_cast<const __half2*>(&gg);
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) oh[j] = __hadd2(ah[j], gh[j]);
+    reinterpret_cast<uint4*>(out + br * inner)[c] = o;
+  }
+}
+
+// per row: 2 - 2 * <a/|a|, b/|b|>; accumulated (sum) into out[0]; host divides by rows. One warp per row.
+__global__ void cosine_loss_kernel(const __half* __restrict__ a, long long lda, const __half* __restrict__ b,
+                                   long long ldb, int rows, int cols, float* __restrict__ out) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const __half* ar = a + (long long)row * lda;
+  const __half* br = b + (long long)row * ldb;
+  float aa = 0.f, bb = 0.f, ab = 0.f;
+  for (int i = lane * 2; i < cols; i += 64) {
+    const float2 x = __half22float2(*reinterpret_cast<const __half2*>(ar + i));
+    const float2 y = __half22float2(*reinterpret_cast<const __half2*>(br + i));
+    aa += x.x * x.x + x.y * x.y;
+    bb += y.x * y.x + y.y * y.y;
+    ab += x.x * y.x + x.y * y.y;
+  }
+  aa = warp_sum(aa);
+  bb = warp_sum(bb);
+  ab = warp_sum(ab);
+  if (lane == 0) atomicAdd(out, (2.f - 2.f * ab * rsqrtf(aa) * rsqrtf(bb)) / (float)rows);
+}
+
+// per row: logsumexp(logits) - logits[label] for label != ignore; out[0] += loss, out[1] += count
+__global__ void cross_entropy_kernel(const __half* __restrict__ logits, long long ldl,
+                                     const long long* __restrict__ labels, int rows, int V, long long ignore_index,
+                                     float* __restrict__ out) {
+  const int row = blockIdx.x;
+  if (row >= rows) return;
+  const long long lab = labels[row];
+  if (lab == ignore_index || lab < 0 || lab >= V) return;
+  const __half* lr = logits + (long long)row * ldl;
+  __shared__ float red[32];
+  float m = -INFINITY;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) m = fmaxf(m, __half2float(lr[i]));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : -INFINITY;
+  m = warp_max(m);
+  m = __shfl_sync(0xffffffffu, m, 0);
+  __syncthreads();
+  float s = 0.f;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) s += __expf(__half2float(lr[i]) - m);
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+    s = warp_sum(s);
+    if (threadIdx.x == 0) {
+      atomicAdd(out, logf(s) + m - __half2float(lr[lab]));
+      atomicAdd(out + 1, 1.f);
+    }
+  }
+}
+
+int grid_for(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  const long long cap = 148LL * 16;
+  return (int)(g < cap ? (g > 0 ? g : 1) : cap);
+}
+
+}  // namespace
+
+extern "C" int stllm_im2col_patch(const void* img, int img_is_f32, void* out, int n_img, int C, int H, int W, int P,
+                                  int kpad, void* stream) {
+  STLLM_CHECK_ARG(img && out && n_img > 0 && C > 0 && P > 0 && H % P == 0 && W % P == 0 && kpad >= C * P * P);
+  const long long total = (long long)n_img * (H / P) * (W / P) * kpad;
+  const int grid = grid_for(total, 256);
+  if (img_is_f32)
+    im2col_patch_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)img, (__half*)out, n_img, C, H, W, P, kpad);
+  else
+    im2col_patch_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)img, (__half*)out, n_img, C, H, W, P, kpad);
+  STLLM_CHECK_CUDA(cudaGetLastError());
+  return STLLM_OK;
+}
+
+extern "C" int stllm_vit_assemble_f16(const void* patches, long long ldp, const void* cls, const void* pos, void* x,
+                                      int n_img, int n_patches, int dim, void* stream) {
+  STLLM_CHECK_ARG(patches && cls && pos && x && n_img > 0 && n_patches > 0 && dim % 8 == 0 && ldp % 8 == 0);
+  STLLM_CHECK_ARG((((uintptr_t)patches | (uintptr_t)cls | (uintptr_t)pos | (uintptr_t)x) & 15) == 0);
+  const long long total = (long long)n_img * (n_patches + 1) * (dim / 8);
+  vit_assemble_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __half*)patches, ldp, (const __half*)cls, (const __half*)pos, (__half*)x, n_img, n_patches, dim);
+  STLLM_CHECK_CUDA(cudaGetLastError());
+  return STLLM_OK;
+}
+
+extern "C" int stllm_rope_f16(void* x, long long ldx, const int* pos, const float* cos_t, const float* sin_t, int rows,
+                              int nheads, int head_dim, int max_pos, void* stream) {
+  STLLM_CHECK_ARG(x && pos && cos_t && sin_t && rows > 0 && nheads > 0 && head_dim % 4 == 0 && ldx % 2 == 0);
+  STLLM_CHECK_ARG(max_pos > 0 && (((uintptr_t)x) & 3) == 0 && (((uintptr_t)cos_t | (uintptr_t)sin_t) & 7) == 0);
+  const long long total = (long long)rows * nheads * (head_dim / 4);
+  rope_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((__half*)x, ldx, pos, cos_t, sin_t, rows, nheads,
+                                                                      head_dim);
+  STLLM_CHECK_CUDA(cudaGetLastError());
+  return STLLM_OK;
+}
+
+extern "C" int stllm_gather_rows_f16(const void* src, long long lds, long long src_rows, const long long* idx, void* dst,
+                                     long long ldd, int n_rows, int cols, int* err_flag, void* stream) {
+  STLLM_CHECK_ARG(src && idx && dst && n_rows > 0 && cols > 0 && cols % 8 == 0 && lds % 8 == 0 && ldd % 8 == 0);
+  STLLM_CHECK_ARG((((uintptr_t)src | (uintptr_t)dst) & 15) == 0);
+  const long long total = (long long)n_rows * (cols / 8);
+  gather_rows_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)src, lds, idx, (__half*)dst,
+                                                                             ldd, n_rows, cols, src_rows, err_flag);
+  STLLM_CHECK_CUDA(cudaGetLastError());
+  return STLLM_OK;
+}
+
+extern "C" int stllm_mean_frames_f16(const void* x, void* y, int B, int T, long long inner, void* stream) {
+  STLLM_CHECK_ARG(x && y && B > 0 && T > 0 && inner > 0 && inner % 2 == 0);
+  const long long total = (long long)B * (inner / 2);
+  mean_frames_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)x, (__half*)y, B, T, inner);
+  STLLM_CHECK_CUDA(cudaGetLastError());
+  return STLLM_OK;
+}
+
+extern "C" int stllm_residual_merge_f16(const void* x, const void* g, const long long* idx, void* out, int B, int T,
+                                        int R, long long inner, void* stream) {
+  STLLM_CHECK_ARG(x && g && idx && out && B > 0 && T > 0 && R > 0 && inner > 0 && inner % 8 == 0);
+  STLLM_CHECK_ARG((((uintptr_t)x | (uintptr_t)g | (uintptr_t)out) & 15) == 0);
+  const long long total = (long long)B * R * (inner / 8);
+  residual_merge_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __half*)x, (const __half*)g, idx, (__half*)out, B, T, R, inner);
+  STLLM_CHECK_CUDA(cudaGetLastError());
+  return STLLM_OK;
+}
+
+extern "C" int stllm_cosine_loss_f16(const void* a, long long lda, const void* b, long long ldb, int rows, int cols,
+                                     float* out_sum, void* stream) {
+  STLLM_CHECK_ARG(a && b && out_sum && rows > 0 && cols > 0 && cols % 2 == 0 && lda % 2 == 0 && ldb % 2 == 0);
+  STLLM_CHECK_CUDA(cudaMemsetAsync(out_sum, 0, sizeof(float), (cudaStream_t)stream));
+  cosine_loss_kernel<<<(rows + 3) / 4, 128, 0, (cudaStream_t)stream>>>((const __half*)a, lda, (const __half*)b, ldb,
+                                                                       rows, cols, out_sum);
+  STLLM_CHECK_CUDA(cudaGetLastError());
+  return STLLM_OK;
+}
+
+extern "C" int stllm_cross_entropy_f16(const void* logits, long long ldl, const long long* labels, int rows, int V,
+                                       long long ignore_index, float* out_sum_count, void* stream) {
+  STLLM_CHECK_ARG(logits && labels && out_sum_count && rows > 0 && V > 0);
+  STLLM_CHECK_CUDA(cudaMemsetAsync(out_sum_count, 0, 2 * sizeof(float), (cudaStream_t)stream));
+  cross_entropy_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>((const __half*)logits, ldl, labels, rows, V,
+                                                               ignore_index, out_sum_count);
+  STLLM_CHECK_CUDA(cudaGetLastError());
+  return STLLM_OK;
+}

@@ -1,0 +1,392 @@
+// tcgen05 / TMEM / TMA GEMM for sm_100a:   C[M,N] = epilogue(A[M,K] * W[N,K]^T + bias) (+ residual)
+//
+// This is the one dense-contraction kernel of the hot path. It replaces every nn.Linear / Conv2d-as-GEMM
+// the reference dispatches to cuBLAS/cuDNN: eva_vit.py:124 (qkv), :146 (proj), :55-59 (fc1/GELU/fc2),
+// :196 (patch-embed conv as im2col GEMM), Qformer.py query/key/value/dense, st_llm.py:368 (llama_proj),
+// the HF Llama q/k/v/o/gate/up/down projections and lm_head (st_llm.py:108,122).
+//
+// Design (B200-first, persistent, warp-specialised):
+//   * grid = min(#tiles, #SMs) persistent CTAs, 1 CTA/SM, 320 threads:
+//       warp 0      : TMA producer   (one elected lane; A and W tiles, 128B-swizzled, mbarrier complete_tx)
+//       warp 1      : TMEM allocator + MMA issuer (one lane issues tcgen05.mma kind::f16, fp32 accumulate)
+//       warps 2..9  : epilogue (tcgen05.ld -> bias / GELU / SwiGLU / residual -> fp16 -> global)
+//   * smem ring of STAGES x {A 128x64, W BNx64} fp16 tiles; TMEM holds 2 accumulator stages (2 x BN
+//     columns) so the epilogue of tile i overlaps the mainloop of tile i+1.
+//   * Both operands are K-major (activations row-major, nn.Linear weights [N,K]) so no transposes exist
+//     anywhere on the path; ragged M/N/K edges are zero-filled by TMA and predicated in the epilogue.
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 fp16 = 128 B = one swizzle-128B row
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
+
+enum Epilogue : int { EPI_NONE = 0, EPI_GELU = 1, EPI_SWIGLU = 2, EPI_RELU = 3 };
+
+struct GemmParams {
+  void* C;
+  const __half* bias;      // [N] or null
+  const __half* residual;  // [M, ldr] or null (added after the activation)
+  long long ldc, ldr;
+  int M, N, K;
+  int m_tiles, n_tiles;
+  int out_f32;  // 0: fp16 output, 1: fp32 output
+};
+
+template <int BN, int STAGES>
+struct SmemLayout {
+  static constexpr int A_BYTES = BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + alignment slack
+};
+
+DEVI float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+DEVI float silu(float x) { return x / (1.0f + __expf(-x)); }
+
+template <int BN, int STAGES, int EPI>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                        const GemmParams p) {
+  using L = SmemLayout<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  // swizzle-128B tiles need 1024-B alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+  const int k_blocks = (p.K + BK - 1) / BK;
+  constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], NUM_EPI_WARPS);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_base_slot, TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m_blk = t % p.m_tiles, n_blk = t / p.m_tiles;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+          tma_load_2d(&tmA, &full_bar[stage], sa, kb * BK, m_blk * BM, TMA_EVICT_NORMAL);
+          tma_load_2d(&tmB, &full_bar[stage], sb, kb * BK, n_blk * BN, TMA_EVICT_NORMAL);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(BM, BN, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint32_t sb = sa + L::A_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t da = make_sdesc_k_sw128(sa + kk * 32);
+            const uint64_t db = make_sdesc_k_sw128(sb + kk * 32);
+            umma_f16_ss(d_tmem, da, db, idesc, (kb | kk) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int e = warp - 2;
+    const int quad = warp & 3;           // TMEM lane quadrant this warp may access
+    const int half_idx = e >> 2;         // which half of the BN columns
+    constexpr int COLS_PER_WARP = BN / 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      const int m_blk = t % p.m_tiles, n_blk = t / p.m_tiles;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_blk * BM + quad * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half_idx * COLS_PER_WARP);
+#pragma unroll 1
+      for (int c = 0; c < COLS_PER_WARP; c += 32) {
+        __syncwarp();
+        uint32_t r[32];
+        tmem_ld_32x32b_x32(t_row + c, r);
+        tmem_ld_wait();
+        if (c + 32 >= COLS_PER_WARP) {
+          // all TMEM reads of this warp for this tile are done -> release the accumulator stage early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        const int col0 = n_blk * BN + half_idx * COLS_PER_WARP + c;  // first accumulator column of the chunk
+        if (col0 >= p.N || !row_ok) continue;  // col0 is warp-uniform; row_ok lanes re-converge at __syncwarp
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        const bool full_chunk = (col0 + 32 <= p.N);
+        if (p.bias != nullptr) {
+          if (full_chunk) {
+            const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              uint4 b = __ldg(bp + q);
+              const __half2* bh = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float2 f = __half22float2(bh[j]);
+                v[q * 8 + 2 * j] += f.x;
+                v[q * 8 + 2 * j + 1] += f.y;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j < p.N) v[j] += __half2float(p.bias[col0 + j]);
+          }
+        }
+        if (EPI == EPI_GELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+        }
+        if (EPI == EPI_RELU) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        constexpr int NC = (EPI == EPI_SWIGLU) ? 16 : 32;  // output columns produced by this chunk
+        int ocol0 = col0, n_out = p.N;
+        if (EPI == EPI_SWIGLU) {
+          // interleaved weights: accumulator column 2j = gate_j, 2j+1 = up_j -> output column j
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = silu(v[2 * j]) * v[2 * j + 1];
+          ocol0 = col0 >> 1;
+          n_out = p.N >> 1;
+        }
+        const bool vec_ok = (ocol0 + NC <= n_out);
+        if (p.residual != nullptr) {
+          const __half* rp = p.residual + (long long)row * p.ldr + ocol0;
+          if (vec_ok && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
+#pragma unroll
+            for (int q = 0; q < NC / 8; ++q) {
+              uint4 b = __ldg(reinterpret_cast<const uint4*>(rp) + q);
+              const __half2* bh = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float2 f = __half22float2(bh[j]);
+                v[q * 8 + 2 * j] += f.x;
+                v[q * 8 + 2 * j + 1] += f.y;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < NC; ++j)
+              if (ocol0 + j < n_out) v[j] += __half2float(rp[j]);
+          }
+        }
+        if (p.out_f32) {
+          float* cp = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + ocol0;
+          if (vec_ok && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
+#pragma unroll
+            for (int q = 0; q < NC / 4; ++q)
+              reinterpret_cast<float4*>(cp)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < NC; ++j)
+              if (ocol0 + j < n_out) cp[j] = v[j];
+          }
+        } else {
+          __half* cp = reinterpret_cast<__half*>(p.C) + (long long)row * p.ldc + ocol0;
+          if (vec_ok && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
+#pragma unroll
+            for (int q = 0; q < NC / 8; ++q) {
+              uint4 o;
+              o.x = pack_half2(v[8 * q + 0], v[8 * q + 1]);
+              o.y = pack_half2(v[8 * q + 2], v[8 * q + 3]);
+              o.z = pack_half2(v[8 * q + 4], v[8 * q + 5]);
+              o.w = pack_half2(v[8 * q + 6], v[8 * q + 7]);
+              reinterpret_cast<uint4*>(cp)[q] = o;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < NC; ++j)
+              if (ocol0 + j < n_out) cp[j] = __float2half_rn(v[j]);
+          }
+        }
+      }
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// host side
+// ----------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (fn == nullptr) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(sym);
+  }
+  return fn;
+}
+
+// 2-D fp16 row-major [rows, cols] tensor, row stride ld elements; box = {64 cols, box_rows}; 128B swizzle
+int make_tmap(CUtensorMap* tm, const void* ptr, long long rows, long long cols, long long ld, int box_rows) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (enc == nullptr) {
+    stllm_set_last_error("cuTensorMapEncodeTiled driver entry point not available");
+    return STLLM_ERR_DRIVER;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    stllm_set_last_error("cuTensorMapEncodeTiled failed: CUresult %d (ptr %p rows %lld cols %lld ld %lld)", (int)r, ptr,
+                         rows, cols, ld);
+    return STLLM_ERR_DRIVER;
+  }
+  return STLLM_OK;
+}
+
+int g_num_sms = 0;
+int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+template <int BN, int STAGES, int EPI>
+int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+  using L = SmemLayout<BN, STAGES>;
+  auto kern = gemm_f16_tcgen05_kernel<BN, STAGES, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    STLLM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int grid = tiles < num_sms() ? tiles : num_sms();
+  kern<<<grid, NUM_THREADS, L::TOTAL, stream>>>(tmA, tmB, p);
+  STLLM_CHECK_CUDA(cudaGetLastError());
+  return STLLM_OK;
+}
+
+template <int BN, int STAGES>
+int dispatch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t s) {
+  switch (epi) {
+    case EPI_NONE: return launch_gemm<BN, STAGES, EPI_NONE>(tmA, tmB, p, s);
+    case EPI_GELU: return launch_gemm<BN, STAGES, EPI_GELU>(tmA, tmB, p, s);
+    case EPI_SWIGLU: return launch_gemm<BN, STAGES, EPI_SWIGLU>(tmA, tmB, p, s);
+    case EPI_RELU: return launch_gemm<BN, STAGES, EPI_RELU>(tmA, tmB, p, s);
+    default: stllm_set_last_error("unknown epilogue %d", epi); return STLLM_ERR_BAD_ARG;
+  }
+}
+
+}  // namespace
+
+extern "C" int stllm_gemm_f16(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc,
+                              int M, int N, int K, const void* bias, const void* residual, long long ldr,
+                              int epilogue, int out_f32, int tile_n, void* stream) {
+  STLLM_CHECK_ARG(A != nullptr && W != nullptr && C != nullptr);
+  STLLM_CHECK_ARG(M > 0 && N > 0 && K > 0);
+  STLLM_CHECK_ARG(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0);  // TMA: 16-byte global strides
+  STLLM_CHECK_ARG(lda >= K && ldw >= K);
+  STLLM_CHECK_ARG((reinterpret_cast<uintptr_t>(A) & 15) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0);
+  STLLM_CHECK_ARG(epilogue != EPI_SWIGLU || (N % 2 == 0));
+  STLLM_CHECK_ARG(ldc >= (epilogue == EPI_SWIGLU ? N / 2 : N));
+  STLLM_CHECK_ARG(residual == nullptr || ldr >= (epilogue == EPI_SWIGLU ? N / 2 : N));
+  int bn = tile_n;
+  if (bn == 0) {
+    // heuristic: wide tiles when there are enough of them to fill the machine, else narrower tiles
+    const long long m_tiles = (M + BM - 1) / BM;
+    const long long t256 = m_tiles * ((N + 255) / 256);
+    bn = (t256 >= num_sms()) ? 256 : 128;
+  }
+  STLLM_CHECK_ARG(bn == 128 || bn == 256);
+  CUtensorMap tmA, tmB;
+  int rc = make_tmap(&tmA, A, M, K, lda, BM);
+  if (rc != STLLM_OK) return rc;
+  rc = make_tmap(&tmB, W, N, K, ldw, bn);
+  if (rc != STLLM_OK) return rc;
+  GemmParams p;
+  p.C = C;
+  p.bias = reinterpret_cast<const __half*>(bias);
+  p.residual = reinterpret_cast<const __half*>(residual);
+  p.ldc = ldc;
+  p.ldr = ldr;
+  p.M = M;
+  p.N = N;
+  p.K = K;
+  p.m_tiles = (M + BM - 1) / BM;
+  p.n_tiles = (N + bn - 1) / bn;
+  p.out_f32 = out_f32;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (bn == 256) return dispatch_epi<256, 4>(epilogue, tmA, tmB, p, s);
+  return dispatch_epi<128, 6>(epilogue, tmA, tmB, p, s);
+}

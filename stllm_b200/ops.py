@@ -1,0 +1,254 @@
+"""Thin torch-tensor wrappers over the C ABI (include/stllm_b200.h).
+
+torch is used only for device memory and the current CUDA stream; all arithmetic happens in the sm_100a
+kernels of ``libstllm_b200.so``.  Every wrapper raises on non-CUDA tensors: there is no CPU fallback.
+"""
+import ctypes
+import math
+
+import torch
+
+from . import _lib
+
+EPI_NONE, EPI_GELU, EPI_SWIGLU, EPI_RELU = 0, 1, 2, 3
+
+# number of kernels launched through this module (bench.py reports it as gpu_launches)
+launch_count = 0
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.StllmNativeError("stllm_b200 ops need CUDA tensors (no CPU fallback exists for the hot path)")
+
+
+def _rows2d(t):
+    """view a [..., C] tensor with contiguous last dim and uniform row stride as (rows, ld)"""
+    assert t.stride(-1) == 1, "last dim must be contiguous"
+    if t.dim() == 1:
+        return 1, t.shape[0]
+    t2 = t if t.dim() == 2 else t.reshape(-1, t.shape[-1]) if t.is_contiguous() else None
+    if t2 is None:
+        raise ValueError("tensor must be 2-D or contiguous")
+    return t2.shape[0], t2.stride(0)
+
+
+def gemm(a, w, bias=None, residual=None, epilogue=EPI_NONE, out=None, out_dtype=torch.float16, tile_n=0):
+    """out = epi(a @ w.T + bias) (+ residual).  a: [..., K] fp16, w: [N, K] fp16 (nn.Linear layout)."""
+    global launch_count
+    _need_cuda(a, w, bias, residual, out)
+    assert a.dtype == torch.float16 and w.dtype == torch.float16
+    K = a.shape[-1]
+    N = w.shape[0]
+    assert w.shape[1] == K, (a.shape, w.shape)
+    M, lda = _rows2d(a)
+    n_out = N // 2 if epilogue == EPI_SWIGLU else N
+    if out is None:
+        out = torch.empty(a.shape[:-1] + (n_out,), dtype=out_dtype, device=a.device)
+    Mo, ldc = _rows2d(out)
+    assert Mo == M and out.shape[-1] == n_out
+    ldr = 0
+    if residual is not None:
+        assert residual.dtype == torch.float16 and residual.shape[-1] == n_out
+        Mr, ldr = _rows2d(residual)
+        assert Mr == M
+    if bias is not None:
+        assert bias.dtype == torch.float16 and bias.numel() == N and bias.is_contiguous()
+    rc = _lib.load().stllm_gemm_f16(_ptr(a), lda, _ptr(w), w.stride(0), _ptr(out), ldc, M, N, K, _ptr(bias),
+                                    _ptr(residual), ldr, epilogue, 1 if out.dtype == torch.float32 else 0, tile_n,
+                                    _stream())
+    _lib.check(rc, "stllm_gemm_f16")
+    launch_count += 1
+    return out
+
+
+def _strides3(t, layout):
+    """(batch, seq, head) element strides of a 4-D tensor given as 'bshd' or 'bhsd'"""
+    assert t.dim() == 4 and t.stride(-1) == 1
+    if layout == "bshd":
+        s = (t.stride(0), t.stride(1), t.stride(2))
+    else:
+        s = (t.stride(0), t.stride(2), t.stride(1))
+    return (ctypes.c_longlong * 3)(*s)
+
+
+def attention(q, k, v, scale, causal=False, key_mask=None, mask_value=-10000.0, q_prescale=0.0, out=None):
+    """q: [B, Sq, H, D], k/v: [B, Skv, H, D] (any strides with contiguous D) -> out [B, Sq, H, D] fp16."""
+    global launch_count
+    _need_cuda(q, k, v, key_mask, out)
+    B, Sq, H, D = q.shape
+    Skv = k.shape[1]
+    assert k.shape == (B, Skv, H, D) and v.shape == (B, Skv, H, D)
+    if out is None:
+        out = torch.empty((B, Sq, H, D), dtype=torch.float16, device=q.device)
+    if key_mask is not None:
+        key_mask = key_mask.to(torch.uint8).contiguous()
+        assert key_mask.shape == (B, Skv)
+    rc = _lib.load().stllm_attention_f16(_ptr(q), _ptr(k), _ptr(v), _ptr(out), B, H, Sq, Skv, D, _strides3(q, "bshd"),
+                                         _strides3(k, "bshd"), _strides3(v, "bshd"), _strides3(out, "bshd"),
+                                         float(scale), float(q_prescale), 1 if causal else 0, _ptr(key_mask),
+                                         float(mask_value), _stream())
+    _lib.check(rc, "stllm_attention_f16")
+    launch_count += 1
+    return out
+
+
+def layernorm(x, gamma, beta, eps, out=None):
+    global launch_count
+    _need_cuda(x, gamma, beta, out)
+    assert x.dtype == torch.float16 and gamma.dtype == torch.float32 and beta.dtype == torch.float32
+    rows, ldx = _rows2d(x)
+    if out is None:
+        out = torch.empty_like(x, memory_format=torch.contiguous_format)
+    _, ldy = _rows2d(out)
+    rc = _lib.load().stllm_layernorm_f16(_ptr(x), ldx, _ptr(out), ldy, _ptr(gamma), _ptr(beta), rows, x.shape[-1],
+                                         float(eps), _stream())
+    _lib.check(rc, "stllm_layernorm_f16")
+    launch_count += 1
+    return out
+
+
+def rmsnorm(x, weight, eps, out=None):
+    global launch_count
+    _need_cuda(x, weight, out)
+    assert x.dtype == torch.float16 and weight.dtype == torch.float16
+    rows, ldx = _rows2d(x)
+    if out is None:
+        out = torch.empty_like(x, memory_format=torch.contiguous_format)
+    _, ldy = _rows2d(out)
+    rc = _lib.load().stllm_rmsnorm_f16(_ptr(x), ldx, _ptr(out), ldy, _ptr(weight), rows, x.shape[-1], float(eps),
+                                       _stream())
+    _lib.check(rc, "stllm_rmsnorm_f16")
+    launch_count += 1
+    return out
+
+
+def im2col_patch(img, patch, kpad):
+    """img [n, C, H, W] fp16/fp32 -> [n * (H/P) * (W/P), kpad] fp16"""
+    global launch_count
+    _need_cuda(img)
+    assert img.dim() == 4 and img.is_contiguous() and img.dtype in (torch.float16, torch.float32)
+    n, C, H, W = img.shape
+    out = torch.empty((n * (H // patch) * (W // patch), kpad), dtype=torch.float16, device=img.device)
+    rc = _lib.load().stllm_im2col_patch(_ptr(img), 1 if img.dtype == torch.float32 else 0, _ptr(out), n, C, H, W,
+                                        patch, kpad, _stream())
+    _lib.check(rc, "stllm_im2col_patch")
+    launch_count += 1
+    return out
+
+
+def vit_assemble(patches, cls, pos, n_img, n_patches):
+    global launch_count
+    _need_cuda(patches, cls, pos)
+    dim = patches.shape[-1]
+    x = torch.empty((n_img, n_patches + 1, dim), dtype=torch.float16, device=patches.device)
+    rc = _lib.load().stllm_vit_assemble_f16(_ptr(patches), patches.stride(0), _ptr(cls), _ptr(pos), _ptr(x), n_img,
+                                            n_patches, dim, _stream())
+    _lib.check(rc, "stllm_vit_assemble_f16")
+    launch_count += 1
+    return x
+
+
+def rope_(x2d, pos, cos_t, sin_t, nheads, head_dim):
+    """in-place RoPE on the first nheads*head_dim columns of x2d [rows, ld]"""
+    global launch_count
+    _need_cuda(x2d, pos, cos_t, sin_t)
+    assert x2d.dim() == 2 and x2d.stride(1) == 1 and pos.dtype == torch.int32
+    assert cos_t.dtype == torch.float32 and cos_t.shape[1] == head_dim // 2 and cos_t.is_contiguous()
+    rc = _lib.load().stllm_rope_f16(_ptr(x2d), x2d.stride(0), _ptr(pos), _ptr(cos_t), _ptr(sin_t), x2d.shape[0],
+                                    nheads, head_dim, cos_t.shape[0], _stream())
+    _lib.check(rc, "stllm_rope_f16")
+    launch_count += 1
+    return x2d
+
+
+def gather_rows(src, idx, out=None):
+    """out[i, :] = src[idx[i], :]   src [R, C] fp16, idx int64 [n]"""
+    global launch_count
+    _need_cuda(src, idx, out)
+    assert src.dim() == 2 and src.stride(1) == 1 and src.dtype == torch.float16
+    idx = idx.to(torch.int64).contiguous()
+    n = idx.numel()
+    if out is None:
+        out = torch.empty((n, src.shape[1]), dtype=torch.float16, device=src.device)
+    if n == 0:
+        return out
+    rc = _lib.load().stllm_gather_rows_f16(_ptr(src), src.stride(0), src.shape[0], _ptr(idx), _ptr(out),
+                                           out.stride(0), n, src.shape[1], ctypes.c_void_p(0), _stream())
+    _lib.check(rc, "stllm_gather_rows_f16")
+    launch_count += 1
+    return out
+
+
+def mean_frames(x):
+    """x [B, T, ...] fp16 -> [B, ...] mean over T"""
+    global launch_count
+    _need_cuda(x)
+    assert x.is_contiguous() and x.dtype == torch.float16
+    B, T = x.shape[:2]
+    inner = x[0, 0].numel()
+    y = torch.empty((B,) + tuple(x.shape[2:]), dtype=torch.float16, device=x.device)
+    rc = _lib.load().stllm_mean_frames_f16(_ptr(x), _ptr(y), B, T, inner, _stream())
+    _lib.check(rc, "stllm_mean_frames_f16")
+    launch_count += 1
+    return y
+
+
+def residual_merge(x, g, idx):
+    """x [B, T, L, D], g [B, L, D], idx int64 [R] -> [B, R, L, D] = x[:, idx] + g[:, None]"""
+    global launch_count
+    _need_cuda(x, g, idx)
+    assert x.is_contiguous() and g.is_contiguous()
+    B, T = x.shape[:2]
+    inner = x[0, 0].numel()
+    idx = idx.to(torch.int64).contiguous()
+    R = idx.numel()
+    out = torch.empty((B, R) + tuple(x.shape[2:]), dtype=torch.float16, device=x.device)
+    rc = _lib.load().stllm_residual_merge_f16(_ptr(x), _ptr(g), _ptr(idx), _ptr(out), B, T, R, inner, _stream())
+    _lib.check(rc, "stllm_residual_merge_f16")
+    launch_count += 1
+    return out
+
+
+def cosine_loss(a, b):
+    """mean over rows of 2 - 2 cos(a_row, b_row); a, b [rows, C] fp16 -> fp32 scalar tensor"""
+    global launch_count
+    _need_cuda(a, b)
+    rows, lda = _rows2d(a)
+    _, ldb = _rows2d(b)
+    out = torch.empty(1, dtype=torch.float32, device=a.device)
+    rc = _lib.load().stllm_cosine_loss_f16(_ptr(a), lda, _ptr(b), ldb, rows, a.shape[-1], _ptr(out), _stream())
+    _lib.check(rc, "stllm_cosine_loss_f16")
+    launch_count += 1
+    return out[0]
+
+
+def cross_entropy(logits, labels, ignore_index=-100):
+    """mean CE over rows with label != ignore_index; logits [rows, V] fp16, labels int64 [rows]"""
+    global launch_count
+    _need_cuda(logits, labels)
+    rows, ldl = _rows2d(logits)
+    labels = labels.to(torch.int64).contiguous().view(-1)
+    assert labels.numel() == rows
+    out = torch.empty(2, dtype=torch.float32, device=logits.device)
+    rc = _lib.load().stllm_cross_entropy_f16(_ptr(logits), ldl, _ptr(labels), rows, logits.shape[-1], ignore_index,
+                                             _ptr(out), _stream())
+    _lib.check(rc, "stllm_cross_entropy_f16")
+    launch_count += 1
+    return out[0] / out[1]
+
+
+def rope_tables(head_dim, max_pos, base=10000.0, device="cuda"):
+    """fp32 cos/sin tables [max_pos, head_dim/2] (modeling_llama_mem.py:81-110 inv_freq/outer/cos/sin)"""
+    inv_freq = 1.0 / (base ** (torch.arange(0, head_dim, 2, dtype=torch.float32) / head_dim))
+    t = torch.arange(max_pos, dtype=torch.float32)
+    freqs = torch.outer(t, inv_freq)
+    return freqs.cos().contiguous().to(device), freqs.sin().contiguous().to(device)
