@@ -177,22 +177,28 @@ __global__ void cross_entropy_kernel(const __half* __restrict__ logits, long lon
   if (lab == ignore_index || lab < 0 || lab >= V) return;
   const __half* lr = logits + (long long)row * ldl;
   __shared__ float red[32];
+  __shared__ float bcast;
+  const int nwarps = blockDim.x >> 5;
   float m = -INFINITY;
   for (int i = threadIdx.x; i < V; i += blockDim.x) m = fmaxf(m, __half2float(lr[i]));
   m = warp_max(m);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
   __syncthreads();
-  m = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : -INFINITY;
-  m = warp_max(m);
-  m = __shfl_sync(0xffffffffu, m, 0);
+  if (threadIdx.x < 32) {
+    float x = (threadIdx.x < nwarps) ? red[threadIdx.x] : -INFINITY;
+    x = warp_max(x);
+    if (threadIdx.x == 0) bcast = x;
+  }
   __syncthreads();
+  m = bcast;
   float s = 0.f;
   for (int i = threadIdx.x; i < V; i += blockDim.x) s += __expf(__half2float(lr[i]) - m);
   s = warp_sum(s);
+  __syncthreads();
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
   if (threadIdx.x < 32) {
-    s = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.f;
+    s = (threadIdx.x < nwarps) ? red[threadIdx.x] : 0.f;
     s = warp_sum(s);
     if (threadIdx.x == 0) {
       atomicAdd(out, logf(s) + m - __half2float(lr[lab]));

@@ -1,0 +1,184 @@
+"""Generate the golden fixtures in tests/golden/ FROM THE REFERENCE ITSELF.
+
+Run in the build container only (needs /root/reference):   python tests/golden/make_golden.py
+It imports the UNMODIFIED reference modules through oracle/ref_shim.py, builds small random-init instances of
+the reference's own classes (eva_vit.VisionTransformer, Qformer.BertLMHeadModel, st_llm.STLLMForCausalLM /
+STLLMModel methods, utils.RandomMaskingGenerator), runs them on seeded inputs in fp32 on CPU and stores
+weights (rounded to fp16 so the files stay small; the fp16 values are what both sides load), inputs and
+outputs.  tests/test_oracle_golden.py checks oracle/stllm_oracle.py against these files; the GPU tests check
+the CUDA path against the oracle.  The fixtures are the pin for "parity" (the reference has no tests).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from oracle import ref_shim  # noqa: E402
+from tests import fake_tokenizer  # noqa: E402
+
+
+def _round_fp16_(module_or_sd):
+    sd = module_or_sd.state_dict() if hasattr(module_or_sd, "state_dict") else module_or_sd
+    for k, v in sd.items():
+        if v.is_floating_point():
+            v.copy_(v.half().float())
+    return sd
+
+
+def _save(name, **arrs):
+    out = {}
+    for k, v in arrs.items():
+        if isinstance(v, torch.Tensor):
+            v = v.detach().cpu().numpy()
+        out[k] = v
+    path = os.path.join(HERE, name)
+    np.savez_compressed(path, **out)
+    print(f"wrote {path}  ({os.path.getsize(path)/1e6:.2f} MB)")
+
+
+def _sd_arrays(prefix, sd):
+    return {f"{prefix}{k}": v.half().numpy() if v.is_floating_point() else v.numpy() for k, v in sd.items()}
+
+
+@torch.no_grad()
+def golden_vit(ref):
+    torch.manual_seed(0)
+    vit = ref_shim.build_vit(ref, img_size=56, embed_dim=176, depth=2, num_heads=2)
+    # the reference initialises biases / q_bias / v_bias to zero; give them values so the fixture pins them
+    for n, p in vit.named_parameters():
+        if n.endswith("bias") or n.endswith("q_bias") or n.endswith("v_bias"):
+            p.data.normal_(0, 0.05)
+        if "norm" in n and n.endswith("weight"):
+            p.data.add_(torch.randn_like(p) * 0.1)
+    sd = _round_fp16_(vit)
+    frames = torch.randn(3, 3, 56, 56, generator=torch.Generator().manual_seed(1234))
+    out = vit(frames)
+    x0 = vit.patch_embed(frames)
+    _save("vit_small.npz", frames=frames.numpy(), out=out.numpy(), patch_embed=x0.numpy(), depth=2, heads=2,
+          **_sd_arrays("w.", sd))
+
+
+@torch.no_grad()
+def golden_qformer(ref, text):
+    torch.manual_seed(1)
+    qf, qtok = ref_shim.build_qformer(ref, hidden=128, heads=2, inter=256, layers=3, enc_width=176, n_query=8,
+                                      vocab=97, max_pos=64, text=text)
+    for n, p in qf.named_parameters():
+        if n.endswith("bias"):
+            p.data.normal_(0, 0.05)
+        elif p.dim() >= 2:
+            p.data.normal_(0, 0.08)   # larger than BERT's 0.02 so attention is not near-uniform
+    sd = _round_fp16_(qf.bert)
+    qtok.data.copy_(qtok.data.half().float())
+    g = torch.Generator().manual_seed(1236)
+    img = torch.randn(5, 17, 176, generator=g)
+    kw = {}
+    extra = {}
+    if text:
+        ids = torch.randint(3, 97, (5, 6), generator=g)
+        tmask = torch.ones(5, 6, dtype=torch.long)
+        tmask[1, 4:] = 0
+        tmask[3, 2:] = 0
+        att = torch.cat([torch.ones(5, 8, dtype=torch.long), tmask], dim=1)
+        out = qf.bert(ids, attention_mask=att, query_embeds=qtok.expand(5, -1, -1), encoder_hidden_states=img,
+                      encoder_attention_mask=torch.ones(5, 17, dtype=torch.long), return_dict=True)
+        extra = dict(text_ids=ids.numpy(), text_mask=tmask.numpy())
+    else:
+        out = qf.bert(query_embeds=qtok.expand(5, -1, -1), encoder_hidden_states=img,
+                      encoder_attention_mask=torch.ones(5, 17, dtype=torch.long), return_dict=True)
+    sd = {k: v for k, v in sd.items() if k != "embeddings.position_ids"}
+    _save("qformer_text_small.npz" if text else "qformer_small.npz", image_embeds=img.numpy(),
+          query_tokens=qtok.data.numpy(), out=out.last_hidden_state.numpy(), layers=3, heads=2, **extra,
+          **_sd_arrays("w.", sd))
+
+
+@torch.no_grad()
+def golden_llama(ref):
+    torch.manual_seed(2)
+    st = ref.st_llm
+    cfg = st.StllmConfig(hidden_size=256, num_attention_heads=2, num_key_value_heads=2, intermediate_size=512,
+                         num_hidden_layers=2, vocab_size=128, max_position_embeddings=2048, rms_norm_eps=1e-6,
+                         attn_implementation="eager")
+    llm = st.STLLMForCausalLM(cfg).eval()
+    for n, p in llm.named_parameters():
+        if p.dim() >= 2:
+            p.data.normal_(0, 0.06)
+        else:
+            p.data.add_(torch.randn_like(p) * 0.1)
+    sd = _round_fp16_(llm)
+    g = torch.Generator().manual_seed(1235)
+    emb = torch.randn(3, 21, 256, generator=g)
+    att = torch.ones(3, 21, dtype=torch.long)
+    att[1, 15:] = 0   # right padding as produced by prompt_wrap / concat_emb_input_output
+    att[2, 9:] = 0
+    out = llm(samples=None, inputs_embeds=emb, attention_mask=att, output_hidden_states=True, return_dict=True,
+              use_cache=False)
+    _save("llama_small.npz", inputs_embeds=emb.numpy(), attention_mask=att.numpy(), logits=out.logits.numpy(),
+          last_hidden=out.hidden_states[-1].numpy(), layer1_hidden=out.hidden_states[1].numpy(), layers=2, heads=2,
+          **_sd_arrays("w.", sd))
+
+
+def golden_mask(ref):
+    """RandomMaskingGenerator (utils.py:4-16) + the rate draw (st_llm.py:484-485) under fixed numpy seeds"""
+    out = {}
+    for seed, (L, B) in {0: (8, 2), 1237: (512, 8), 7: (128, 3)}.items():
+        np.random.seed(seed)
+        rate = np.random.normal(0.5, 0.1)
+        mask_rate = float(np.clip(rate, 0.1, 0.7))
+        m = ref.utils.RandomMaskingGenerator(L, mask_rate, B, "cpu")
+        out[f"seed{seed}_rate"] = np.float64(mask_rate)
+        out[f"seed{seed}_mask"] = m.numpy()
+        np.random.seed(seed)
+        m2 = ref.utils.RandomMaskingGenerator(L, 0.5, B, "cpu")
+        out[f"seed{seed}_mask_fixed_half"] = m2.numpy()
+    # get_residual_index (st_llm.py:434-445) through the reference's own method
+    obj = type("O", (), {"register_buffer": lambda self, n, v: None})()
+    for (R, T) in [(4, 64), (16, 64), (4, 16), (2, 4), (3, 10), (5, 7)]:
+        idx = ref.st_llm.STLLMModel.get_residual_index(obj, R, T, "cpu")
+        out[f"residual_R{R}_T{T}"] = idx.numpy()
+    _save("mask_kat.npz", **out)
+
+
+def flow_weights(seed=0):
+    """Deterministic weights for the end-to-end flow fixture (too large to store: 4096-wide LLM layer).
+    Regenerated from the seed by the tests; only outputs are stored."""
+    g = torch.Generator().manual_seed(seed)
+
+    def rn(*shape, std=0.02):
+        return (torch.randn(*shape, generator=g) * std).half().float()
+    return g, rn
+
+
+@torch.no_grad()
+def golden_flow(ref):
+    """Whole training-branch hot path a1-a22 through the reference's own methods:
+    STLLMForCausalLM.forward(samples) -> STLLMLlamaModel.forward -> STLLMModel.forward (encode_img, residual
+    aggregation, dynamic mask, prompt_wrap, concat, targets) -> LLM masked+unmasked passes -> MVM + CE loss."""
+    from tests.flow_fixture import build_reference_flow, flow_samples
+    llm, M = build_reference_flow(ref)
+    samples = flow_samples()
+    np.random.seed(1237)
+    out = llm(samples=samples)
+    _save("stllm_flow.npz", loss=out.loss.numpy(), logits_head=out.logits[:, :, :64].numpy(),
+          logits_shape=np.array(out.logits.shape), mask=M.mask.numpy(), img_len=M.img_len,
+          mask_img_len=M.mask_img_len, residual_index=M.residual_index.numpy())
+
+
+if __name__ == "__main__":
+    ref = ref_shim.load_reference()
+    which = sys.argv[1:] or ["vit", "qformer", "qformer_text", "llama", "mask", "flow"]
+    if "vit" in which:
+        golden_vit(ref)
+    if "qformer" in which:
+        golden_qformer(ref, text=False)
+    if "qformer_text" in which:
+        golden_qformer(ref, text=True)
+    if "llama" in which:
+        golden_llama(ref)
+    if "mask" in which:
+        golden_mask(ref)
+    if "flow" in which:
+        golden_flow(ref)
