@@ -79,10 +79,12 @@ int stllm_vit_assemble_f16(const void* patches, long long ldp, const void* cls, 
 int stllm_rope_f16(void* x, long long ldx, const int* pos, const float* cos_t, const float* sin_t, int rows,
                    int nheads, int head_dim, int max_pos, void* stream);
 
-/* dst[i,:] = src[idx[i],:] (int64 idx).  st_llm.py:491 (img_embeds[~mask]) and nn.Embedding lookups.
+/* dst[i,:] = src[idx[i],:] (+ addend[i % add_period,:] when addend != NULL), int64 idx.
+ * st_llm.py:491 (img_embeds[~mask]), nn.Embedding lookups, Qformer.py:95-99 (word + position embeddings).
  * err_flag (optional, device int): set to 1 on an out-of-range index. */
 int stllm_gather_rows_f16(const void* src, long long lds, long long src_rows, const long long* idx, void* dst,
-                          long long ldd, int n_rows, int cols, int* err_flag, void* stream);
+                          long long ldd, int n_rows, int cols, const void* addend, int add_period, int* err_flag,
+                          void* stream);
 
 /* y[b,:] = mean_t x[b,t,:] (fp32 accumulate).  st_llm.py:466,470. */
 int stllm_mean_frames_f16(const void* x, void* y, int B, int T, long long inner, void* stream);

@@ -25,7 +25,8 @@ SIGNATURES = {
     "stllm_im2col_patch": [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p],
     "stllm_vit_assemble_f16": [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p],
     "stllm_rope_f16": [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
-    "stllm_gather_rows_f16": [c_void_p, c_ll, c_ll, c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p],
+    "stllm_gather_rows_f16": [c_void_p, c_ll, c_ll, c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p, c_int, c_void_p,
+                              c_void_p],
     "stllm_mean_frames_f16": [c_void_p, c_void_p, c_int, c_int, c_ll, c_void_p],
     "stllm_residual_merge_f16": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_ll, c_void_p],
     "stllm_cosine_loss_f16": [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p],

@@ -85,7 +85,7 @@ __global__ void rope_kernel(__half* __restrict__ x, long long ldx, const int* __
 
 __global__ void gather_rows_kernel(const __half* __restrict__ src, long long lds, const long long* __restrict__ idx,
                                    __half* __restrict__ dst, long long ldd, int n_rows, int cols, long long src_rows,
-                                   int* __restrict__ err) {
+                                   const __half* __restrict__ addend, int add_period, int* __restrict__ err) {
   const int cv = cols >> 3;
   const long long total = (long long)n_rows * cv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -97,7 +97,15 @@ __global__ void gather_rows_kernel(const __half* __restrict__ src, long long lds
       if (err != nullptr) *err = 1;
       continue;
     }
-    reinterpret_cast<uint4*>(dst + r * ldd)[c] = __ldg(reinterpret_cast<const uint4*>(src + s * lds) + c);
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(src + s * lds) + c);
+    if (addend != nullptr) {  // dst[r] = src[idx[r]] + addend[r % add_period]   (BertEmbeddings word + position)
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(addend + (r % add_period) * (long long)cols) + c);
+      __half2* vh = reinterpret_cast<__half2*>(&v);
+      const __half2* ah = reinterpret_cast<const __half2*>(&a);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) vh[j] = __hadd2(vh[j], ah[j]);
+    }
+    reinterpret_cast<uint4*>(dst + r * ldd)[c] = v;
   }
 }
 
@@ -251,12 +259,14 @@ extern "C" int stllm_rope_f16(void* x, long long ldx, const int* pos, const floa
 }
 
 extern "C" int stllm_gather_rows_f16(const void* src, long long lds, long long src_rows, const long long* idx, void* dst,
-                                     long long ldd, int n_rows, int cols, int* err_flag, void* stream) {
+                                     long long ldd, int n_rows, int cols, const void* addend, int add_period,
+                                     int* err_flag, void* stream) {
   STLLM_CHECK_ARG(src && idx && dst && n_rows > 0 && cols > 0 && cols % 8 == 0 && lds % 8 == 0 && ldd % 8 == 0);
-  STLLM_CHECK_ARG((((uintptr_t)src | (uintptr_t)dst) & 15) == 0);
+  STLLM_CHECK_ARG((((uintptr_t)src | (uintptr_t)dst | (uintptr_t)addend) & 15) == 0);
+  STLLM_CHECK_ARG(addend == nullptr || add_period > 0);
   const long long total = (long long)n_rows * (cols / 8);
-  gather_rows_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)src, lds, idx, (__half*)dst,
-                                                                             ldd, n_rows, cols, src_rows, err_flag);
+  gather_rows_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __half*)src, lds, idx, (__half*)dst, ldd, n_rows, cols, src_rows, (const __half*)addend, add_period, err_flag);
   STLLM_CHECK_CUDA(cudaGetLastError());
   return STLLM_OK;
 }

@@ -170,8 +170,8 @@ def rope_(x2d, pos, cos_t, sin_t, nheads, head_dim):
     return x2d
 
 
-def gather_rows(src, idx, out=None):
-    """out[i, :] = src[idx[i], :]   src [R, C] fp16, idx int64 [n]"""
+def gather_rows(src, idx, out=None, addend=None):
+    """out[i, :] = src[idx[i], :] (+ addend[i % addend.shape[0]])   src [R, C] fp16, idx int64 [n]"""
     global launch_count
     _need_cuda(src, idx, out)
     assert src.dim() == 2 and src.stride(1) == 1 and src.dtype == torch.float16
@@ -181,8 +181,12 @@ def gather_rows(src, idx, out=None):
         out = torch.empty((n, src.shape[1]), dtype=torch.float16, device=src.device)
     if n == 0:
         return out
+    if addend is not None:
+        assert addend.dtype == torch.float16 and addend.is_contiguous() and addend.shape[1] == src.shape[1]
     rc = _lib.load().stllm_gather_rows_f16(_ptr(src), src.stride(0), src.shape[0], _ptr(idx), _ptr(out),
-                                           out.stride(0), n, src.shape[1], ctypes.c_void_p(0), _stream())
+                                           out.stride(0), n, src.shape[1], _ptr(addend),
+                                           addend.shape[0] if addend is not None else 0, ctypes.c_void_p(0),
+                                           _stream())
     _lib.check(rc, "stllm_gather_rows_f16")
     launch_count += 1
     return out

@@ -1,0 +1,543 @@
+"""ST-LLM model API on the sm_100a kernels: STLLMModel / STLLMLlamaModel / STLLMForCausalLM.
+
+Drop-in for the reference's stllm/models/st_llm.py: same class names, attribute graph
+(`model.model.stllm_model.{encode_img, video_input, residual_size, up_proj, down_proj, non_linear_func,
+embed_tokens, llama_tokenizer, qformer_text_input, mask, img_len, mask_img_len, mvm_decoder}`, `model.get_model()`),
+state-dict keys (`model.stllm_model.visual_encoder.*`, `.ln_vision.*`, `.Qformer.bert.*`, `.query_tokens`,
+`.llama_proj.*`, `.up_proj/.down_proj`, `.mvm_decoder.*`, `model.layers.*`, `lm_head.*`), registry name
+("st_llm_hf") and error behaviour (asserts of st_llm.py:336, eva_vit.py:201).  nn.Modules hold parameters only;
+all arithmetic of the path runs in libstllm_b200.so through stllm_b200.ops (no torch math, no CPU fallback).
+Host-side integer logic that must be bit-exact with the reference (dynamic mask RNG order, residual frame index)
+stays in numpy exactly as the reference does it (st_llm.py:434-445,482-493; utils.py:4-16).
+"""
+import math
+import os
+import re
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .eva_vit import create_eva_vit_g, VisionTransformer
+from .llama import (BaseModelOutputWithPast, CausalLMOutputWithPast, KVCache, LlamaConfig, LlamaModel)
+from .qformer import BertConfig, BertLMHeadModel
+from .registry import registry
+
+
+class StllmConfig(LlamaConfig):
+    model_type = "st_llm_hf"
+
+
+def RandomMaskingGenerator(num_patches, mask_ratio, batch, device="cuda"):
+    """utils.py:4-16 -- identical consumption of numpy's global RNG (one shuffle per row); bool [batch, L]"""
+    num_mask = int(mask_ratio * num_patches)
+    mask_list = []
+    for _ in range(batch):
+        mask = np.hstack([np.zeros(num_patches - num_mask), np.ones(num_mask)])
+        np.random.shuffle(mask)
+        mask_list.append(mask)
+    return torch.from_numpy(np.array(mask_list)).to(torch.bool).to(device)
+
+
+class LayerNorm(nn.LayerNorm):
+    """blip2.py:103-109 (`ln_vision`): fp32 statistics, output cast back to the input dtype"""
+
+    @torch.no_grad()
+    def forward(self, x):
+        return ops.layernorm(x if x.dtype == torch.float16 else x.half(), self.weight.float(), self.bias.float(),
+                             self.eps)
+
+
+class Linear_Decoder(nn.Module):
+    """st_llm.py:35-43"""
+
+    def __init__(self, output_dim=4096, embed_dim=4096):
+        super().__init__()
+        self.head = nn.Linear(embed_dim, output_dim)
+        self.norm = nn.LayerNorm(output_dim)
+
+    @torch.no_grad()
+    def forward(self, x):
+        y = ops.gemm(x, self.head.weight.half(), bias=self.head.bias.half())
+        return ops.layernorm(y, self.norm.weight.float(), self.norm.bias.float(), self.norm.eps)
+
+
+def _linear(mod, x, epilogue=ops.EPI_NONE):
+    w = mod.weight if mod.weight.dtype == torch.float16 else mod.weight.half()
+    b = None if mod.bias is None else (mod.bias if mod.bias.dtype == torch.float16 else mod.bias.half())
+    return ops.gemm(x, w, bias=b, epilogue=epilogue)
+
+
+class STLLMModel(nn.Module):
+    """st_llm.py:205-606 (Blip2Base subclass in the reference)"""
+
+    def __init__(self, vit_model="eva_clip_g", q_former_model=None, img_size=224, pre_encoding=False, use_mask=False,
+                 mvm_decode=False, video_input=None, residual_size=4, qformer_text_input=False, drop_path_rate=0,
+                 use_grad_checkpoint=False, vit_precision="fp16", freeze_vit=True, has_qformer=True,
+                 freeze_qformer=True, num_query_token=32, llama_model="", max_txt_len=32, end_sym="\n",
+                 # offline / test hooks (the reference downloads these):
+                 tokenizer=None, llama_tokenizer=None, vit_depth=39, qformer_config=None, vit_checkpoint=None,
+                 llama_hidden=4096):
+        super().__init__()
+        assert vit_model == "eva_clip_g", "vit model must be eva_clip_g (eva_btadapter_g is outside this build's scope)"
+        if not has_qformer:
+            raise NotImplementedError("has_qformer=False is not used by any shipped config (SURVEY a15')")
+        self.tokenizer = tokenizer
+        self.pre_encoding = pre_encoding
+        self.video_input = video_input
+        self.use_mask = use_mask
+        self.mvm_decode = mvm_decode
+        self.qformer_text_input = qformer_text_input
+        self.residual_size = residual_size
+        D = llama_hidden
+        if self.video_input == "residual":
+            self.down_proj = nn.Linear(D, 1024)
+            self.non_linear_func = nn.ReLU()
+            self.up_proj = nn.Linear(1024, D)
+            nn.init.kaiming_uniform_(self.down_proj.weight, a=math.sqrt(5))
+            nn.init.zeros_(self.up_proj.weight)
+            nn.init.zeros_(self.down_proj.bias)
+            nn.init.zeros_(self.up_proj.bias)
+        if self.mvm_decode:
+            self.mvm_decoder = Linear_Decoder(D, D)
+        self.vit_model = vit_model
+        self.visual_encoder = create_eva_vit_g(img_size, drop_path_rate, use_grad_checkpoint, vit_precision,
+                                               checkpoint_path=vit_checkpoint, depth=vit_depth)
+        self.ln_vision = LayerNorm(self.visual_encoder.num_features)
+        self.has_qformer = has_qformer
+        qcfg = qformer_config or BertConfig()
+        qcfg.encoder_width = self.visual_encoder.num_features
+        qcfg.query_length = num_query_token
+        self.Qformer = BertLMHeadModel(qcfg)
+        self.query_tokens = nn.Parameter(torch.zeros(1, num_query_token, qcfg.hidden_size))
+        self.query_tokens.data.normal_(mean=0.0, std=qcfg.initializer_range)
+        if not qformer_text_input:                                   # st_llm.py:277-283
+            self.Qformer.bert.embeddings.word_embeddings = None
+            self.Qformer.bert.embeddings.position_embeddings = None
+            for layer in self.Qformer.bert.encoder.layer:
+                layer.output = None
+                layer.intermediate = None
+        elif tokenizer is not None:
+            self.Qformer.resize_token_embeddings(len(tokenizer))    # st_llm.py:285
+        self.Qformer.cls = None
+        self.llama_tokenizer = llama_tokenizer
+        self.llama_proj = nn.Linear(qcfg.hidden_size, D)
+        self.max_txt_len = max_txt_len
+        self.end_sym = end_sym
+        self.embed_tokens = None  # set by STLLMLlamaModel.initialize_vision_modules (st_llm.py:54)
+        for p in self.parameters():
+            p.requires_grad = False
+
+    # keep embed_tokens out of this module's parameters/state_dict (it belongs to the LLM, as in the reference
+    # where the attribute is assigned after construction and shares the LLM's tensor)
+    def __setattr__(self, name, value):
+        if name == "embed_tokens":
+            object.__setattr__(self, name, value)
+        else:
+            super().__setattr__(name, value)
+
+    @property
+    def device(self):
+        return self.llama_proj.weight.device
+
+    def _embed(self, ids):
+        w = self.embed_tokens.weight
+        w = w if w.dtype == torch.float16 else w.half()
+        return ops.gather_rows(w, ids.reshape(-1).to(w.device)).view(tuple(ids.shape) + (w.shape[1],))
+
+    @torch.no_grad()
+    def encode_img(self, image, text=None):
+        """st_llm.py:321-377"""
+        device = image.device
+        T = image.shape[1]
+        infer = True if len(image.shape) == 4 else False
+        use_image = True if T == 1 or (len(image.shape) == 4) else False
+        if (not use_image or len(image.shape) == 5) and (self.vit_model == "eva_clip_g"):
+            image = image.reshape((-1,) + tuple(image.shape[2:]))   # 'B T C H W -> (B T) C H W'
+        image_embeds = self.visual_encoder(image)
+        image_embeds = self.ln_vision(image_embeds)
+        query_tokens = self.query_tokens.expand(image_embeds.shape[0], -1, -1)
+        if self.qformer_text_input:
+            assert text
+            if isinstance(text, str):
+                text = [text] * query_tokens.size(0)
+            elif len(text) != query_tokens.size(0):
+                text_ = []
+                for t in text:
+                    text_ += [t] * T
+                text = text_
+            text_Qformer = self.tokenizer(text, padding="longest", truncation=True, max_length=self.max_txt_len,
+                                          return_tensors="pt").to(device)
+            query_atts = torch.ones(query_tokens.size()[:-1], dtype=torch.long, device=device)
+            Qformer_atts = torch.cat([query_atts, text_Qformer.attention_mask], dim=1)
+            query_output = self.Qformer.bert(text_Qformer.input_ids, attention_mask=Qformer_atts,
+                                             query_embeds=query_tokens, encoder_hidden_states=image_embeds,
+                                             return_dict=True)
+        else:
+            query_output = self.Qformer.bert(query_embeds=query_tokens, encoder_hidden_states=image_embeds,
+                                             return_dict=True)
+        Q = query_tokens.size(1)
+        last = query_output.last_hidden_state
+        q_hidden = last if last.shape[1] == Q else last[:, :Q].contiguous()
+        inputs_llama = _linear(self.llama_proj, q_hidden)
+        if not infer:
+            inputs_llama = inputs_llama.view(-1, T, Q, inputs_llama.shape[-1])
+        atts_llama = torch.ones(inputs_llama.size()[:-1], dtype=torch.long, device=device)
+        return inputs_llama, atts_llama, use_image
+
+    # the north_star's name for the same function (VideoChat2 naming)
+    encode_videoQformer_visual = encode_img
+
+    @torch.no_grad()
+    def prompt_wrap(self, img_embeds, atts_img, prompts):
+        """st_llm.py:379-407"""
+        if prompts:
+            emb_lists = []
+            if isinstance(prompts, str):
+                prompts = [prompts] * len(img_embeds)
+            dev = img_embeds.device
+            for each_img_embed, each_prompt in zip(img_embeds, prompts):
+                p_before, p_after = each_prompt.split("<ImageHere>")
+                p_before_tokens = self.llama_tokenizer(p_before, return_tensors="pt", add_special_tokens=False).to(dev)
+                p_after_tokens = self.llama_tokenizer(p_after, return_tensors="pt",
+                                                      add_special_tokens=self.qformer_text_input).to(dev)
+                p_before_embed = self._embed(p_before_tokens.input_ids) \
+                    if min(p_before_tokens.input_ids.shape) != 0 else None
+                p_after_embed = self._embed(p_after_tokens.input_ids)
+                if len(each_img_embed.size()) == 2:
+                    each_img_embed = each_img_embed[None]
+                wrapped_emb = torch.cat([p_before_embed, each_img_embed, p_after_embed], dim=1) \
+                    if p_before_embed is not None else torch.cat([each_img_embed, p_after_embed], dim=1)
+                emb_lists.append(wrapped_emb)
+            emb_lens = [emb.shape[1] for emb in emb_lists]
+            pad_emb = self._embed(torch.tensor(self.llama_tokenizer.pad_token_id, device=dev))
+            wrapped_embs = pad_emb.expand(len(emb_lens), max(emb_lens), -1).clone()
+            wrapped_atts = torch.zeros([len(emb_lens), max(emb_lens)], dtype=torch.int, device=dev)
+            for i, emb in enumerate(emb_lists):
+                wrapped_embs[i, :emb_lens[i]] = emb
+                wrapped_atts[i, :emb_lens[i]] = 1
+            return wrapped_embs, wrapped_atts
+        return img_embeds, atts_img
+
+    def concat_emb_input_output(self, input_embs, input_atts, output_embs, output_atts):
+        """st_llm.py:409-432"""
+        input_lens, cat_embs, cat_atts = [], [], []
+        lens_host = input_atts.sum(dim=1).tolist()
+        for i in range(input_embs.size(0)):
+            input_len = int(lens_host[i])
+            input_lens.append(input_len)
+            cat_embs.append(torch.cat([input_embs[i][:input_len], output_embs[i], input_embs[i][input_len:]]))
+            cat_atts.append(torch.cat([input_atts[i][:input_len], output_atts[i].to(input_atts.dtype),
+                                       input_atts[i][input_len:]]))
+        return torch.stack(cat_embs), torch.stack(cat_atts), input_lens
+
+    def get_residual_index(self, sample_segments, total_segments, devices):
+        """st_llm.py:434-445"""
+        if hasattr(self, "residual_index"):
+            return self.residual_index
+        seg_size = float(total_segments) / sample_segments
+        frame_indices = np.array([int((seg_size / 2) + np.round(seg_size * idx)) for idx in range(sample_segments)])
+        frame_indices = torch.from_numpy(frame_indices).to(devices)
+        self.register_buffer("residual_index", frame_indices)
+        return frame_indices
+
+    @torch.no_grad()
+    def aggregate_video(self, img_embeds):
+        """st_llm.py:463-478 (inference twin conversation.py:281-293): [B,T,Q,D] -> [B,1,L,D]"""
+        T = img_embeds.size(1)
+        if self.video_input == "all":
+            return img_embeds.reshape(img_embeds.size(0), 1, -1, img_embeds.size(-1)).contiguous()
+        if self.video_input == "mean":
+            return ops.mean_frames(img_embeds.contiguous()).unsqueeze(1)
+        if self.video_input == "residual":
+            residual_index = self.get_residual_index(self.residual_size, T, img_embeds.device)
+            g = ops.mean_frames(img_embeds.contiguous())                      # [B,Q,D]
+            g = _linear(self.up_proj, _linear(self.down_proj, g, ops.EPI_RELU))
+            out = ops.residual_merge(img_embeds.contiguous(), g, residual_index)   # [B,R,Q,D]
+            return out.view(img_embeds.size(0), 1, -1, img_embeds.size(-1))
+        return img_embeds
+
+    @torch.no_grad()
+    def forward(self, samples):
+        """st_llm.py:447-546"""
+        image = samples["image"]
+        instruction = samples["instruction_input"] if "instruction_input" in samples else None
+        use_image = False
+        if self.pre_encoding:
+            img_embeds = _linear(self.llama_proj, image.half())
+            atts_img = torch.ones(img_embeds.size()[:-1], dtype=torch.long, device=image.device)
+        else:
+            if self.qformer_text_input:
+                qformer_text_input = [it.split("Human: ")[1].split(" ###")[0] for it in instruction]
+            else:
+                qformer_text_input = None
+            img_embeds, atts_img, use_image = self.encode_img(image, qformer_text_input)
+        if not use_image:
+            img_embeds = self.aggregate_video(img_embeds)
+        B, _, L, D = img_embeds.size()
+        dev = img_embeds.device
+        unmask_img_embeds = None
+        if not use_image and self.use_mask:
+            self.img_len = L
+            rate = np.random.normal(0.5, 0.1)
+            mask_rate = float(np.clip(rate, 0.1, 0.7)) if getattr(self, "fixed_mask_rate", None) is None \
+                else float(self.fixed_mask_rate)
+            mask_cpu = RandomMaskingGenerator(L, mask_rate, B, "cpu").unsqueeze(1)
+            self.mask = mask_cpu.to(dev)
+            unmask_img_embeds = img_embeds
+            unmask_atts_img = torch.ones(unmask_img_embeds.size()[:-1], dtype=torch.long, device=dev)
+            keep = torch.nonzero(~mask_cpu.reshape(-1)).reshape(-1).to(dev)     # row-major order == img_embeds[~mask]
+            img_embeds = ops.gather_rows(img_embeds.reshape(B * L, D), keep).view(B, 1, -1, D)
+            atts_img = torch.ones(img_embeds.size()[:-1], dtype=torch.long, device=dev)
+            self.mask_img_len = img_embeds.size(2)
+
+        img_embeds, atts_img = self.prompt_wrap(img_embeds, atts_img, instruction)
+        self.llama_tokenizer.padding_side = "right"
+        text = [t + self.llama_tokenizer.eos_token for t in samples["answer"]] if self.qformer_text_input \
+            else [t + self.end_sym for t in samples["answer"]]
+        to_regress_tokens = self.llama_tokenizer(text, return_tensors="pt", padding="longest", truncation=True,
+                                                 max_length=self.max_txt_len, add_special_tokens=False).to(dev)
+        to_regress_embeds = self._embed(to_regress_tokens.input_ids)
+        inputs_embeds, attention_mask, input_lens = self.concat_emb_input_output(
+            img_embeds, atts_img, to_regress_embeds, to_regress_tokens.attention_mask)
+        if unmask_img_embeds is not None:
+            unmask_img_embeds, unmask_atts_img = self.prompt_wrap(unmask_img_embeds, unmask_atts_img, instruction)
+            unmask_inputs_embeds, unmask_attention_mask, _ = self.concat_emb_input_output(
+                unmask_img_embeds, unmask_atts_img, to_regress_embeds, to_regress_tokens.attention_mask)
+        if not self.qformer_text_input:
+            batch_size = img_embeds.shape[0]
+            bos = torch.ones([batch_size, 1], dtype=to_regress_tokens.input_ids.dtype,
+                             device=dev) * self.llama_tokenizer.bos_token_id
+            bos_embeds = self._embed(bos)
+            atts_bos = atts_img[:, :1]
+            inputs_embeds = torch.cat([bos_embeds, inputs_embeds], dim=1)
+            attention_mask = torch.cat([atts_bos, attention_mask], dim=1)
+            if unmask_img_embeds is not None:
+                unmask_inputs_embeds = torch.cat([bos_embeds, unmask_inputs_embeds], dim=1)
+                unmask_attention_mask = torch.cat([atts_bos, unmask_attention_mask], dim=1)
+        part_targets = to_regress_tokens.input_ids.masked_fill(
+            to_regress_tokens.input_ids == self.llama_tokenizer.pad_token_id, -100)
+        targets = torch.ones([inputs_embeds.shape[0], inputs_embeds.shape[1]], dtype=torch.long, device=dev).fill_(-100)
+        offset = 0 if self.qformer_text_input else 1
+        for i, target in enumerate(part_targets):
+            targets[i, input_lens[i] + offset:input_lens[i] + len(target) + offset] = target
+        if unmask_img_embeds is None:
+            unmask_inputs_embeds, unmask_attention_mask = None, None
+        return inputs_embeds, attention_mask, unmask_inputs_embeds, unmask_attention_mask, targets
+
+    @classmethod
+    def from_config(cls, cfg, **overrides):
+        """st_llm.py:549-606: same keys / defaults"""
+        kw = dict(
+            vit_model=cfg.get("vit_model", "eva_clip_g"),
+            q_former_model=cfg.get("q_former_model", None),
+            img_size=cfg.get("image_size", 224),
+            num_query_token=cfg.get("num_query_token", 32),
+            llama_model=cfg.get("llama_model", ""),
+            drop_path_rate=cfg.get("drop_path_rate", 0),
+            use_grad_checkpoint=cfg.get("use_grad_checkpoint", False),
+            vit_precision=cfg.get("vit_precision", "fp16"),
+            freeze_vit=cfg.get("freeze_vit", True),
+            has_qformer=cfg.get("has_qformer", True),
+            freeze_qformer=cfg.get("freeze_qformer", True),
+            max_txt_len=cfg.get("max_txt_len", 32),
+            end_sym=cfg.get("end_sym", "\n"),
+            pre_encoding=cfg.get("pre_encoding", False),
+            use_mask=cfg.get("use_mask", False),
+            mvm_decode=cfg.get("mvm_decode", False),
+            video_input=cfg.get("video_input", None),
+            residual_size=cfg.get("residual_size", 4),
+            qformer_text_input=cfg.get("qformer_text_input", False),
+        )
+        for k in ("tokenizer", "llama_tokenizer", "vit_depth", "qformer_config", "vit_checkpoint"):
+            if cfg.get(k, None) is not None:
+                kw[k] = cfg.get(k)
+        kw.update(overrides)
+        return cls(**kw)
+
+
+class STLLMLlamaModel(LlamaModel):
+    """st_llm.py:45-92"""
+    config_class = StllmConfig
+
+    def initialize_vision_modules(self, cfg, **overrides):
+        self.stllm_model = STLLMModel.from_config(cfg, llama_hidden=self.config.hidden_size, **overrides)
+        if cfg.get("qformer_text_input", False) and self.stllm_model.llama_tokenizer is not None:
+            self.resize_token_embeddings(len(self.stllm_model.llama_tokenizer))
+        self.stllm_model.embed_tokens = self.embed_tokens
+
+    def resize_token_embeddings(self, n):
+        old = self.embed_tokens
+        if n == old.num_embeddings:
+            return old
+        new = nn.Embedding(n, old.embedding_dim).to(device=old.weight.device, dtype=old.weight.dtype)
+        new.weight.data.normal_(mean=0.0, std=self.config.initializer_range)
+        m = min(n, old.num_embeddings)
+        new.weight.data[:m] = old.weight.data[:m]
+        self.embed_tokens = new
+        self.config.vocab_size = n
+        self.vocab_size = n
+        if hasattr(self, "stllm_model"):
+            self.stllm_model.embed_tokens = new
+        return new
+
+    @torch.no_grad()
+    def forward(self, samples=None, inputs_embeds=None, **kwargs):
+        if samples is None:
+            return super().forward(inputs_embeds=inputs_embeds, **kwargs)
+        inputs_embeds, attention_mask, unmask_inputs_embeds, unmask_attention_mask, labels = self.stllm_model(samples)
+        output_hidden_states = not (unmask_inputs_embeds is None)
+        outputs = super().forward(input_ids=None, attention_mask=attention_mask, inputs_embeds=inputs_embeds,
+                                  use_cache=False, output_hidden_states=output_hidden_states, return_dict=True)
+        if unmask_inputs_embeds is None:
+            return outputs, None, labels
+        img_start = 0 if self.stllm_model.qformer_text_input else 8                   # st_llm.py:71
+        mask_output = outputs.hidden_states[-1]
+        B, _, D = mask_output.size()
+        mask_img_output = mask_output[:, img_start:img_start + self.stllm_model.mask_img_len].contiguous()
+        if hasattr(self.stllm_model, "mvm_decoder"):
+            mask_img_output = self.stllm_model.mvm_decoder(mask_img_output)
+        unmask_outputs = super().forward(inputs_embeds=unmask_inputs_embeds, attention_mask=unmask_attention_mask,
+                                         return_dict=True, use_cache=False, output_hidden_states=True)
+        unmask_output = unmask_outputs.hidden_states[-1]
+        S_u = unmask_output.shape[1]
+        # unmask_output[:, img_start:img_start+img_len][~mask]  as one row gather (bit-exact index path)
+        keep = torch.nonzero(~self.stllm_model.mask.squeeze(1).reshape(-1)).reshape(-1)
+        L = self.stllm_model.img_len
+        rows = (keep // L) * S_u + img_start + (keep % L)
+        unmask_img_output = ops.gather_rows(unmask_output.reshape(B * S_u, D), rows)
+        loss_mvm = ops.cosine_loss(mask_img_output.reshape(-1, D), unmask_img_output)  # st_llm.py:89-91
+        return outputs, loss_mvm, labels
+
+
+class STLLMForCausalLM(nn.Module):
+    """st_llm.py:94-203"""
+    config_class = StllmConfig
+    PRETRAINED_MODEL_CONFIG_DICT = {
+        "instructblip_vicuna0": "configs/models/instructblip_vicuna0.yaml",
+        "instructblip_vicuna0_btadapter": "configs/models/instructblip_vicuna0_btadapter.yaml",
+        "minigpt4_vicuna0": "configs/models/minigpt4_vicuna0.yaml",
+        "minigpt4_vicuna0_btadapter": "configs/models/minigpt4_vicuna0_btadapter.yaml",
+    }
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = config
+        self.model = STLLMLlamaModel(config)
+        self.vocab_size = config.vocab_size
+        self.lm_head = nn.Linear(config.hidden_size, config.vocab_size, bias=False)
+        self.lm_head.weight.data.normal_(mean=0.0, std=config.initializer_range)
+
+    def get_model(self):
+        return self.model
+
+    @property
+    def device(self):
+        return self.lm_head.weight.device
+
+    def _lm_head(self, hidden):
+        w = self.lm_head.weight
+        return ops.gemm(hidden, w if w.dtype == torch.float16 else w.half())
+
+    @torch.no_grad()
+    def forward(self, samples=None, inputs_embeds=None, input_ids=None, attention_mask=None, labels=None,
+                past_key_values=None, use_cache=False, output_hidden_states=False, return_dict=True,
+                cache_max_len=None, **kwargs):
+        if samples is None:
+            # == HF LlamaForCausalLM.forward (used by generate's prefill/decode steps)
+            out = self.model(samples=None, inputs_embeds=inputs_embeds, input_ids=input_ids,
+                             attention_mask=attention_mask, past_key_values=past_key_values, use_cache=use_cache,
+                             output_hidden_states=output_hidden_states, cache_max_len=cache_max_len)
+            logits = self._lm_head(out.last_hidden_state)
+            loss = None
+            if labels is not None:
+                loss = self._ce(logits, labels)
+            return CausalLMOutputWithPast(loss, logits, out.past_key_values, out.hidden_states, None)
+        outputs, loss_pretrain, labels = self.model(samples)
+        hidden_states = outputs[0]
+        logits = self._lm_head(hidden_states)
+        loss = None
+        if labels is not None:
+            loss = self._ce(logits, labels)
+        if loss_pretrain is not None:
+            loss = loss + loss_pretrain
+        return CausalLMOutputWithPast(loss=loss, logits=logits, past_key_values=outputs.past_key_values,
+                                      hidden_states=outputs.hidden_states, attentions=outputs.attentions)
+
+    def _ce(self, logits, labels):
+        """st_llm.py:124-135: logits[..., :-1, :] vs labels[..., 1:], ignore_index -100 -- without copying the logits"""
+        B, S, V = logits.shape
+        shifted = torch.full((B, S), -100, dtype=torch.long, device=logits.device)
+        shifted[:, :-1] = labels[:, 1:]
+        return ops.cross_entropy(logits.view(B * S, V), shifted.view(-1))
+
+    # ---- generation (greedy / beam / sampling) over the kernel forward ------------------------------------
+    @torch.no_grad()
+    def generate(self, inputs_embeds=None, input_ids=None, max_new_tokens=20, stopping_criteria=None, num_beams=1,
+                 do_sample=False, min_length=1, top_p=1.0, repetition_penalty=1.0, length_penalty=1.0,
+                 temperature=1.0, eos_token_id=None, pad_token_id=None, attention_mask=None, **unused):
+        from .generation import generate as _generate
+        return _generate(self, inputs_embeds=inputs_embeds, input_ids=input_ids, max_new_tokens=max_new_tokens,
+                         stopping_criteria=stopping_criteria, num_beams=num_beams, do_sample=do_sample,
+                         min_length=min_length, top_p=top_p, repetition_penalty=repetition_penalty,
+                         length_penalty=length_penalty, temperature=temperature, eos_token_id=eos_token_id,
+                         pad_token_id=pad_token_id, attention_mask=attention_mask)
+
+    # ---- construction -------------------------------------------------------------------------------------
+    @classmethod
+    def get_state_dict(cls, path, prefix="pytorch_model"):
+        """st_llm.py:149-158: merge sharded `pytorch_model-N-of-M.bin`"""
+        pattern = re.compile(rf"{prefix}-(\d+)-of-(\d+).bin")
+        sd = {}
+        for fn in [f for f in os.listdir(path) if pattern.match(f)]:
+            sd.update(torch.load(os.path.join(path, fn), map_location="cpu"))
+        return sd
+
+    @classmethod
+    def from_config(cls, cfg, **overrides):
+        """st_llm.py:160-203.  `llama_model` = HF checkpoint dir (config.json + pytorch_model-*.bin) when available;
+        offline, `llama_config` (dict of LlamaConfig fields) builds a random-init LLM of that architecture."""
+        llama_model = cfg.get("llama_model", "")
+        lcfg = dict(cfg.get("llama_config", None) or {})
+        sd = None
+        if llama_model and os.path.isdir(llama_model):
+            import json
+            with open(os.path.join(llama_model, "config.json")) as f:
+                hf = json.load(f)
+            for k in ("vocab_size", "hidden_size", "intermediate_size", "num_hidden_layers", "num_attention_heads",
+                      "max_position_embeddings", "rms_norm_eps", "pad_token_id", "bos_token_id", "eos_token_id"):
+                if k in hf and hf[k] is not None:
+                    lcfg.setdefault(k, hf[k])
+            sd = cls.get_state_dict(llama_model)
+        if cfg.get("lora_r", 0) > 0:
+            raise NotImplementedError("LoRA training is outside the hot path (SURVEY section 2: peft_model.py out of scope)")
+        model = cls(StllmConfig(**lcfg))
+        if sd:
+            model.load_state_dict(sd, strict=False)
+        model.get_model().initialize_vision_modules(cfg, **overrides)
+        if cfg.get("qformer_text_input", False) and model.get_model().stllm_model.llama_tokenizer is not None:
+            n = len(model.get_model().stllm_model.llama_tokenizer)
+            if n != model.lm_head.out_features:                       # resize_token_embeddings also resizes lm_head in HF
+                old = model.lm_head
+                new = nn.Linear(old.in_features, n, bias=False)
+                new.weight.data.normal_(mean=0.0, std=model.config.initializer_range)
+                new.weight.data[:min(n, old.out_features)] = old.weight.data[:min(n, old.out_features)]
+                model.lm_head = new
+                model.vocab_size = n
+        ckpt_path = cfg.get("ckpt", "")
+        if ckpt_path:
+            ckpt = cls.get_state_dict(ckpt_path)
+            for key in list(ckpt.keys()):                                 # st_llm.py:196-200
+                if "llm_proj" in key:
+                    ckpt[key.replace("llm_proj", "llama_proj")] = ckpt.pop(key)
+            model.load_state_dict(ckpt, strict=False)
+        return model
+
+    @classmethod
+    def default_config_path(cls, model_type):
+        assert model_type in cls.PRETRAINED_MODEL_CONFIG_DICT, "Unknown model type {}".format(model_type)
+        return cls.PRETRAINED_MODEL_CONFIG_DICT[model_type]
+
+
+registry.register_model("st_llm_hf")(STLLMForCausalLM)
