@@ -354,3 +354,39 @@ def assemble_sequence(video_embeds, prompt_embeds, answer_embeds, answer_mask, p
         atts[i, n:n + A] = answer_mask[i]
         targets[i, n:n + A] = part[i]
     return embs, atts, targets
+
+
+# --------------------------------------------------------------------------------------------------
+# whole-path composition on a full state dict with the reference's key names
+# --------------------------------------------------------------------------------------------------
+
+
+def split_state_dict(sd):
+    """STLLMForCausalLM.state_dict() (reference key names, st_llm.py / SURVEY section 5) -> oracle sub-dicts, fp32 CPU"""
+    f = {k: (v.detach().float().cpu() if v.is_floating_point() else v.detach().cpu()) for k, v in sd.items()}
+    pre = "model.stllm_model."
+
+    def sub(prefix):
+        return {k[len(prefix):]: v for k, v in f.items() if k.startswith(prefix)}
+    w = {"vit": sub(pre + "visual_encoder."), "ln_vision": sub(pre + "ln_vision."),
+         "qformer": sub(pre + "Qformer.bert."), "query_tokens": f.get(pre + "query_tokens"),
+         "llama_proj": sub(pre + "llama_proj."), "residual": {k[len(pre):]: v for k, v in f.items()
+                                                               if k.startswith(pre + "down_proj.") or k.startswith(pre + "up_proj.")},
+         "mvm_decoder": sub(pre + "mvm_decoder."),
+         "llama": {k[len("model."):]: v for k, v in f.items()
+                   if k.startswith("model.") and not k.startswith(pre)},
+         "lm_head": f.get("lm_head.weight")}
+    return w
+
+
+def video_prefill(w, frames, prompt_ids, cfg, video_input="all", residual_size=4, collect=None):
+    """The inference path of bench.py / smoke(): frames [B,T,3,H,W] -> encode_img -> aggregate -> [video ‖ prompt]
+    -> LlamaModel -> lm_head logits [B,S,V]   (conversation.py:274-293,322-340 + st_llm.py:118-122)."""
+    emb = encode_img(w, frames, cfg, collect=collect)
+    vid = video_aggregate(emb, video_input, residual_size, w["residual"])
+    prompt = w["llama"]["embed_tokens.weight"][prompt_ids]
+    seq = torch.cat([vid[:, 0], prompt], dim=1)
+    if collect is not None:
+        collect["inputs_embeds"] = seq
+    hid = llama_forward(w["llama"], seq, None, cfg["llama_layers"], cfg["llama_heads"], collect=collect)
+    return F.linear(hid, w["lm_head"])

@@ -152,7 +152,7 @@ class VisionTransformer(nn.Module):
                 w_qkv=f16(a.qkv.weight), qkv_bias=qkv_bias, w_proj=f16(a.proj.weight), b_proj=f16(a.proj.bias),
                 w_fc1=f16(blk.mlp.fc1.weight), b_fc1=f16(blk.mlp.fc1.bias),
                 w_fc2=f16(blk.mlp.fc2.weight), b_fc2=f16(blk.mlp.fc2.bias)))
-        self._packed = dict(w_patch=w_patch, kpad=kpad, b_patch=f16(self.patch_embed.proj.bias),
+        self._packed = dict(w_patch=w_patch, kpad=kpad, kreal=kreal, b_patch=f16(self.patch_embed.proj.bias),
                             cls=f16(self.cls_token).reshape(-1), pos=f16(self.pos_embed).reshape(-1, D), blocks=blocks)
 
     # ---- forward --------------------------------------------------------------------------------
@@ -170,7 +170,7 @@ class VisionTransformer(nn.Module):
         d = D // Hh
         n_tok = self.patch_embed.num_patches + 1
         cols = ops.im2col_patch(x.contiguous(), self.patch_embed.patch_size[0], P["kpad"])
-        patches = ops.gemm(cols, P["w_patch"], bias=P["b_patch"])
+        patches = ops.gemm(cols, P["w_patch"], bias=P["b_patch"], k_real=P["kreal"])
         xt = ops.vit_assemble(patches, P["cls"], P["pos"], B, self.patch_embed.num_patches).view(B * n_tok, D)
         outs = []
         h = torch.empty_like(xt)

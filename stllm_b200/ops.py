@@ -14,6 +14,8 @@ EPI_NONE, EPI_GELU, EPI_SWIGLU, EPI_RELU = 0, 1, 2, 3
 
 # number of kernels launched through this module (bench.py reports it as gpu_launches)
 launch_count = 0
+# when set to a list, every gemm() call is recorded (bench.py replays the GEMMs alone to time the dominant kernel)
+gemm_recorder = None
 
 
 def _stream():
@@ -41,8 +43,9 @@ def _rows2d(t):
     return t2.shape[0], t2.stride(0)
 
 
-def gemm(a, w, bias=None, residual=None, epilogue=EPI_NONE, out=None, out_dtype=torch.float16, tile_n=0):
-    """out = epi(a @ w.T + bias) (+ residual).  a: [..., K] fp16, w: [N, K] fp16 (nn.Linear layout)."""
+def gemm(a, w, bias=None, residual=None, epilogue=EPI_NONE, out=None, out_dtype=torch.float16, tile_n=0, k_real=None):
+    """out = epi(a @ w.T + bias) (+ residual).  a: [..., K] fp16, w: [N, K] fp16 (nn.Linear layout).
+    k_real: un-padded K, only used for algorithmic-FLOP accounting (patch-embed 588 of 640)."""
     global launch_count
     _need_cuda(a, w, bias, residual, out)
     assert a.dtype == torch.float16 and w.dtype == torch.float16
@@ -67,6 +70,9 @@ def gemm(a, w, bias=None, residual=None, epilogue=EPI_NONE, out=None, out_dtype=
                                     _stream())
     _lib.check(rc, "stllm_gemm_f16")
     launch_count += 1
+    if gemm_recorder is not None:
+        gemm_recorder.append(dict(a=a, w=w, bias=bias, residual=residual, epilogue=epilogue, out=out, tile_n=tile_n,
+                                  M=M, N=N, K=k_real or K))
     return out
 
 
