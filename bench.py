@@ -117,7 +117,10 @@ class CpuReference:
 
     def __init__(self, budget_frames=1, llama_layers_timed=1, S=T_FRAMES * Q_TOK + PROMPT_LEN):
         import torch
-        torch.set_num_threads(os.cpu_count())
+        # all host threads torch can use productively: beyond ~32 threads the fp32 GEMMs of this path (M = 257..576
+        # rows) get slower from oversubscription (measured: 128 threads were 15x slower than 8 on the same code)
+        self.threads = min(os.cpu_count(), 32)
+        torch.set_num_threads(self.threads)
         self.torch = torch
         self.nf, self.nl, self.S = budget_frames, llama_layers_timed, S
         g = torch.Generator().manual_seed(0)
@@ -184,7 +187,7 @@ class CpuReference:
             _ = torch.nn.functional.linear(hid, self.w_head)
             t_head = time.perf_counter() - t0
         t_clip = T_FRAMES * (t_vit + t_qf) + 32 * t_layers + t_head
-        sample = (f"oracle port (fp32 torch CPU, {os.cpu_count()} threads): ViT-g 39 blocks on {self.nf} frame(s) "
+        sample = (f"oracle port (fp32 torch CPU, {self.threads} threads): ViT-g 39 blocks on {self.nf} frame(s) "
                   f"{t_vit*self.nf:.2f}s, ln_vision+12-layer Q-Former+llama_proj {t_qf*self.nf:.2f}s, {self.nl} "
                   f"Vicuna layer(s) at S={self.S} {t_layers*self.nl:.2f}s, lm_head {t_head:.2f}s; scaled to 16 "
                   f"frames / 32 layers (layer-extrapolated) = {t_clip:.1f} s/clip")
@@ -232,7 +235,7 @@ def main():
                 "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                 "ms_per_step": 1000.0 * T_FRAMES / v, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": v, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+                "cpu_baseline": {"value": v, "unit": "frames/s", "cores": cpu.threads, "kind": "port",
                                  "sample": sample},
                 "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -303,11 +306,13 @@ def main():
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
+    torch.cuda.profiler.start()   # no-op unless run under `ncu --profile-from-start off`
     e0.record()
     for _ in range(args.steps):
         step_device()
     e1.record()
     torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
     t_wall1 = time.time()
     if world > 1:
         dist.barrier()
@@ -387,10 +392,10 @@ def main():
             "gpu_launches": pipe.launches_per_step * args.steps, "launches_per_step": pipe.launches_per_step,
             "roofline": roofline}
     if world == 1 and not args.skip_cpu_baseline:
-        cpu = CpuReference(budget_frames=2, llama_layers_timed=2)
+        cpu = CpuReference(budget_frames=1, llama_layers_timed=1)
         cpu.run()  # warm-up
         fps, sample, _ = cpu.run()
-        line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": os.cpu_count(), "kind": "port",
+        line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cpu.threads, "kind": "port",
                                 "sample": sample}
     print(json.dumps(line))
     if world > 1:
