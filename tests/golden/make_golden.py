@@ -157,14 +157,20 @@ def golden_flow(ref):
     """Whole training-branch hot path a1-a22 through the reference's own methods:
     STLLMForCausalLM.forward(samples) -> STLLMLlamaModel.forward -> STLLMModel.forward (encode_img, residual
     aggregation, dynamic mask, prompt_wrap, concat, targets) -> LLM masked+unmasked passes -> MVM + CE loss."""
-    from tests.flow_fixture import build_reference_flow, flow_samples
-    llm, M = build_reference_flow(ref)
+    import json
+    from tests.flow_fixture import build_reference_flow, flow_samples, weights_checksum
+    llm, M, sd = build_reference_flow(ref)
     samples = flow_samples()
     np.random.seed(1237)
     out = llm(samples=samples)
     _save("stllm_flow.npz", loss=out.loss.numpy(), logits_head=out.logits[:, :, :64].numpy(),
           logits_shape=np.array(out.logits.shape), mask=M.mask.numpy(), img_len=M.img_len,
-          mask_img_len=M.mask_img_len, residual_index=M.residual_index.numpy())
+          mask_img_len=M.mask_img_len, residual_index=M.residual_index.numpy(),
+          weights_checksum=np.float64(weights_checksum(sd)))
+    # the reference's own state-dict keys (the checkpoint contract of SURVEY section 5)
+    keys = {k: list(v.shape) for k, v in llm.state_dict().items()}
+    with open(os.path.join(HERE, "stllm_flow_state_dict_keys.json"), "w") as f:
+        json.dump(keys, f, indent=0, sort_keys=True)
 
 
 if __name__ == "__main__":
