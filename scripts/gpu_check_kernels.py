@@ -158,6 +158,17 @@ def main():
     gemm_case(32, 1024, 4096, epi=ops.EPI_RELU, bias=True)
     gemm_case(1, 4096, 4096)                       # decode-like M=1
     gemm_case(300, 768, 768, bias=True, lda_pad=8) # strided A (ld != K)
+    # --- CTA-pair (cta_group::2) kernel, tile_n=512 ---
+    gemm_case(256, 256, 64, tile_n=512)
+    gemm_case(256, 256, 512, tile_n=512)
+    gemm_case(512, 1024, 256, tile_n=512)
+    gemm_case(100, 200, 72, tile_n=512)
+    gemm_case(4112, 4224, 1408, bias=True, tile_n=512)
+    gemm_case(4112, 6144, 1408, epi=ops.EPI_GELU, bias=True, tile_n=512)
+    gemm_case(4112, 1408, 6144, bias=True, residual=True, tile_n=512)
+    gemm_case(576, 22016, 4096, epi=ops.EPI_SWIGLU, tile_n=512)
+    gemm_case(576, 4096, 11008, residual=True, tile_n=512)
+    gemm_case(64, 32001, 4096, out_f32=True, tile_n=512)
     # --- attention ---
     attn_case(2, 16, 257, 257, 88, prescale=True, packed=True)   # ViT
     attn_case(3, 12, 32, 32, 64)                                  # Q-Former self (no text)
@@ -234,13 +245,16 @@ def main():
         print("  FAILED:", f)
     # --- timings ---
     if "--no-time" not in sys.argv:
-        for tn in (128, 256):
+        for tn in (256, 512):
             time_gemm(4112, 6144, 1408, ops.EPI_GELU, tn)
             time_gemm(4112, 4224, 1408, ops.EPI_NONE, tn)
             time_gemm(4112, 1408, 6144, ops.EPI_NONE, tn)
             time_gemm(576, 22016, 4096, ops.EPI_SWIGLU, tn)
             time_gemm(576, 4096, 11008, ops.EPI_NONE, tn)
             time_gemm(576, 12288, 4096, ops.EPI_NONE, tn)
+            time_gemm(4112, 1408, 1408, ops.EPI_NONE, tn)
+            time_gemm(576, 4096, 4096, ops.EPI_NONE, tn)
+            time_gemm(576, 32000, 4096, ops.EPI_NONE, tn)
             time_gemm(8192, 8192, 8192, ops.EPI_NONE, tn)
     return 1 if fails else 0
 

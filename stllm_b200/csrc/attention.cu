@@ -150,6 +150,7 @@ attention_f16_kernel(const AttnParams p) {
   const float sl2 = p.scale * LOG2E;
   const float mask_l2 = p.mask_value * LOG2E;
   const int qrow0 = q0 + warp * 16 + (lane >> 2);  // this thread's two query rows: qrow0, qrow0 + 8
+  const bool warp_active = (q0 + warp * 16) < p.Sq;
   const unsigned char* kmask = p.kmask ? p.kmask + (long long)b * p.Skv : nullptr;
 
   for (int t = 0; t < n_tiles; ++t) {
@@ -164,6 +165,11 @@ attention_f16_kernel(const AttnParams p) {
     __syncthreads();
     const __half* tK = sK + buf * BKV * LD;
     const __half* tV = sV + buf * BKV * LD;
+    // ragged edges (S = 257 = 4*64 + 1 in the ViT): skip 16-key groups beyond the last valid key and warps whose
+    // 16 query rows are all beyond Sq, instead of computing on zero padding
+    const int valid_keys = (kv_end - t * BKV) < BKV ? (kv_end - t * BKV) : BKV;
+    const int n_groups = (valid_keys + 15) >> 4;
+    if (warp_active) {
 
     // ---- S = Q K^T  (16 x 64 per warp) ----
     float s[BKV / 8][4];
@@ -175,6 +181,7 @@ attention_f16_kernel(const AttnParams p) {
       for (int ks = 0; ks < KSTEPS; ++ks) {
 #pragma unroll
         for (int np = 0; np < BKV / 16; ++np) {
+          if (np >= n_groups) continue;
           uint32_t b0, b1, b2, b3;
           const int key = np * 16 + (m >> 1) * 8 + r;
           const int col = ks * 16 + (m & 1) * 8;
@@ -247,6 +254,7 @@ attention_f16_kernel(const AttnParams p) {
       const int m = lane >> 3, r = lane & 7;
 #pragma unroll
       for (int ks = 0; ks < BKV / 16; ++ks) {
+        if (ks >= n_groups) continue;
 #pragma unroll
         for (int np = 0; np < NT_O / 2; ++np) {
           uint32_t b0, b1, b2, b3;
@@ -258,6 +266,7 @@ attention_f16_kernel(const AttnParams p) {
         }
       }
     }
+    }  // warp_active
     __syncthreads();  // everyone done with buf before it is refilled
   }
 

@@ -47,6 +47,115 @@ struct SmemLayout {
 DEVI float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 DEVI float silu(float x) { return x / (1.0f + __expf(-x)); }
 
+// One 32-column chunk of one accumulator row: bias / activation / SwiGLU / residual / convert / store.
+// bias and residual are fetched BEFORE the TMEM load is waited on, so their global-load latency overlaps it.
+template <int EPI>
+DEVI void epilogue_chunk(const GemmParams& p, uint32_t taddr, int row, bool row_ok, int col0) {
+  constexpr int NC = (EPI == EPI_SWIGLU) ? 16 : 32;  // output columns produced by this chunk
+  const int ocol0 = (EPI == EPI_SWIGLU) ? (col0 >> 1) : col0;
+  const int n_out = (EPI == EPI_SWIGLU) ? (p.N >> 1) : p.N;
+  const bool active = row_ok && col0 < p.N;
+  const bool full_chunk = (col0 + 32 <= p.N);
+  const bool vec_ok = (ocol0 + NC <= n_out);
+  uint32_t r[32];
+  tmem_ld_32x32b_x32(taddr, r);
+  uint4 bq[4], rq[NC / 8];
+  const bool bias_vec = active && p.bias != nullptr && full_chunk;
+  const __half* rp = active && p.residual != nullptr ? p.residual + (long long)row * p.ldr + ocol0 : nullptr;
+  const bool res_vec = rp != nullptr && vec_ok && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0);
+  if (bias_vec) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) bq[q] = __ldg(reinterpret_cast<const uint4*>(p.bias + col0) + q);
+  }
+  if (res_vec) {
+#pragma unroll
+    for (int q = 0; q < NC / 8; ++q) rq[q] = __ldg(reinterpret_cast<const uint4*>(rp) + q);
+  }
+  tmem_ld_wait();
+  if (!active) return;
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  if (p.bias != nullptr) {
+    if (bias_vec) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const __half2* bh = reinterpret_cast<const __half2*>(&bq[q]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(bh[j]);
+          v[q * 8 + 2 * j] += f.x;
+          v[q * 8 + 2 * j + 1] += f.y;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (col0 + j < p.N) v[j] += __half2float(p.bias[col0 + j]);
+    }
+  }
+  if (EPI == EPI_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+  }
+  if (EPI == EPI_RELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+  }
+  if (EPI == EPI_SWIGLU) {
+    // interleaved weights: accumulator column 2j = gate_j, 2j+1 = up_j -> output column j
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = silu(v[2 * j]) * v[2 * j + 1];
+  }
+  if (rp != nullptr) {
+    if (res_vec) {
+#pragma unroll
+      for (int q = 0; q < NC / 8; ++q) {
+        const __half2* bh = reinterpret_cast<const __half2*>(&rq[q]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(bh[j]);
+          v[q * 8 + 2 * j] += f.x;
+          v[q * 8 + 2 * j + 1] += f.y;
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NC; ++j)
+        if (ocol0 + j < n_out) v[j] += __half2float(rp[j]);
+    }
+  }
+  if (p.out_f32) {
+    float* cp = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + ocol0;
+    if (vec_ok && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
+#pragma unroll
+      for (int q = 0; q < NC / 4; ++q)
+        reinterpret_cast<float4*>(cp)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < NC; ++j)
+        if (ocol0 + j < n_out) cp[j] = v[j];
+    }
+  } else {
+    __half* cp = reinterpret_cast<__half*>(p.C) + (long long)row * p.ldc + ocol0;
+    if (vec_ok && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
+#pragma unroll
+      for (int q = 0; q < NC / 8; ++q) {
+        uint4 o;
+        o.x = pack_half2(v[8 * q + 0], v[8 * q + 1]);
+        o.y = pack_half2(v[8 * q + 2], v[8 * q + 3]);
+        o.z = pack_half2(v[8 * q + 4], v[8 * q + 5]);
+        o.w = pack_half2(v[8 * q + 6], v[8 * q + 7]);
+        reinterpret_cast<uint4*>(cp)[q] = o;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NC; ++j)
+        if (ocol0 + j < n_out) cp[j] = __float2half_rn(v[j]);
+    }
+  }
+}
+
 template <int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -152,107 +261,13 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 #pragma unroll 1
       for (int c = 0; c < COLS_PER_WARP; c += 32) {
         __syncwarp();
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(t_row + c, r);
-        tmem_ld_wait();
+        const int col0 = n_blk * BN + half_idx * COLS_PER_WARP + c;  // first accumulator column of the chunk
+        epilogue_chunk<EPI>(p, t_row + c, row, row_ok, col0);
         if (c + 32 >= COLS_PER_WARP) {
-          // all TMEM reads of this warp for this tile are done -> release the accumulator stage early
+          // all TMEM reads of this warp for this tile are done -> release the accumulator stage
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-        }
-        const int col0 = n_blk * BN + half_idx * COLS_PER_WARP + c;  // first accumulator column of the chunk
-        if (col0 >= p.N || !row_ok) continue;  // col0 is warp-uniform; row_ok lanes re-converge at __syncwarp
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        const bool full_chunk = (col0 + 32 <= p.N);
-        if (p.bias != nullptr) {
-          if (full_chunk) {
-            const uint4* bp = reinterpret_cast<const uint4*>(p.bias + col0);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              uint4 b = __ldg(bp + q);
-              const __half2* bh = reinterpret_cast<const __half2*>(&b);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float2 f = __half22float2(bh[j]);
-                v[q * 8 + 2 * j] += f.x;
-                v[q * 8 + 2 * j + 1] += f.y;
-              }
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (col0 + j < p.N) v[j] += __half2float(p.bias[col0 + j]);
-          }
-        }
-        if (EPI == EPI_GELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
-        }
-        if (EPI == EPI_RELU) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-        constexpr int NC = (EPI == EPI_SWIGLU) ? 16 : 32;  // output columns produced by this chunk
-        int ocol0 = col0, n_out = p.N;
-        if (EPI == EPI_SWIGLU) {
-          // interleaved weights: accumulator column 2j = gate_j, 2j+1 = up_j -> output column j
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = silu(v[2 * j]) * v[2 * j + 1];
-          ocol0 = col0 >> 1;
-          n_out = p.N >> 1;
-        }
-        const bool vec_ok = (ocol0 + NC <= n_out);
-        if (p.residual != nullptr) {
-          const __half* rp = p.residual + (long long)row * p.ldr + ocol0;
-          if (vec_ok && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0)) {
-#pragma unroll
-            for (int q = 0; q < NC / 8; ++q) {
-              uint4 b = __ldg(reinterpret_cast<const uint4*>(rp) + q);
-              const __half2* bh = reinterpret_cast<const __half2*>(&b);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float2 f = __half22float2(bh[j]);
-                v[q * 8 + 2 * j] += f.x;
-                v[q * 8 + 2 * j + 1] += f.y;
-              }
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < NC; ++j)
-              if (ocol0 + j < n_out) v[j] += __half2float(rp[j]);
-          }
-        }
-        if (p.out_f32) {
-          float* cp = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + ocol0;
-          if (vec_ok && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
-#pragma unroll
-            for (int q = 0; q < NC / 4; ++q)
-              reinterpret_cast<float4*>(cp)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < NC; ++j)
-              if (ocol0 + j < n_out) cp[j] = v[j];
-          }
-        } else {
-          __half* cp = reinterpret_cast<__half*>(p.C) + (long long)row * p.ldc + ocol0;
-          if (vec_ok && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
-#pragma unroll
-            for (int q = 0; q < NC / 8; ++q) {
-              uint4 o;
-              o.x = pack_half2(v[8 * q + 0], v[8 * q + 1]);
-              o.y = pack_half2(v[8 * q + 2], v[8 * q + 3]);
-              o.z = pack_half2(v[8 * q + 4], v[8 * q + 5]);
-              o.w = pack_half2(v[8 * q + 6], v[8 * q + 7]);
-              reinterpret_cast<uint4*>(cp)[q] = o;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < NC; ++j)
-              if (ocol0 + j < n_out) cp[j] = __float2half_rn(v[j]);
-          }
         }
       }
       __syncwarp();
@@ -265,6 +280,157 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ==============================================================================================
+// CTA-pair variant (cta_group::2): a cluster of 2 CTAs computes a 256 x 256 output tile.
+//   * each CTA TMA-loads its own 128 rows of A and its own 128 rows (= half of the N tile) of W per k-block:
+//     32 KB per CTA per 512-cycle k-block = 64 B/clk of L2->SMEM ingest instead of 96 B/clk for the 128x256
+//     one-CTA tile (ncu: the one-CTA kernel sits at 0.67 tensor-pipe utilisation = 64/96).
+//   * the LEADER CTA's elected thread issues tcgen05.mma.cta_group::2 (M=256, N=256); the hardware reads A/B
+//     from both CTAs' shared memory and writes 128 accumulator rows into each CTA's TMEM.
+//   * barriers: full[s] lives in the leader (both CTAs' TMA complete_tx on it); empty[s] and tmem_full[a] are
+//     multicast-committed to both CTAs; tmem_empty[a] lives in the leader and collects both CTAs' epilogue warps.
+// ==============================================================================================
+constexpr int BN2 = 256;
+constexpr int STAGES2 = 6;
+struct SmemLayout2 {
+  static constexpr int A_BYTES = BM * BK * 2;          // 16 KB: this CTA's 128 rows of A
+  static constexpr int B_BYTES = (BN2 / 2) * BK * 2;   // 16 KB: this CTA's half of the W tile
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES2 * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
+};
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                             const GemmParams p) {
+  using L = SmemLayout2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
+  uint64_t* empty_bar = full_bar + STAGES2;
+  uint64_t* tmem_full_bar = empty_bar + STAGES2;
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t cta_rank = cluster_ctarank();
+  const bool is_leader = cta_rank == 0;
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+  const int num_tiles = p.m_tiles * p.n_tiles;   // 256 x 256 pair tiles
+  const int k_blocks = (p.K + BK - 1) / BK;
+  constexpr uint32_t TMEM_COLS = 512;            // 2 accumulator stages x 256 fp32 columns
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < STAGES2; ++s) {
+      mbar_init(&full_bar[s], 1);     // leader's copy is the one in use: 1 arrival (leader producer) + tx bytes
+      mbar_init(&empty_bar[s], 1);    // one multicast tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);                    // one multicast tcgen05.commit
+      mbar_init(&tmem_empty_bar[a], 2 * NUM_EPI_WARPS);   // leader's copy: epilogue warps of both CTAs
+    }
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_base_slot, TMEM_COLS);
+  tc_fence_before();
+  cluster_sync_all();   // barriers of BOTH CTAs initialised before any remote arrive / TMA complete_tx
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        const int m_blk = t % p.m_tiles, n_blk = t / p.m_tiles;
+        const int row_a = m_blk * 256 + (int)cta_rank * 128;
+        const int row_b = n_blk * BN2 + (int)cta_rank * (BN2 / 2);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);  // bytes of both CTAs
+          tma_load_2d_2sm(&tmA, &full_bar[stage], sa, kb * BK, row_a, TMA_EVICT_NORMAL);
+          tma_load_2d_2sm(&tmB, &full_bar[stage], sb, kb * BK, row_b, TMA_EVICT_NORMAL);
+          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (is_leader && lane == 0) {
+      constexpr uint32_t idesc = make_idesc_f16(256, BN2, false);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN2);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+          const uint32_t sb = sa + L::A_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t da = make_sdesc_k_sw128(sa + kk * 32);
+            const uint64_t db = make_sdesc_k_sw128(sb + kk * 32);
+            umma_f16_ss_2sm(d_tmem, da, db, idesc, (kb | kk) != 0 ? 1u : 0u);
+          }
+          umma_commit_2sm(&empty_bar[stage], 3);   // frees this smem slot in BOTH CTAs
+          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+        }
+        umma_commit_2sm(&tmem_full_bar[acc], 3);   // accumulators of both CTAs complete
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (both CTAs, 128 rows each) =====================
+    const int e = warp - 2;
+    const int quad = warp & 3;
+    const int half_idx = e >> 2;
+    constexpr int COLS_PER_WARP = BN2 / 2;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+      const int m_blk = t % p.m_tiles, n_blk = t / p.m_tiles;
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tc_fence_after();
+      const int row = m_blk * 256 + (int)cta_rank * 128 + quad * 32 + lane;
+      const bool row_ok = row < p.M;
+      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN2 + half_idx * COLS_PER_WARP);
+#pragma unroll 1
+      for (int c = 0; c < COLS_PER_WARP; c += 32) {
+        __syncwarp();
+        const int col0 = n_blk * BN2 + half_idx * COLS_PER_WARP + c;
+        epilogue_chunk<EPI>(p, t_row + c, row, row_ok, col0);
+        if (c + 32 >= COLS_PER_WARP) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty_bar[acc]), 0));  // leader's barrier
+        }
+      }
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();   // the peer's smem/TMEM/barriers stay alive until the leader's last MMA and commit landed
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, TMEM_COLS);
   }
 }
 
@@ -348,6 +514,32 @@ int dispatch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const 
   }
 }
 
+template <int EPI>
+int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+  auto kern = gemm_f16_tcgen05_2cta_kernel<EPI>;
+  static bool configured = false;
+  if (!configured) {
+    STLLM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout2::TOTAL));
+    configured = true;
+  }
+  const int tiles = p.m_tiles * p.n_tiles;
+  int clusters = num_sms() / 2;
+  if (tiles < clusters) clusters = tiles;
+  kern<<<2 * clusters, NUM_THREADS, SmemLayout2::TOTAL, stream>>>(tmA, tmB, p);
+  STLLM_CHECK_CUDA(cudaGetLastError());
+  return STLLM_OK;
+}
+
+int dispatch_epi_2cta(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t s) {
+  switch (epi) {
+    case EPI_NONE: return launch_gemm_2cta<EPI_NONE>(tmA, tmB, p, s);
+    case EPI_GELU: return launch_gemm_2cta<EPI_GELU>(tmA, tmB, p, s);
+    case EPI_SWIGLU: return launch_gemm_2cta<EPI_SWIGLU>(tmA, tmB, p, s);
+    case EPI_RELU: return launch_gemm_2cta<EPI_RELU>(tmA, tmB, p, s);
+    default: stllm_set_last_error("unknown epilogue %d", epi); return STLLM_ERR_BAD_ARG;
+  }
+}
+
 }  // namespace
 
 extern "C" int stllm_gemm_f16(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc,
@@ -368,11 +560,11 @@ extern "C" int stllm_gemm_f16(const void* A, long long lda, const void* W, long 
     const long long t256 = m_tiles * ((N + 255) / 256);
     bn = (t256 >= num_sms()) ? 256 : 128;
   }
-  STLLM_CHECK_ARG(bn == 128 || bn == 256);
+  STLLM_CHECK_ARG(bn == 128 || bn == 256 || bn == 512);   // 512 = CTA-pair kernel (256 x 256 tile per 2 SMs)
   CUtensorMap tmA, tmB;
   int rc = make_tmap(&tmA, A, M, K, lda, BM);
   if (rc != STLLM_OK) return rc;
-  rc = make_tmap(&tmB, W, N, K, ldw, bn);
+  rc = make_tmap(&tmB, W, N, K, ldw, bn == 512 ? 128 : bn);
   if (rc != STLLM_OK) return rc;
   GemmParams p;
   p.C = C;
@@ -387,6 +579,11 @@ extern "C" int stllm_gemm_f16(const void* A, long long lda, const void* W, long 
   p.n_tiles = (N + bn - 1) / bn;
   p.out_f32 = out_f32;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (bn == 512) {
+    p.m_tiles = (M + 255) / 256;
+    p.n_tiles = (N + 255) / 256;
+    return dispatch_epi_2cta(epilogue, tmA, tmB, p, s);
+  }
   if (bn == 256) return dispatch_epi<256, 4>(epilogue, tmA, tmB, p, s);
   return dispatch_epi<128, 6>(epilogue, tmA, tmB, p, s);
 }

@@ -121,6 +121,118 @@ rmsnorm_f16_kernel(const __half* __restrict__ x, long long ldx, __half* __restri
     yr[i] = __hmul(w[i], __float2half_rn(__half2float(xr[i]) * rstd));
 }
 
+
+// Register-cached LayerNorm: one warp per row, the row (<= 32 * MAXV * 8 elements) is read from global ONCE.
+template <int MAXV>
+__global__ void __launch_bounds__(256)
+layernorm_f16_regs_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict__ y, long long ldy,
+                          const float* __restrict__ gamma, const float* __restrict__ beta, int rows, int cols,
+                          float eps) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + (long long)row * ldx);
+  uint4* yr = reinterpret_cast<uint4*>(y + (long long)row * ldy);
+  const int nvec = cols >> 3;
+  float v[MAXV][8];
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      const uint4 u = __ldg(xr + vi);
+      const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        v[i][2 * j] = f.x;
+        v[i][2 * j + 1] = f.y;
+        sum += f.x + f.y;
+      }
+    }
+  }
+  const float mean = warp_sum(sum) / (float)cols;
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    if (lane + i * 32 < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float a = v[i][j] - mean;
+        sq += a * a;
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(sq) / (float)cols + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * vi);
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * vi + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * vi);
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * vi + 1);
+      uint4 w;
+      w.x = pack_half2((v[i][0] - mean) * rstd * g0.x + b0.x, (v[i][1] - mean) * rstd * g0.y + b0.y);
+      w.y = pack_half2((v[i][2] - mean) * rstd * g0.z + b0.z, (v[i][3] - mean) * rstd * g0.w + b0.w);
+      w.z = pack_half2((v[i][4] - mean) * rstd * g1.x + b1.x, (v[i][5] - mean) * rstd * g1.y + b1.y);
+      w.w = pack_half2((v[i][6] - mean) * rstd * g1.z + b1.z, (v[i][7] - mean) * rstd * g1.w + b1.w);
+      yr[vi] = w;
+    }
+  }
+}
+
+// Block-per-row RMSNorm for wide rows (Llama hidden 4096): 256 threads x VPT 16-byte vectors, one global read.
+template <int VPT>
+__global__ void __launch_bounds__(256)
+rmsnorm_f16_block_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict__ y, long long ldy,
+                         const __half* __restrict__ w, int rows, int cols, float eps) {
+  const int row = blockIdx.x;
+  const uint4* xr = reinterpret_cast<const uint4*>(x + (long long)row * ldx);
+  uint4* yr = reinterpret_cast<uint4*>(y + (long long)row * ldy);
+  const int nvec = cols >> 3;
+  __shared__ float red[8];
+  uint4 u[VPT];
+  float sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int vi = threadIdx.x + i * 256;
+    if (vi < nvec) {
+      u[i] = __ldg(xr + vi);
+      const __half2* h = reinterpret_cast<const __half2*>(&u[i]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        sq += f.x * f.x + f.y * f.y;
+      }
+    }
+  }
+  sq = warp_sum(sq);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sq;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) tot += red[i];
+  const float rstd = rsqrtf(tot / (float)cols + eps);
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    const int vi = threadIdx.x + i * 256;
+    if (vi < nvec) {
+      const uint4 wv = __ldg(reinterpret_cast<const uint4*>(w) + vi);
+      const __half2* h = reinterpret_cast<const __half2*>(&u[i]);
+      const __half2* wh = reinterpret_cast<const __half2*>(&wv);
+      uint4 o;
+      __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        oh[j] = __hmul2(wh[j], __floats2half2_rn(f.x * rstd, f.y * rstd));
+      }
+      yr[vi] = o;
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" int stllm_layernorm_f16(const void* x, long long ldx, void* y, long long ldy, const float* gamma,
@@ -128,9 +240,17 @@ extern "C" int stllm_layernorm_f16(const void* x, long long ldx, void* y, long l
   STLLM_CHECK_ARG(x && y && gamma && beta && rows > 0 && cols > 0);
   STLLM_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0);
   STLLM_CHECK_ARG(((uintptr_t)gamma & 15) == 0 && ((uintptr_t)beta & 15) == 0);
-  const int grid = (rows + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
-  layernorm_f16_kernel<<<grid, ROWS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(
-      (const __half*)x, ldx, (__half*)y, ldy, gamma, beta, rows, cols, eps);
+  if (cols % 8 == 0 && cols <= 32 * 8 * 6) {
+    layernorm_f16_regs_kernel<6><<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
+        (const __half*)x, ldx, (__half*)y, ldy, gamma, beta, rows, cols, eps);
+  } else if (cols % 8 == 0 && cols <= 32 * 8 * 16) {
+    layernorm_f16_regs_kernel<16><<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
+        (const __half*)x, ldx, (__half*)y, ldy, gamma, beta, rows, cols, eps);
+  } else {
+    const int grid = (rows + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
+    layernorm_f16_kernel<<<grid, ROWS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(
+        (const __half*)x, ldx, (__half*)y, ldy, gamma, beta, rows, cols, eps);
+  }
   STLLM_CHECK_CUDA(cudaGetLastError());
   return STLLM_OK;
 }
@@ -140,9 +260,14 @@ extern "C" int stllm_rmsnorm_f16(const void* x, long long ldx, void* y, long lon
   STLLM_CHECK_ARG(x && y && weight && rows > 0 && cols > 0);
   STLLM_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 &&
                   ((uintptr_t)weight & 15) == 0);
-  const int grid = (rows + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
-  rmsnorm_f16_kernel<<<grid, ROWS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(
-      (const __half*)x, ldx, (__half*)y, ldy, (const __half*)weight, rows, cols, eps);
+  if (cols % 8 == 0 && cols >= 2048 && cols <= 256 * 8 * 2) {
+    rmsnorm_f16_block_kernel<2><<<rows, 256, 0, (cudaStream_t)stream>>>(
+        (const __half*)x, ldx, (__half*)y, ldy, (const __half*)weight, rows, cols, eps);
+  } else {
+    const int grid = (rows + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
+    rmsnorm_f16_kernel<<<grid, ROWS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(
+        (const __half*)x, ldx, (__half*)y, ldy, (const __half*)weight, rows, cols, eps);
+  }
   STLLM_CHECK_CUDA(cudaGetLastError());
   return STLLM_OK;
 }
