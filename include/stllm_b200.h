@@ -41,10 +41,20 @@ int stllm_device_sm_count(void);
  * 357,371; st_llm.py:368 (llama_proj), :38 (mvm head), :108,122 (lm_head); modeling_llama_mem.py:160-163,
  * 139-143 (q/k/v/o, gate/up/down).  K, lda, ldw multiples of 8; A, W 16-byte aligned.
  * For STLLM_EPI_SWIGLU the output has N/2 columns.  out_f32: 0 -> fp16 C, 1 -> fp32 C.
- * tile_n: 0 = auto, or 128 / 256. */
+ * tile_n: 0 = auto, 128 / 256 = one-CTA tiles, 512 = CTA-pair (cta_group::2) 256x256 tiles, 1024 = stream-K. */
 int stllm_gemm_f16(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N,
                    int K, const void* bias, const void* residual, long long ldr, int epilogue, int out_f32,
                    int tile_n, void* stream);
+
+/* Stream-K scheduling of the GEMM needs a caller-owned, ZEROED device workspace of at least
+ * stllm_gemm_workspace_bytes() bytes (256-byte aligned), registered once per process/device.  Passing NULL
+ * unregisters it (data-parallel tiles only).  tile_n = 1024 forces stream-K, 512 the CTA-pair kernel. */
+long long stllm_gemm_workspace_bytes(void);
+int stllm_set_gemm_workspace(void* ptr, long long bytes);
+
+/* Debug aid: copies and resets 8 cycle counters of the GEMM kernels ([0] producer waits, [1] MMA waits for TMA data,
+ * [2] MMA waits for a free accumulator, [3] epilogue waits, [4] CTA-0 kernel cycles, [5] launches).  Synchronises. */
+int stllm_gemm_debug_counters(unsigned long long* out8);
 
 /* out[b,s,h,:] = softmax(scale * q k^T + mask) v   (flash-style, fp32 softmax).  Strides: {batch, seq, head} in
  * elements, multiples of 8.  q_prescale != 0: q <- fp16(q * q_prescale) first (eva_vit.py:128).

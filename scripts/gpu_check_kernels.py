@@ -8,6 +8,8 @@ import time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
+os.environ.setdefault("STLLM_GEMM_SK", "1")  # exercise the hybrid stream-K schedule in the 256/512 cases
+
 from stllm_b200 import ops
 
 torch.manual_seed(0)
@@ -102,34 +104,35 @@ def attn_case(B, H, Sq, Skv, D, causal=False, mask=False, prescale=False, packed
     return report(name, out.reshape(-1, D), ref.reshape(-1, D), atol=4e-3, rtol=1e-2)
 
 
-def time_gemm(M, N, K, epi=ops.EPI_NONE, tile_n=0, iters=20):
+def time_gemm(M, N, K, epi=ops.EPI_NONE, variants=(0, 257, 256, 513, 512), rounds=5, iters=10, bias=False, residual=False):
+    """interleaved A/B timing: every round times each variant and cuBLAS back to back (same clocks)"""
     a = torch.randn(M, K, device=dev, dtype=torch.float16)
     w = torch.randn(N, K, device=dev, dtype=torch.float16) * 0.02
     n_out = N // 2 if epi == ops.EPI_SWIGLU else N
     out = torch.empty(M, n_out, device=dev, dtype=torch.float16)
-    for _ in range(3):
-        ops.gemm(a, w, epilogue=epi, out=out, tile_n=tile_n)
-    torch.cuda.synchronize()
+    b = torch.randn(N, device=dev, dtype=torch.float16) if bias else None
+    r = torch.randn(M, n_out, device=dev, dtype=torch.float16) if residual else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(iters):
-        ops.gemm(a, w, epilogue=epi, out=out, tile_n=tile_n)
-    e1.record()
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
-    tf = 2.0 * M * N * K / ms / 1e9
-    # cuBLAS bar (not on the product path)
-    for _ in range(3):
-        torch.matmul(a, w.t())
-    torch.cuda.synchronize()
-    e0.record()
-    for _ in range(iters):
-        torch.matmul(a, w.t())
-    e1.record()
-    torch.cuda.synchronize()
-    ms_cb = e0.elapsed_time(e1) / iters
-    print(f"TIME gemm M={M} N={N} K={K} epi={epi} tn={tile_n}: {ms*1e3:.1f} us  {tf:.1f} TFLOP/s   "
-          f"(cuBLAS {ms_cb*1e3:.1f} us {2.0*M*N*K/ms_cb/1e9:.1f} TFLOP/s)", flush=True)
+
+    def run(fn):
+        fn()
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters * 1e3
+    res = {v: [] for v in variants}
+    res["cublas"] = []
+    for _ in range(rounds):
+        for v in variants:
+            res[v].append(run(lambda: ops.gemm(a, w, bias=b, residual=r, epilogue=epi, out=out, tile_n=v)))
+        res["cublas"].append(run(lambda: torch.matmul(a, w.t())))
+    med = {k: sorted(x)[len(x) // 2] for k, x in res.items()}
+    fl = 2.0 * M * N * K
+    txt = "  ".join(f"{k}: {med[k]:6.1f}us {fl/med[k]/1e6:6.0f}TF" for k in list(variants) + ["cublas"])
+    best = min(variants, key=lambda k: med[k])
+    print(f"TIME gemm M={M} N={N} K={K} epi={epi}: {txt}  best={best}", flush=True)
 
 
 def main():
@@ -158,6 +161,22 @@ def main():
     gemm_case(32, 1024, 4096, epi=ops.EPI_RELU, bias=True)
     gemm_case(1, 4096, 4096)                       # decode-like M=1
     gemm_case(300, 768, 768, bias=True, lda_pad=8) # strided A (ld != K)
+    # --- hybrid stream-K schedule (default for 256/512) vs pure data-parallel (257/513) ---
+    for tn in (256, 512, 128):
+        gemm_case(4112, 1408, 6144, bias=True, residual=True, tile_n=tn)
+        gemm_case(4112, 1408, 1408, bias=True, residual=True, tile_n=tn)
+        gemm_case(576, 4096, 11008, residual=True, tile_n=tn)
+        gemm_case(576, 4096, 4096, residual=True, tile_n=tn)
+        gemm_case(576, 12288, 4096, tile_n=tn)
+        gemm_case(576, 32000, 4096, tile_n=tn)
+        gemm_case(300, 700, 4096, bias=True, tile_n=tn)
+    gemm_case(100, 200, 72 * 64, tile_n=256)       # 1 tile, K long: split across many CTAs
+    gemm_case(100, 200, 72 * 64, tile_n=512)
+    gemm_case(576, 4096, 11008, residual=True, tile_n=257)
+    gemm_case(576, 4096, 11008, residual=True, tile_n=513)
+    for _ in range(3):                             # repeated launches: flags must return to zero
+        gemm_case(576, 4096, 11008, residual=True, tile_n=256)
+        gemm_case(576, 4096, 11008, residual=True, tile_n=512)
     # --- CTA-pair (cta_group::2) kernel, tile_n=512 ---
     gemm_case(256, 256, 64, tile_n=512)
     gemm_case(256, 256, 512, tile_n=512)
@@ -245,17 +264,21 @@ def main():
         print("  FAILED:", f)
     # --- timings ---
     if "--no-time" not in sys.argv:
-        for tn in (256, 512):
-            time_gemm(4112, 6144, 1408, ops.EPI_GELU, tn)
-            time_gemm(4112, 4224, 1408, ops.EPI_NONE, tn)
-            time_gemm(4112, 1408, 6144, ops.EPI_NONE, tn)
-            time_gemm(576, 22016, 4096, ops.EPI_SWIGLU, tn)
-            time_gemm(576, 4096, 11008, ops.EPI_NONE, tn)
-            time_gemm(576, 12288, 4096, ops.EPI_NONE, tn)
-            time_gemm(4112, 1408, 1408, ops.EPI_NONE, tn)
-            time_gemm(576, 4096, 4096, ops.EPI_NONE, tn)
-            time_gemm(576, 32000, 4096, ops.EPI_NONE, tn)
-            time_gemm(8192, 8192, 8192, ops.EPI_NONE, tn)
+        time_gemm(4112, 4224, 1408, bias=True)                       # ViT qkv
+        time_gemm(4112, 1408, 1408, bias=True, residual=True)        # ViT proj
+        time_gemm(4112, 6144, 1408, ops.EPI_GELU, bias=True)         # ViT fc1
+        time_gemm(4112, 1408, 6144, bias=True, residual=True)        # ViT fc2
+        time_gemm(4112, 9216, 1408, bias=True)                       # Q-Former cross K|V (all layers)
+        time_gemm(512, 2304, 768, bias=True)                         # Q-Former qkv
+        time_gemm(512, 3072, 768, ops.EPI_GELU, bias=True)           # Q-Former FFN in
+        time_gemm(512, 768, 3072, bias=True, residual=True)          # Q-Former FFN out
+        time_gemm(512, 4096, 768, bias=True)                         # llama_proj
+        time_gemm(576, 12288, 4096)                                  # Llama qkv
+        time_gemm(576, 4096, 4096, residual=True)                    # Llama o_proj
+        time_gemm(576, 22016, 4096, ops.EPI_SWIGLU)                  # Llama gate|up
+        time_gemm(576, 4096, 11008, residual=True)                   # Llama down
+        time_gemm(576, 32000, 4096)                                  # lm_head
+        time_gemm(8192, 8192, 8192, rounds=3, iters=5)
     return 1 if fails else 0
 
 

@@ -16,6 +16,9 @@ c_ll_p = ctypes.POINTER(ctypes.c_longlong)
 SIGNATURES = {
     "stllm_abi_version": [],
     "stllm_device_sm_count": [],
+    "stllm_gemm_workspace_bytes": [],
+    "stllm_set_gemm_workspace": [c_void_p, c_ll],
+    "stllm_gemm_debug_counters": [c_void_p],
     "stllm_gemm_f16": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_ll,
                        c_int, c_int, c_int, c_void_p],
     "stllm_attention_f16": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_ll_p, c_ll_p,
@@ -55,6 +58,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the symbol is missing
         fn.argtypes = argtypes
         fn.restype = c_int
+    lib.stllm_gemm_workspace_bytes.restype = c_ll
     lib.stllm_last_error.argtypes = []
     lib.stllm_last_error.restype = ctypes.c_char_p
     _lib = lib

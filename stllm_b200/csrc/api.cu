@@ -1,5 +1,6 @@
 // C-ABI glue: error string, version, device queries.  See include/stllm_b200.h.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -20,4 +21,14 @@ extern "C" int stllm_device_sm_count(void) {
   if (cudaGetDevice(&dev) != cudaSuccess) return STLLM_ERR_CUDA;
   if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return STLLM_ERR_CUDA;
   return n;
+}
+
+// STLLM_PDL=0 disables programmatic dependent launch (default: on)
+bool stllm_pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("STLLM_PDL");
+    v = (e != nullptr && atoi(e) == 0) ? 0 : 1;
+  }
+  return v != 0;
 }

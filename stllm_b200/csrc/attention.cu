@@ -71,6 +71,7 @@ attention_f16_kernel(const AttnParams p) {
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
+  pdl_launch_dependents();
   const __half* qg = p.q + b * p.q_sb + h * p.q_sh;
   const __half* kg = p.k + b * p.k_sb + h * p.k_sh;
   const __half* vg = p.v + b * p.v_sb + h * p.v_sh;
@@ -113,6 +114,7 @@ attention_f16_kernel(const AttnParams p) {
     }
   };
 
+  pdl_wait();   // q/k/v come from the previous kernel
   load_q();
   cp_async_commit();
   load_kv(0, 0);
@@ -299,8 +301,7 @@ int launch_attention(const AttnParams& p, cudaStream_t stream) {
     configured = true;
   }
   dim3 grid((p.Sq + BQ - 1) / BQ, p.H, p.B);
-  kern<<<grid, ATT_THREADS, SMEM, stream>>>(p);
-  STLLM_CHECK_CUDA(cudaGetLastError());
+  STLLM_CHECK_CUDA(stllm_launch(kern, grid, dim3(ATT_THREADS), SMEM, stream, p));
   return STLLM_OK;
 }
 

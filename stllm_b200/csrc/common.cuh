@@ -73,8 +73,9 @@ DEVI uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok;
 }
 // Bounded wait: a protocol bug must trap (-> CUDA error on the host) instead of hanging the GPU.
-DEVI void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
+// Returns the number of cycles spent waiting (0 if the phase had already completed).
+DEVI long long mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return 0;
   long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
@@ -82,6 +83,7 @@ DEVI void mbar_wait(uint64_t* bar, uint32_t parity) {
       __trap();
     }
   }
+  return clock64() - t0;
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -257,4 +259,31 @@ DEVI void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask) {
           smem_u32(bar)),
       "h"(cta_mask)
       : "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may
+// start while its predecessor is still running; it must execute pdl_wait() before reading or writing any global
+// memory the predecessor touches.  pdl_launch_dependents() lets the NEXT kernel begin its launch/prologue early.
+// Both are no-ops for kernels launched without the attribute.
+// ----------------------------------------------------------------------------------------------
+DEVI void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+DEVI void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool stllm_pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+cudaError_t stllm_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                         Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = stllm_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }

@@ -14,6 +14,8 @@ namespace {
 template <typename TIN>
 __global__ void im2col_patch_kernel(const TIN* __restrict__ img, __half* __restrict__ out, int n_img, int C, int H,
                                     int W, int P, int kpad) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int gw = W / P, gh = H / P;
   const int kreal = C * P * P;
   const long long total = (long long)n_img * gh * gw * kpad;
@@ -36,6 +38,8 @@ __global__ void im2col_patch_kernel(const TIN* __restrict__ img, __half* __restr
 __global__ void vit_assemble_kernel(const __half* __restrict__ patches, long long ldp, const __half* __restrict__ cls,
                                     const __half* __restrict__ pos, __half* __restrict__ x, int n_img, int np,
                                     int dim) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int dv = dim >> 3;
   const long long total = (long long)n_img * (np + 1) * dv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -62,6 +66,8 @@ __global__ void vit_assemble_kernel(const __half* __restrict__ patches, long lon
 __global__ void rope_kernel(__half* __restrict__ x, long long ldx, const int* __restrict__ pos,
                             const float* __restrict__ cos_t, const float* __restrict__ sin_t, int rows, int nheads,
                             int D) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int half_d = D >> 1;
   const long long total = (long long)rows * nheads * (half_d >> 1);  // 2 pairs per thread (half2)
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -86,6 +92,8 @@ __global__ void rope_kernel(__half* __restrict__ x, long long ldx, const int* __
 __global__ void gather_rows_kernel(const __half* __restrict__ src, long long lds, const long long* __restrict__ idx,
                                    __half* __restrict__ dst, long long ldd, int n_rows, int cols, long long src_rows,
                                    const __half* __restrict__ addend, int add_period, int* __restrict__ err) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int cv = cols >> 3;
   const long long total = (long long)n_rows * cv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -112,6 +120,8 @@ __global__ void gather_rows_kernel(const __half* __restrict__ src, long long lds
 // x: [B, T, inner] -> y: [B, inner], mean over T with fp32 accumulation (torch.mean on fp16 does the same)
 __global__ void mean_frames_kernel(const __half* __restrict__ x, __half* __restrict__ y, int B, int T,
                                    long long inner) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long iv = inner >> 1;
   const long long total = (long long)B * iv;
   const float inv = 1.f / (float)T;
@@ -132,6 +142,8 @@ __global__ void mean_frames_kernel(const __half* __restrict__ x, __half* __restr
 __global__ void residual_merge_kernel(const __half* __restrict__ x, const __half* __restrict__ g,
                                       const long long* __restrict__ idx, __half* __restrict__ out, int B, int T,
                                       int R, long long inner) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long iv = inner >> 3;
   const long long total = (long long)B * R * iv;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -156,6 +168,8 @@ __global__ void residual_merge_kernel(const __half* __restrict__ x, const __half
 // per row: 2 - 2 * <a/|a|, b/|b|>; accumulated (sum) into out[0]; host divides by rows. One warp per row.
 __global__ void cosine_loss_kernel(const __half* __restrict__ a, long long lda, const __half* __restrict__ b,
                                    long long ldb, int rows, int cols, float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -179,6 +193,8 @@ __global__ void cosine_loss_kernel(const __half* __restrict__ a, long long lda, 
 __global__ void cross_entropy_kernel(const __half* __restrict__ logits, long long ldl,
                                      const long long* __restrict__ labels, int rows, int V, long long ignore_index,
                                      float* __restrict__ out) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x;
   if (row >= rows) return;
   const long long lab = labels[row];
@@ -229,11 +245,10 @@ extern "C" int stllm_im2col_patch(const void* img, int img_is_f32, void* out, in
   const long long total = (long long)n_img * (H / P) * (W / P) * kpad;
   const int grid = grid_for(total, 256);
   if (img_is_f32)
-    im2col_patch_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)img, (__half*)out, n_img, C, H, W, P, kpad);
+    STLLM_CHECK_CUDA(stllm_launch(im2col_patch_kernel<float>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const float*)img, (__half*)out, n_img, C, H, W, P, kpad));
   else
-    im2col_patch_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)img, (__half*)out, n_img, C, H, W, P, kpad);
-  STLLM_CHECK_CUDA(cudaGetLastError());
-  return STLLM_OK;
+    STLLM_CHECK_CUDA(stllm_launch(im2col_patch_kernel<__half>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const __half*)img, (__half*)out, n_img, C, H, W, P, kpad));
+    return STLLM_OK;
 }
 
 extern "C" int stllm_vit_assemble_f16(const void* patches, long long ldp, const void* cls, const void* pos, void* x,
@@ -241,10 +256,8 @@ extern "C" int stllm_vit_assemble_f16(const void* patches, long long ldp, const 
   STLLM_CHECK_ARG(patches && cls && pos && x && n_img > 0 && n_patches > 0 && dim % 8 == 0 && ldp % 8 == 0);
   STLLM_CHECK_ARG((((uintptr_t)patches | (uintptr_t)cls | (uintptr_t)pos | (uintptr_t)x) & 15) == 0);
   const long long total = (long long)n_img * (n_patches + 1) * (dim / 8);
-  vit_assemble_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const __half*)patches, ldp, (const __half*)cls, (const __half*)pos, (__half*)x, n_img, n_patches, dim);
-  STLLM_CHECK_CUDA(cudaGetLastError());
-  return STLLM_OK;
+  STLLM_CHECK_CUDA(stllm_launch(vit_assemble_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, (const __half*)patches, ldp, (const __half*)cls, (const __half*)pos, (__half*)x, n_img, n_patches, dim));
+    return STLLM_OK;
 }
 
 extern "C" int stllm_rope_f16(void* x, long long ldx, const int* pos, const float* cos_t, const float* sin_t, int rows,
@@ -252,10 +265,9 @@ extern "C" int stllm_rope_f16(void* x, long long ldx, const int* pos, const floa
   STLLM_CHECK_ARG(x && pos && cos_t && sin_t && rows > 0 && nheads > 0 && head_dim % 4 == 0 && ldx % 2 == 0);
   STLLM_CHECK_ARG(max_pos > 0 && (((uintptr_t)x) & 3) == 0 && (((uintptr_t)cos_t | (uintptr_t)sin_t) & 7) == 0);
   const long long total = (long long)rows * nheads * (head_dim / 4);
-  rope_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((__half*)x, ldx, pos, cos_t, sin_t, rows, nheads,
-                                                                      head_dim);
-  STLLM_CHECK_CUDA(cudaGetLastError());
-  return STLLM_OK;
+  STLLM_CHECK_CUDA(stllm_launch(rope_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, (__half*)x, ldx, pos, cos_t, sin_t, rows, nheads,
+                                                                      head_dim));
+    return STLLM_OK;
 }
 
 extern "C" int stllm_gather_rows_f16(const void* src, long long lds, long long src_rows, const long long* idx, void* dst,
@@ -265,18 +277,15 @@ extern "C" int stllm_gather_rows_f16(const void* src, long long lds, long long s
   STLLM_CHECK_ARG((((uintptr_t)src | (uintptr_t)dst | (uintptr_t)addend) & 15) == 0);
   STLLM_CHECK_ARG(addend == nullptr || add_period > 0);
   const long long total = (long long)n_rows * (cols / 8);
-  gather_rows_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const __half*)src, lds, idx, (__half*)dst, ldd, n_rows, cols, src_rows, (const __half*)addend, add_period, err_flag);
-  STLLM_CHECK_CUDA(cudaGetLastError());
-  return STLLM_OK;
+  STLLM_CHECK_CUDA(stllm_launch(gather_rows_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, (const __half*)src, lds, idx, (__half*)dst, ldd, n_rows, cols, src_rows, (const __half*)addend, add_period, err_flag));
+    return STLLM_OK;
 }
 
 extern "C" int stllm_mean_frames_f16(const void* x, void* y, int B, int T, long long inner, void* stream) {
   STLLM_CHECK_ARG(x && y && B > 0 && T > 0 && inner > 0 && inner % 2 == 0);
   const long long total = (long long)B * (inner / 2);
-  mean_frames_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)x, (__half*)y, B, T, inner);
-  STLLM_CHECK_CUDA(cudaGetLastError());
-  return STLLM_OK;
+  STLLM_CHECK_CUDA(stllm_launch(mean_frames_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, (const __half*)x, (__half*)y, B, T, inner));
+    return STLLM_OK;
 }
 
 extern "C" int stllm_residual_merge_f16(const void* x, const void* g, const long long* idx, void* out, int B, int T,
@@ -284,28 +293,24 @@ extern "C" int stllm_residual_merge_f16(const void* x, const void* g, const long
   STLLM_CHECK_ARG(x && g && idx && out && B > 0 && T > 0 && R > 0 && inner > 0 && inner % 8 == 0);
   STLLM_CHECK_ARG((((uintptr_t)x | (uintptr_t)g | (uintptr_t)out) & 15) == 0);
   const long long total = (long long)B * R * (inner / 8);
-  residual_merge_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const __half*)x, (const __half*)g, idx, (__half*)out, B, T, R, inner);
-  STLLM_CHECK_CUDA(cudaGetLastError());
-  return STLLM_OK;
+  STLLM_CHECK_CUDA(stllm_launch(residual_merge_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, (const __half*)x, (const __half*)g, idx, (__half*)out, B, T, R, inner));
+    return STLLM_OK;
 }
 
 extern "C" int stllm_cosine_loss_f16(const void* a, long long lda, const void* b, long long ldb, int rows, int cols,
                                      float* out_sum, void* stream) {
   STLLM_CHECK_ARG(a && b && out_sum && rows > 0 && cols > 0 && cols % 2 == 0 && lda % 2 == 0 && ldb % 2 == 0);
   STLLM_CHECK_CUDA(cudaMemsetAsync(out_sum, 0, sizeof(float), (cudaStream_t)stream));
-  cosine_loss_kernel<<<(rows + 3) / 4, 128, 0, (cudaStream_t)stream>>>((const __half*)a, lda, (const __half*)b, ldb,
-                                                                       rows, cols, out_sum);
-  STLLM_CHECK_CUDA(cudaGetLastError());
-  return STLLM_OK;
+  STLLM_CHECK_CUDA(stllm_launch(cosine_loss_kernel, dim3((rows + 3) / 4), dim3(128), 0, (cudaStream_t)stream, (const __half*)a, lda, (const __half*)b, ldb,
+                                                                       rows, cols, out_sum));
+    return STLLM_OK;
 }
 
 extern "C" int stllm_cross_entropy_f16(const void* logits, long long ldl, const long long* labels, int rows, int V,
                                        long long ignore_index, float* out_sum_count, void* stream) {
   STLLM_CHECK_ARG(logits && labels && out_sum_count && rows > 0 && V > 0);
   STLLM_CHECK_CUDA(cudaMemsetAsync(out_sum_count, 0, 2 * sizeof(float), (cudaStream_t)stream));
-  cross_entropy_kernel<<<rows, 256, 0, (cudaStream_t)stream>>>((const __half*)logits, ldl, labels, rows, V,
-                                                               ignore_index, out_sum_count);
-  STLLM_CHECK_CUDA(cudaGetLastError());
-  return STLLM_OK;
+  STLLM_CHECK_CUDA(stllm_launch(cross_entropy_kernel, dim3(rows), dim3(256), 0, (cudaStream_t)stream, (const __half*)logits, ldl, labels, rows, V,
+                                                               ignore_index, out_sum_count));
+    return STLLM_OK;
 }

@@ -5,15 +5,25 @@
 // :196 (patch-embed conv as im2col GEMM), Qformer.py query/key/value/dense, st_llm.py:368 (llama_proj),
 // the HF Llama q/k/v/o/gate/up/down projections and lm_head (st_llm.py:108,122).
 //
-// Design (B200-first, persistent, warp-specialised):
-//   * grid = min(#tiles, #SMs) persistent CTAs, 1 CTA/SM, 320 threads:
-//       warp 0      : TMA producer   (one elected lane; A and W tiles, 128B-swizzled, mbarrier complete_tx)
-//       warp 1      : TMEM allocator + MMA issuer (one lane issues tcgen05.mma kind::f16, fp32 accumulate)
-//       warps 2..9  : epilogue (tcgen05.ld -> bias / GELU / SwiGLU / residual -> fp16 -> global)
-//   * smem ring of STAGES x {A 128x64, W BNx64} fp16 tiles; TMEM holds 2 accumulator stages (2 x BN
-//     columns) so the epilogue of tile i overlaps the mainloop of tile i+1.
-//   * Both operands are K-major (activations row-major, nn.Linear weights [N,K]) so no transposes exist
-//     anywhere on the path; ragged M/N/K edges are zero-filled by TMA and predicated in the epilogue.
+// Design (B200-first, persistent, warp-specialised), 320 threads per CTA, 1 CTA per SM:
+//     warp 0      : TMA producer   (one elected lane; 128B-swizzled A and W tiles, mbarrier complete_tx)
+//     warp 1      : TMEM allocator + MMA issuer (one lane issues tcgen05.mma kind::f16, fp32 accumulate)
+//     warps 2..9  : epilogue (tcgen05.ld -> bias / GELU / SwiGLU / ReLU / residual -> fp16 -> global)
+//   * smem ring of {A 128x64, W tile} fp16 stages; TMEM holds 2 accumulator stages so the epilogue of tile i
+//     overlaps the mainloop of tile i+1.
+//   * Both operands are K-major (activations row-major, nn.Linear weights [N,K]) so no transposes exist anywhere
+//     on the path; ragged M/N/K edges are zero-filled by TMA and predicated in the epilogue.
+//   * Two tile engines:
+//       one-CTA   : 128 x BN (BN = 128 | 256) tile per SM, tcgen05.mma.cta_group::1
+//       CTA-pair  : 256 x 256 tile per 2-CTA cluster, tcgen05.mma.cta_group::2; each CTA loads 128 rows of A and
+//                   128 rows (half) of the W tile: 32 KB instead of 48 KB of L2->SMEM ingest per k-block.
+//   * Scheduler ("hybrid stream-K"): whole waves of tiles are processed data-parallel (tile = wave * G + cta, m
+//     fastest -> concurrent CTAs share the same W tile in L2).  Only the ragged LAST wave (tiles % G) is cut into
+//     (tile, k-block) units and spread evenly over all G CTAs/clusters: a CTA that computes the tail of a tile dumps
+//     its raw fp32 accumulator to a workspace slot and raises a flag; the CTA that computed the head of that tile
+//     adds the partials and runs the fused epilogue.  The split tiles run FIRST, so every CTA finishes together.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
@@ -22,6 +32,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 fp16 = 128 B = one swizzle-128B row
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 64 + NUM_EPI_WARPS * 32;
+constexpr int SLOT_ELEMS = 128 * 256;  // fp32 partial-tile slot per CTA (one-CTA BN<=256; CTA-pair: 128 rows x 256)
 
 enum Epilogue : int { EPI_NONE = 0, EPI_GELU = 1, EPI_SWIGLU = 2, EPI_RELU = 3 };
 
@@ -32,8 +43,55 @@ struct GemmParams {
   long long ldc, ldr;
   int M, N, K;
   int m_tiles, n_tiles;
-  int out_f32;  // 0: fp16 output, 1: fp32 output
+  int out_f32;    // 0: fp16 output, 1: fp32 output
+  int sk_tiles;   // number of leading tiles scheduled stream-K (0 = pure data-parallel)
+  float* sk_ws;   // per-CTA fp32 partial-tile slots [gridDim.x][SLOT_ELEMS]
+  int* sk_flags;  // per-CTA arrival counters (zero between launches)
 };
+
+// ------------------------------------------------------------------------------------------------
+// work iterator shared by all three warp roles: first the stream-K share of the split tiles, then whole tiles
+// ------------------------------------------------------------------------------------------------
+struct WorkIter {
+  long long u, u_end;   // this worker's unit range inside the stream-K region
+  int k_blocks;
+  int dp_tile, tiles, workers;
+  DEVI WorkIter(int worker, int n_workers, int tiles_, int sk_tiles, int k_blocks_) {
+    k_blocks = k_blocks_;
+    tiles = tiles_;
+    workers = n_workers;
+    const long long total = (long long)sk_tiles * k_blocks_;
+    u = ((long long)worker * total) / n_workers;
+    u_end = ((long long)(worker + 1) * total) / n_workers;
+    dp_tile = sk_tiles + worker;
+  }
+  DEVI bool next(int& tile, int& kb0, int& kb1) {
+    if (u < u_end) {
+      tile = (int)(u / k_blocks);
+      kb0 = (int)(u - (long long)tile * k_blocks);
+      const long long left = u_end - u;
+      kb1 = (left < (long long)(k_blocks - kb0)) ? kb0 + (int)left : k_blocks;
+      u += kb1 - kb0;
+      return true;
+    }
+    if (dp_tile < tiles) {
+      tile = dp_tile;
+      kb0 = 0;
+      kb1 = k_blocks;
+      dp_tile += workers;
+      return true;
+    }
+    return false;
+  }
+};
+// number of workers after `worker` whose stream-K range starts inside tile `tile` (they hold its later k-ranges)
+DEVI int sk_contributors(int worker, int n_workers, int tile, int sk_tiles, int k_blocks) {
+  const long long total = (long long)sk_tiles * k_blocks;
+  const long long tile_end = (long long)(tile + 1) * k_blocks;
+  int n = 0;
+  while (worker + 1 + n < n_workers && ((long long)(worker + 1 + n) * total) / n_workers < tile_end) ++n;
+  return n;
+}
 
 template <int BN, int STAGES>
 struct SmemLayout {
@@ -44,43 +102,83 @@ struct SmemLayout {
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + alignment slack
 };
 
+// wait-cycle counters (debug/profiling aid, read by stllm_gemm_debug_counters):
+//  [0] producer waiting for a free smem slot   [1] MMA waiting for TMA data   [2] MMA waiting for a free accumulator
+//  [3] epilogue (warp 2) waiting for an accumulator   [4] total kernel cycles of CTA 0's MMA warp   [5] launches
+__device__ unsigned long long g_gemm_prof[8];
+
 DEVI float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 DEVI float silu(float x) { return x / (1.0f + __expf(-x)); }
 
-// One 32-column chunk of one accumulator row: bias / activation / SwiGLU / residual / convert / store.
-// bias and residual are fetched BEFORE the TMEM load is waited on, so their global-load latency overlaps it.
+// ------------------------------------------------------------------------------------------------
+// Epilogue.  One warp owns 32 accumulator rows (its TMEM lane quadrant) x `cols` columns, processed in 32-column
+// chunks with a 2-deep software pipeline: while chunk c is converted and stored, the TMEM load of chunk c+1 and the
+// global loads of its bias / residual / stream-K partials are already in flight.
+// ------------------------------------------------------------------------------------------------
+// partial-tile slot layout (private format, fully coalesced): float4 #q of chunk ch of row r lives at
+//   ((ch * 8 + q) * 128 + r) * 4   -> the 32 lanes of a warp store/load 512 contiguous bytes per instruction.
+DEVI long long slot_off(int chunk_global, int q, int row_in_slot) {
+  return ((long long)(chunk_global * 8 + q) * 128 + row_in_slot) * 4;
+}
+
 template <int EPI>
-DEVI void epilogue_chunk(const GemmParams& p, uint32_t taddr, int row, bool row_ok, int col0) {
-  constexpr int NC = (EPI == EPI_SWIGLU) ? 16 : 32;  // output columns produced by this chunk
+struct ChunkIn {
+  static constexpr int NC = (EPI == EPI_SWIGLU) ? 16 : 32;
+  uint32_t r[32];
+  uint4 bq[4];
+  uint4 rq[NC / 8];
+  bool bias_vec, res_vec;
+};
+
+template <int EPI>
+DEVI void chunk_issue(ChunkIn<EPI>& in, const GemmParams& p, uint32_t taddr, int row, bool row_ok, int col0,
+                      const float* part0, int chunk_global, int row_in_slot) {
+  constexpr int NC = ChunkIn<EPI>::NC;
   const int ocol0 = (EPI == EPI_SWIGLU) ? (col0 >> 1) : col0;
   const int n_out = (EPI == EPI_SWIGLU) ? (p.N >> 1) : p.N;
   const bool active = row_ok && col0 < p.N;
-  const bool full_chunk = (col0 + 32 <= p.N);
-  const bool vec_ok = (ocol0 + NC <= n_out);
-  uint32_t r[32];
-  tmem_ld_32x32b_x32(taddr, r);
-  uint4 bq[4], rq[NC / 8];
-  const bool bias_vec = active && p.bias != nullptr && full_chunk;
+  tmem_ld_32x32b_x32(taddr, in.r);
+  in.bias_vec = active && p.bias != nullptr && (col0 + 32 <= p.N);
   const __half* rp = active && p.residual != nullptr ? p.residual + (long long)row * p.ldr + ocol0 : nullptr;
-  const bool res_vec = rp != nullptr && vec_ok && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0);
-  if (bias_vec) {
+  in.res_vec = rp != nullptr && (ocol0 + NC <= n_out) && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0);
+  if (in.bias_vec) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) bq[q] = __ldg(reinterpret_cast<const uint4*>(p.bias + col0) + q);
+    for (int q = 0; q < 4; ++q) in.bq[q] = __ldg(reinterpret_cast<const uint4*>(p.bias + col0) + q);
   }
-  if (res_vec) {
+  if (in.res_vec) {
 #pragma unroll
-    for (int q = 0; q < NC / 8; ++q) rq[q] = __ldg(reinterpret_cast<const uint4*>(rp) + q);
+    for (int q = 0; q < NC / 8; ++q) in.rq[q] = __ldg(reinterpret_cast<const uint4*>(rp) + q);
   }
-  tmem_ld_wait();
-  if (!active) return;
+}
+
+template <int EPI>
+DEVI void chunk_finish(const ChunkIn<EPI>& in, const GemmParams& p, int row, bool row_ok, int col0, const float* part0,
+                       int n_parts, long long part_stride, int chunk_global, int row_in_slot) {
+  constexpr int NC = ChunkIn<EPI>::NC;
+  const int ocol0 = (EPI == EPI_SWIGLU) ? (col0 >> 1) : col0;
+  const int n_out = (EPI == EPI_SWIGLU) ? (p.N >> 1) : p.N;
+  if (!(row_ok && col0 < p.N)) return;
+  const bool vec_ok = (ocol0 + NC <= n_out);
   float v[32];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(in.r[j]);
+  if (part0 != nullptr) {
+    for (int pi = 0; pi < n_parts; ++pi) {   // stream-K: partial accumulators of the later k-ranges of this tile
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 f = __ldcg(reinterpret_cast<const float4*>(part0 + pi * part_stride + slot_off(chunk_global, q, row_in_slot)));
+        v[4 * q] += f.x;
+        v[4 * q + 1] += f.y;
+        v[4 * q + 2] += f.z;
+        v[4 * q + 3] += f.w;
+      }
+    }
+  }
   if (p.bias != nullptr) {
-    if (bias_vec) {
+    if (in.bias_vec) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const __half2* bh = reinterpret_cast<const __half2*>(&bq[q]);
+        const __half2* bh = reinterpret_cast<const __half2*>(&in.bq[q]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float2 f = __half22float2(bh[j]);
@@ -107,11 +205,12 @@ DEVI void epilogue_chunk(const GemmParams& p, uint32_t taddr, int row, bool row_
 #pragma unroll
     for (int j = 0; j < 16; ++j) v[j] = silu(v[2 * j]) * v[2 * j + 1];
   }
-  if (rp != nullptr) {
-    if (res_vec) {
+  if (p.residual != nullptr) {
+    const __half* rp = p.residual + (long long)row * p.ldr + ocol0;
+    if (in.res_vec) {
 #pragma unroll
       for (int q = 0; q < NC / 8; ++q) {
-        const __half2* bh = reinterpret_cast<const __half2*>(&rq[q]);
+        const __half2* bh = reinterpret_cast<const __half2*>(&in.rq[q]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float2 f = __half22float2(bh[j]);
@@ -156,6 +255,83 @@ DEVI void epilogue_chunk(const GemmParams& p, uint32_t taddr, int row, bool row_
   }
 }
 
+DEVI void dump_store(const uint32_t (&r)[32], float* slot, int chunk_global, int row_in_slot) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q)
+    __stcg(reinterpret_cast<float4*>(slot + slot_off(chunk_global, q, row_in_slot)),
+           make_float4(__uint_as_float(r[4 * q]), __uint_as_float(r[4 * q + 1]), __uint_as_float(r[4 * q + 2]),
+                       __uint_as_float(r[4 * q + 3])));
+}
+
+// Epilogue of one (tile, k-range) segment for one warp: COLS accumulator columns starting at TMEM address t_row.
+//   tail/middle part of a split tile -> raw fp32 dump to this CTA's workspace slot + flag
+//   head of a split tile            -> wait for the contributors' flags, add their partials, fused epilogue
+//   whole tile                      -> fused epilogue
+// `slot_stride_ctas`: distance in CTA slots between consecutive contributors (1 one-CTA, 2 CTA-pair).
+// chunk0_global: index of this warp's first 32-column chunk inside the tile (for the slot layout).
+template <int EPI, int COLS>
+DEVI void epilogue_segment(const GemmParams& p, uint32_t t_row, int chunk0_global, int row, bool row_ok,
+                           int row_in_slot, int col_base, bool is_tail, int n_parts, int slot_stride_ctas, int lane) {
+  static_assert(COLS % 64 == 0, "two chunks per pipeline step");
+  if (is_tail) {
+    float* slot = p.sk_ws + (long long)blockIdx.x * SLOT_ELEMS;
+#pragma unroll 1
+    for (int c = 0; c < COLS; c += 32) {
+      __syncwarp();
+      uint32_t ra[32];
+      tmem_ld_32x32b_x32(t_row + c, ra);
+      tmem_ld_wait();
+      dump_store(ra, slot, chunk0_global + c / 32, row_in_slot);
+    }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) atomicAdd(p.sk_flags + blockIdx.x, 1);
+    return;
+  }
+  if (n_parts > 0) {
+    if (lane == 0) {
+      for (int pi = 0; pi < n_parts; ++pi) {
+        const int* f = p.sk_flags + blockIdx.x + (1 + pi) * slot_stride_ctas;
+        const long long t0 = clock64();
+        int v;
+        do {
+          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+          if (v < NUM_EPI_WARPS && clock64() - t0 > 4000000000LL) {
+            printf("stllm: stream-K flag timeout (cta %d waits for %d)\n", (int)blockIdx.x,
+                   (int)blockIdx.x + (1 + pi) * slot_stride_ctas);
+            __trap();
+          }
+        } while (v < NUM_EPI_WARPS);
+      }
+    }
+    __syncwarp();
+    __threadfence();
+  }
+  const float* part0 = n_parts > 0 ? p.sk_ws + (long long)(blockIdx.x + slot_stride_ctas) * SLOT_ELEMS : nullptr;
+  const long long pstride = (long long)slot_stride_ctas * SLOT_ELEMS;
+  // one 32-column chunk at a time (a 2-deep software pipeline was measured SLOWER: it needs > 168 registers/thread,
+  // the cap at 320 threads/CTA, and spills; profiles/r01_gemm_ab.md)
+#pragma unroll 1
+  for (int c = 0; c < COLS; c += 32) {
+    __syncwarp();
+    ChunkIn<EPI> a;
+    chunk_issue<EPI>(a, p, t_row + c, row, row_ok, col_base + c, part0, chunk0_global + c / 32, row_in_slot);
+    tmem_ld_wait();
+    chunk_finish<EPI>(a, p, row, row_ok, col_base + c, part0, n_parts, pstride, chunk0_global + c / 32, row_in_slot);
+  }
+  __syncwarp();
+  if (n_parts > 0 && lane == 0) {
+    // consumed: the last of the 8 consumer warps resets each contributor flag for the next launch
+    for (int pi = 0; pi < n_parts; ++pi) {
+      int* f = p.sk_flags + blockIdx.x + (1 + pi) * slot_stride_ctas;
+      if (atomicAdd(f, 1) == 2 * NUM_EPI_WARPS - 1) atomicExch(f, 0);
+    }
+  }
+}
+
+// ================================================================================================
+// one-CTA engine: 128 x BN tile per CTA
+// ================================================================================================
 template <int BN, int STAGES, int EPI>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -174,7 +350,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.m_tiles * p.n_tiles;
   const int k_blocks = (p.K + BK - 1) / BK;
-  constexpr uint32_t TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  constexpr uint32_t TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -190,20 +366,25 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc(tmem_base_slot, TMEM_COLS);
+  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();   // everything above (barriers, TMEM, descriptors) overlapped the previous kernel's tail
   const uint32_t tmem_base = *tmem_base_slot;
+  WorkIter it((int)blockIdx.x, (int)gridDim.x, num_tiles, p.sk_tiles, k_blocks);
+  int tile, kb0, kb1;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int m_blk = t % p.m_tiles, n_blk = t / p.m_tiles;
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+      long long w_acc = 0;
+      while (it.next(tile, kb0, kb1)) {
+        const int m_blk = tile % p.m_tiles, n_blk = tile / p.m_tiles;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          w_acc += mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
           mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
@@ -212,6 +393,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
+      atomicAdd(&g_gemm_prof[0], (unsigned long long)w_acc);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -221,12 +403,14 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+      long long w_full = 0, w_acc = 0;
+      const long long t_start = clock64();
+      while (it.next(tile, kb0, kb1)) {
+        w_acc += mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          w_full += mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
           const uint32_t sb = sa + L::A_BYTES;
@@ -234,7 +418,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
           for (int kk = 0; kk < BK / 16; ++kk) {
             const uint64_t da = make_sdesc_k_sw128(sa + kk * 32);
             const uint64_t db = make_sdesc_k_sw128(sb + kk * 32);
-            umma_f16_ss(d_tmem, da, db, idesc, (kb | kk) != 0 ? 1u : 0u);
+            umma_f16_ss(d_tmem, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -242,35 +426,39 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
+      atomicAdd(&g_gemm_prof[1], (unsigned long long)w_full);
+      atomicAdd(&g_gemm_prof[2], (unsigned long long)w_acc);
+      if (blockIdx.x == 0) {
+        atomicAdd(&g_gemm_prof[4], (unsigned long long)(clock64() - t_start));
+        atomicAdd(&g_gemm_prof[5], 1ull);
+      }
     }
   } else {
     // ===================== epilogue warps =====================
     const int e = warp - 2;
-    const int quad = warp & 3;           // TMEM lane quadrant this warp may access
-    const int half_idx = e >> 2;         // which half of the BN columns
+    const int quad = warp & 3;     // TMEM lane quadrant this warp may access
+    const int half_idx = e >> 2;   // which half of the BN columns
     constexpr int COLS_PER_WARP = BN / 2;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int m_blk = t % p.m_tiles, n_blk = t / p.m_tiles;
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
-      tc_fence_after();
-      const int row = m_blk * BM + quad * 32 + lane;
-      const bool row_ok = row < p.M;
+    while (it.next(tile, kb0, kb1)) {
+      const int m_blk = tile % p.m_tiles, n_blk = tile / p.m_tiles;
+      const int row_in_tile = quad * 32 + lane;
+      const int row = m_blk * BM + row_in_tile;
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half_idx * COLS_PER_WARP);
-#pragma unroll 1
-      for (int c = 0; c < COLS_PER_WARP; c += 32) {
-        __syncwarp();
-        const int col0 = n_blk * BN + half_idx * COLS_PER_WARP + c;  // first accumulator column of the chunk
-        epilogue_chunk<EPI>(p, t_row + c, row, row_ok, col0);
-        if (c + 32 >= COLS_PER_WARP) {
-          // all TMEM reads of this warp for this tile are done -> release the accumulator stage
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-        }
+      const bool split_head = (kb0 == 0 && kb1 < k_blocks);
+      const int n_parts = split_head ? sk_contributors((int)blockIdx.x, (int)gridDim.x, tile, p.sk_tiles, k_blocks) : 0;
+      {
+        const long long w = mbar_wait(&tmem_full_bar[acc], acc_phase);
+        if (warp == 2 && lane == 0) atomicAdd(&g_gemm_prof[3], (unsigned long long)w);
       }
+      tc_fence_after();
+      epilogue_segment<EPI, COLS_PER_WARP>(p, t_row, half_idx * (COLS_PER_WARP / 32), row, row < p.M, row_in_tile,
+                                           n_blk * BN + half_idx * COLS_PER_WARP, kb0 > 0, n_parts, 1, lane);
+      // all TMEM reads of this warp for this segment are done -> release the accumulator stage
+      tc_fence_before();
       __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -283,16 +471,14 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   }
 }
 
-// ==============================================================================================
-// CTA-pair variant (cta_group::2): a cluster of 2 CTAs computes a 256 x 256 output tile.
-//   * each CTA TMA-loads its own 128 rows of A and its own 128 rows (= half of the N tile) of W per k-block:
-//     32 KB per CTA per 512-cycle k-block = 64 B/clk of L2->SMEM ingest instead of 96 B/clk for the 128x256
-//     one-CTA tile (ncu: the one-CTA kernel sits at 0.67 tensor-pipe utilisation = 64/96).
+// ================================================================================================
+// CTA-pair engine (cta_group::2): a cluster of 2 CTAs computes a 256 x 256 output tile.
+//   * each CTA TMA-loads its own 128 rows of A and its own 128 rows (= half of the N tile) of W per k-block
 //   * the LEADER CTA's elected thread issues tcgen05.mma.cta_group::2 (M=256, N=256); the hardware reads A/B
 //     from both CTAs' shared memory and writes 128 accumulator rows into each CTA's TMEM.
 //   * barriers: full[s] lives in the leader (both CTAs' TMA complete_tx on it); empty[s] and tmem_full[a] are
 //     multicast-committed to both CTAs; tmem_empty[a] lives in the leader and collects both CTAs' epilogue warps.
-// ==============================================================================================
+// ================================================================================================
 constexpr int BN2 = 256;
 constexpr int STAGES2 = 6;
 struct SmemLayout2 {
@@ -340,22 +526,27 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
     fence_mbar_init();
   }
   if (warp == 1) tmem_alloc_2sm(tmem_base_slot, TMEM_COLS);
+  pdl_launch_dependents();
   tc_fence_before();
   cluster_sync_all();   // barriers of BOTH CTAs initialised before any remote arrive / TMA complete_tx
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_base_slot;
+  WorkIter it(cluster_id, num_clusters, num_tiles, p.sk_tiles, k_blocks);
+  int tile, kb0, kb1;
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-        const int m_blk = t % p.m_tiles, n_blk = t / p.m_tiles;
+      long long w_acc = 0;
+      while (it.next(tile, kb0, kb1)) {
+        const int m_blk = tile % p.m_tiles, n_blk = tile / p.m_tiles;
         const int row_a = m_blk * 256 + (int)cta_rank * 128;
         const int row_b = n_blk * BN2 + (int)cta_rank * (BN2 / 2);
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          w_acc += mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
           if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);  // bytes of both CTAs
@@ -364,6 +555,7 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
           if (++stage == STAGES2) { stage = 0; phase ^= 1; }
         }
       }
+      atomicAdd(&g_gemm_prof[0], (unsigned long long)w_acc);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
@@ -373,12 +565,14 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-        mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+      long long w_full = 0, w_acc = 0;
+      const long long t_start = clock64();
+      while (it.next(tile, kb0, kb1)) {
+        w_acc += mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN2);
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          w_full += mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
           const uint32_t sb = sa + L::A_BYTES;
@@ -386,13 +580,19 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
           for (int kk = 0; kk < BK / 16; ++kk) {
             const uint64_t da = make_sdesc_k_sw128(sa + kk * 32);
             const uint64_t db = make_sdesc_k_sw128(sb + kk * 32);
-            umma_f16_ss_2sm(d_tmem, da, db, idesc, (kb | kk) != 0 ? 1u : 0u);
+            umma_f16_ss_2sm(d_tmem, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
           }
           umma_commit_2sm(&empty_bar[stage], 3);   // frees this smem slot in BOTH CTAs
           if (++stage == STAGES2) { stage = 0; phase ^= 1; }
         }
         umma_commit_2sm(&tmem_full_bar[acc], 3);   // accumulators of both CTAs complete
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      atomicAdd(&g_gemm_prof[1], (unsigned long long)w_full);
+      atomicAdd(&g_gemm_prof[2], (unsigned long long)w_acc);
+      if (blockIdx.x == 0) {
+        atomicAdd(&g_gemm_prof[4], (unsigned long long)(clock64() - t_start));
+        atomicAdd(&g_gemm_prof[5], 1ull);
       }
     }
   } else {
@@ -403,25 +603,26 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
     constexpr int COLS_PER_WARP = BN2 / 2;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int t = cluster_id; t < num_tiles; t += num_clusters) {
-      const int m_blk = t % p.m_tiles, n_blk = t / p.m_tiles;
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
-      tc_fence_after();
-      const int row = m_blk * 256 + (int)cta_rank * 128 + quad * 32 + lane;
-      const bool row_ok = row < p.M;
+    const uint32_t leader_empty0 = mapa_shared(smem_u32(&tmem_empty_bar[0]), 0);
+    const uint32_t leader_empty1 = mapa_shared(smem_u32(&tmem_empty_bar[1]), 0);
+    while (it.next(tile, kb0, kb1)) {
+      const int m_blk = tile % p.m_tiles, n_blk = tile / p.m_tiles;
+      const int row_in_slot = quad * 32 + lane;
+      const int row = m_blk * 256 + (int)cta_rank * 128 + row_in_slot;
       const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN2 + half_idx * COLS_PER_WARP);
-#pragma unroll 1
-      for (int c = 0; c < COLS_PER_WARP; c += 32) {
-        __syncwarp();
-        const int col0 = n_blk * BN2 + half_idx * COLS_PER_WARP + c;
-        epilogue_chunk<EPI>(p, t_row + c, row, row_ok, col0);
-        if (c + 32 >= COLS_PER_WARP) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive_cluster(mapa_shared(smem_u32(&tmem_empty_bar[acc]), 0));  // leader's barrier
-        }
+      const bool split_head = (kb0 == 0 && kb1 < k_blocks);
+      const int n_parts = split_head ? sk_contributors(cluster_id, num_clusters, tile, p.sk_tiles, k_blocks) : 0;
+      {
+        const long long w = mbar_wait(&tmem_full_bar[acc], acc_phase);
+        if (warp == 2 && lane == 0) atomicAdd(&g_gemm_prof[3], (unsigned long long)w);
       }
+      tc_fence_after();
+      // contributors of this CTA's 128 rows are the same-rank CTAs of the following clusters: slot stride 2
+      epilogue_segment<EPI, COLS_PER_WARP>(p, t_row, half_idx * (COLS_PER_WARP / 32), row, row < p.M, row_in_slot,
+                                           n_blk * BN2 + half_idx * COLS_PER_WARP, kb0 > 0, n_parts, 2, lane);
+      tc_fence_before();
       __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(acc == 0 ? leader_empty0 : leader_empty1);  // leader's barrier
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -434,9 +635,9 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
   }
 }
 
-// ----------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
 // host side
-// ----------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -487,8 +688,29 @@ int num_sms() {
   return g_num_sms;
 }
 
+float* g_sk_ws = nullptr;
+int* g_sk_flags = nullptr;
+
+// how many leading tiles to schedule stream-K for `tiles` tiles on `workers` CTAs/clusters (0 = none)
+int choose_sk_tiles(int tiles, int workers, int k_blocks) {
+  // Measured on B200 (profiles/r01_gemm_ab.md): the fix-up of a split last wave costs about what it saves on this
+  // path's shapes, so the hybrid schedule is opt-in (STLLM_GEMM_SK=1) and whole-tile scheduling is the default.
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("STLLM_GEMM_SK");
+    enabled = (e != nullptr && atoi(e) != 0) ? 1 : 0;
+  }
+  if (!enabled || g_sk_ws == nullptr) return 0;
+  const int rem = tiles % workers;
+  if (rem == 0) return 0;
+  if (rem * 100 >= workers * 88) return 0;                 // last wave already >= 88 % full
+  const long long units = (long long)rem * k_blocks;
+  if (units < 6LL * workers) return 0;                     // < 6 k-blocks per worker: fix-up costs more than it saves
+  return rem;
+}
+
 template <int BN, int STAGES, int EPI>
-int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, int allow_sk, cudaStream_t stream) {
   using L = SmemLayout<BN, STAGES>;
   auto kern = gemm_f16_tcgen05_kernel<BN, STAGES, EPI>;
   static bool configured = false;
@@ -497,25 +719,15 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams
     configured = true;
   }
   const int tiles = p.m_tiles * p.n_tiles;
-  const int grid = tiles < num_sms() ? tiles : num_sms();
-  kern<<<grid, NUM_THREADS, L::TOTAL, stream>>>(tmA, tmB, p);
-  STLLM_CHECK_CUDA(cudaGetLastError());
+  const int k_blocks = (p.K + BK - 1) / BK;
+  p.sk_tiles = allow_sk ? choose_sk_tiles(tiles, num_sms(), k_blocks) : 0;
+  const int grid = (p.sk_tiles > 0 || tiles >= num_sms()) ? num_sms() : tiles;
+  STLLM_CHECK_CUDA(stllm_launch(kern, dim3(grid), dim3(NUM_THREADS), L::TOTAL, stream, tmA, tmB, p));
   return STLLM_OK;
 }
 
-template <int BN, int STAGES>
-int dispatch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t s) {
-  switch (epi) {
-    case EPI_NONE: return launch_gemm<BN, STAGES, EPI_NONE>(tmA, tmB, p, s);
-    case EPI_GELU: return launch_gemm<BN, STAGES, EPI_GELU>(tmA, tmB, p, s);
-    case EPI_SWIGLU: return launch_gemm<BN, STAGES, EPI_SWIGLU>(tmA, tmB, p, s);
-    case EPI_RELU: return launch_gemm<BN, STAGES, EPI_RELU>(tmA, tmB, p, s);
-    default: stllm_set_last_error("unknown epilogue %d", epi); return STLLM_ERR_BAD_ARG;
-  }
-}
-
 template <int EPI>
-int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, int allow_sk, cudaStream_t stream) {
   auto kern = gemm_f16_tcgen05_2cta_kernel<EPI>;
   static bool configured = false;
   if (!configured) {
@@ -523,25 +735,74 @@ int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmP
     configured = true;
   }
   const int tiles = p.m_tiles * p.n_tiles;
+  const int k_blocks = (p.K + BK - 1) / BK;
   int clusters = num_sms() / 2;
-  if (tiles < clusters) clusters = tiles;
-  kern<<<2 * clusters, NUM_THREADS, SmemLayout2::TOTAL, stream>>>(tmA, tmB, p);
-  STLLM_CHECK_CUDA(cudaGetLastError());
+  p.sk_tiles = allow_sk ? choose_sk_tiles(tiles, clusters, k_blocks) : 0;
+  if (p.sk_tiles == 0 && tiles < clusters) clusters = tiles;
+  STLLM_CHECK_CUDA(stllm_launch(kern, dim3(2 * clusters), dim3(NUM_THREADS), SmemLayout2::TOTAL, stream, tmA, tmB, p));
   return STLLM_OK;
 }
 
-int dispatch_epi_2cta(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t s) {
+template <int BN, int STAGES>
+int dispatch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int sk, cudaStream_t s) {
   switch (epi) {
-    case EPI_NONE: return launch_gemm_2cta<EPI_NONE>(tmA, tmB, p, s);
-    case EPI_GELU: return launch_gemm_2cta<EPI_GELU>(tmA, tmB, p, s);
-    case EPI_SWIGLU: return launch_gemm_2cta<EPI_SWIGLU>(tmA, tmB, p, s);
-    case EPI_RELU: return launch_gemm_2cta<EPI_RELU>(tmA, tmB, p, s);
+    case EPI_NONE: return launch_gemm<BN, STAGES, EPI_NONE>(tmA, tmB, p, sk, s);
+    case EPI_GELU: return launch_gemm<BN, STAGES, EPI_GELU>(tmA, tmB, p, sk, s);
+    case EPI_SWIGLU: return launch_gemm<BN, STAGES, EPI_SWIGLU>(tmA, tmB, p, sk, s);
+    case EPI_RELU: return launch_gemm<BN, STAGES, EPI_RELU>(tmA, tmB, p, sk, s);
+    default: stllm_set_last_error("unknown epilogue %d", epi); return STLLM_ERR_BAD_ARG;
+  }
+}
+int dispatch_epi_2cta(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int sk, cudaStream_t s) {
+  switch (epi) {
+    case EPI_NONE: return launch_gemm_2cta<EPI_NONE>(tmA, tmB, p, sk, s);
+    case EPI_GELU: return launch_gemm_2cta<EPI_GELU>(tmA, tmB, p, sk, s);
+    case EPI_SWIGLU: return launch_gemm_2cta<EPI_SWIGLU>(tmA, tmB, p, sk, s);
+    case EPI_RELU: return launch_gemm_2cta<EPI_RELU>(tmA, tmB, p, sk, s);
     default: stllm_set_last_error("unknown epilogue %d", epi); return STLLM_ERR_BAD_ARG;
   }
 }
 
+// Cost model (units: k-block times of a 128x256 one-CTA tile).  Measured on B200 (profiles/r01_gemm_ab.log): a
+// CTA-pair tile runs ~11 % faster per FLOP than a one-CTA tile, and a stream-K'ed last wave costs its fill fraction
+// plus ~1.5 k-block times of fix-up.
+double sched_cost(int tiles, int workers, int k_blocks, double tile_cost, bool sk_possible) {
+  const int full = tiles / workers, rem = tiles % workers;
+  double waves = full;
+  if (rem > 0) {
+    const bool sk = sk_possible && choose_sk_tiles(tiles, workers, k_blocks) > 0;
+    waves += sk ? ((double)rem / workers + 1.5 / k_blocks) : 1.0;
+  }
+  return waves * k_blocks * tile_cost;
+}
+
 }  // namespace
 
+// Workspace for the stream-K part of the scheduler: >= stllm_gemm_workspace_bytes() bytes of ZEROED device memory,
+// owned by the caller and valid until replaced.  Without it the GEMM schedules whole tiles only.
+extern "C" long long stllm_gemm_workspace_bytes(void) {
+  return (long long)num_sms() * SLOT_ELEMS * 4 + 4096;
+}
+extern "C" int stllm_set_gemm_workspace(void* ptr, long long bytes) {
+  if (ptr == nullptr) { g_sk_ws = nullptr; g_sk_flags = nullptr; return STLLM_OK; }
+  STLLM_CHECK_ARG(bytes >= stllm_gemm_workspace_bytes() && ((uintptr_t)ptr & 255) == 0);
+  g_sk_flags = reinterpret_cast<int*>(ptr);                               // first 4 KB: flags
+  g_sk_ws = reinterpret_cast<float*>(reinterpret_cast<char*>(ptr) + 4096);
+  return STLLM_OK;
+}
+
+// debug: copy (and reset) the 8 wait-cycle counters (see g_gemm_prof); synchronises the device
+extern "C" int stllm_gemm_debug_counters(unsigned long long* out8) {
+  STLLM_CHECK_ARG(out8 != nullptr);
+  STLLM_CHECK_CUDA(cudaDeviceSynchronize());
+  STLLM_CHECK_CUDA(cudaMemcpyFromSymbol(out8, g_gemm_prof, 8 * sizeof(unsigned long long)));
+  unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  STLLM_CHECK_CUDA(cudaMemcpyToSymbol(g_gemm_prof, z, sizeof(z)));
+  return STLLM_OK;
+}
+
+// tile_n: 0 = auto (cost model); 128 / 256 = one-CTA tiles; 512 = CTA-pair tiles; add 1 (129/257/513) to forbid the
+// stream-K treatment of the last wave (pure data-parallel schedule, for A/B measurements).
 extern "C" int stllm_gemm_f16(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc,
                               int M, int N, int K, const void* bias, const void* residual, long long ldr,
                               int epilogue, int out_f32, int tile_n, void* stream) {
@@ -555,12 +816,28 @@ extern "C" int stllm_gemm_f16(const void* A, long long lda, const void* W, long 
   STLLM_CHECK_ARG(residual == nullptr || ldr >= (epilogue == EPI_SWIGLU ? N / 2 : N));
   int bn = tile_n;
   if (bn == 0) {
-    // heuristic: wide tiles when there are enough of them to fill the machine, else narrower tiles
-    const long long m_tiles = (M + BM - 1) / BM;
-    const long long t256 = m_tiles * ((N + 255) / 256);
-    bn = (t256 >= num_sms()) ? 256 : 128;
+    static int forced = -1;  // experiment knob: STLLM_GEMM_TILE=128|256|512 (+1: no stream-K) forces a configuration
+    if (forced < 0) {
+      const char* e = getenv("STLLM_GEMM_TILE");
+      forced = e ? atoi(e) : 0;
+    }
+    bn = forced;
   }
-  STLLM_CHECK_ARG(bn == 128 || bn == 256 || bn == 512);   // 512 = CTA-pair kernel (256 x 256 tile per 2 SMs)
+  int allow_sk = 1;
+  if (bn & 1) { allow_sk = 0; bn -= 1; }
+  const int k_blocks = (K + BK - 1) / BK;
+  if (bn == 0) {
+    const int t1 = ((M + 127) / 128) * ((N + 255) / 256);
+    const int t2 = ((M + 255) / 256) * ((N + 255) / 256);
+    const double c1 = sched_cost(t1, num_sms(), k_blocks, 1.0, true);
+    const double c2 = sched_cost(t2, num_sms() / 2, k_blocks, 0.89, true);
+    bn = (M > 128 && c2 < c1 * 0.97) ? 512 : 256;
+    if (bn == 256 && t1 < num_sms() && choose_sk_tiles(t1, num_sms(), k_blocks) == 0) {
+      // too few 256-wide tiles and stream-K not applicable: narrower tiles fill more SMs
+      if (((M + 127) / 128) * ((N + 127) / 128) > t1) bn = 128;
+    }
+  }
+  STLLM_CHECK_ARG(bn == 128 || bn == 256 || bn == 512);
   CUtensorMap tmA, tmB;
   int rc = make_tmap(&tmA, A, M, K, lda, BM);
   if (rc != STLLM_OK) return rc;
@@ -575,15 +852,18 @@ extern "C" int stllm_gemm_f16(const void* A, long long lda, const void* W, long 
   p.M = M;
   p.N = N;
   p.K = K;
-  p.m_tiles = (M + BM - 1) / BM;
-  p.n_tiles = (N + bn - 1) / bn;
   p.out_f32 = out_f32;
+  p.sk_tiles = 0;
+  p.sk_ws = g_sk_ws;
+  p.sk_flags = g_sk_flags;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   if (bn == 512) {
     p.m_tiles = (M + 255) / 256;
     p.n_tiles = (N + 255) / 256;
-    return dispatch_epi_2cta(epilogue, tmA, tmB, p, s);
+    return dispatch_epi_2cta(epilogue, tmA, tmB, p, allow_sk, s);
   }
-  if (bn == 256) return dispatch_epi<256, 4>(epilogue, tmA, tmB, p, s);
-  return dispatch_epi<128, 6>(epilogue, tmA, tmB, p, s);
+  p.m_tiles = (M + BM - 1) / BM;
+  p.n_tiles = (N + bn - 1) / bn;
+  if (bn == 256) return dispatch_epi<256, 4>(epilogue, tmA, tmB, p, allow_sk, s);
+  return dispatch_epi<128, 6>(epilogue, tmA, tmB, p, allow_sk, s);
 }

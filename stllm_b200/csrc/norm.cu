@@ -13,6 +13,8 @@ __global__ void __launch_bounds__(ROWS_PER_CTA * 32)
 layernorm_f16_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict__ y, long long ldy,
                      const float* __restrict__ gamma, const float* __restrict__ beta, int rows, int cols,
                      float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -81,6 +83,8 @@ layernorm_f16_kernel(const __half* __restrict__ x, long long ldx, __half* __rest
 __global__ void __launch_bounds__(ROWS_PER_CTA * 32)
 rmsnorm_f16_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict__ y, long long ldy,
                    const __half* __restrict__ w, int rows, int cols, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x * ROWS_PER_CTA + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -128,6 +132,8 @@ __global__ void __launch_bounds__(256)
 layernorm_f16_regs_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict__ y, long long ldy,
                           const float* __restrict__ gamma, const float* __restrict__ beta, int rows, int cols,
                           float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -187,6 +193,8 @@ template <int VPT>
 __global__ void __launch_bounds__(256)
 rmsnorm_f16_block_kernel(const __half* __restrict__ x, long long ldx, __half* __restrict__ y, long long ldy,
                          const __half* __restrict__ w, int rows, int cols, float eps) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int row = blockIdx.x;
   const uint4* xr = reinterpret_cast<const uint4*>(x + (long long)row * ldx);
   uint4* yr = reinterpret_cast<uint4*>(y + (long long)row * ldy);
@@ -241,18 +249,14 @@ extern "C" int stllm_layernorm_f16(const void* x, long long ldx, void* y, long l
   STLLM_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0);
   STLLM_CHECK_ARG(((uintptr_t)gamma & 15) == 0 && ((uintptr_t)beta & 15) == 0);
   if (cols % 8 == 0 && cols <= 32 * 8 * 6) {
-    layernorm_f16_regs_kernel<6><<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
-        (const __half*)x, ldx, (__half*)y, ldy, gamma, beta, rows, cols, eps);
+    STLLM_CHECK_CUDA(stllm_launch(layernorm_f16_regs_kernel<6>, dim3((rows + 7) / 8), dim3(256), 0, (cudaStream_t)stream, (const __half*)x, ldx, (__half*)y, ldy, gamma, beta, rows, cols, eps));
   } else if (cols % 8 == 0 && cols <= 32 * 8 * 16) {
-    layernorm_f16_regs_kernel<16><<<(rows + 7) / 8, 256, 0, (cudaStream_t)stream>>>(
-        (const __half*)x, ldx, (__half*)y, ldy, gamma, beta, rows, cols, eps);
+    STLLM_CHECK_CUDA(stllm_launch(layernorm_f16_regs_kernel<16>, dim3((rows + 7) / 8), dim3(256), 0, (cudaStream_t)stream, (const __half*)x, ldx, (__half*)y, ldy, gamma, beta, rows, cols, eps));
   } else {
     const int grid = (rows + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
-    layernorm_f16_kernel<<<grid, ROWS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(
-        (const __half*)x, ldx, (__half*)y, ldy, gamma, beta, rows, cols, eps);
+    STLLM_CHECK_CUDA(stllm_launch(layernorm_f16_kernel, dim3(grid), dim3(ROWS_PER_CTA * 32), 0, (cudaStream_t)stream, (const __half*)x, ldx, (__half*)y, ldy, gamma, beta, rows, cols, eps));
   }
-  STLLM_CHECK_CUDA(cudaGetLastError());
-  return STLLM_OK;
+    return STLLM_OK;
 }
 
 extern "C" int stllm_rmsnorm_f16(const void* x, long long ldx, void* y, long long ldy, const void* weight, int rows,
@@ -261,13 +265,10 @@ extern "C" int stllm_rmsnorm_f16(const void* x, long long ldx, void* y, long lon
   STLLM_CHECK_ARG(ldx % 8 == 0 && ldy % 8 == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 &&
                   ((uintptr_t)weight & 15) == 0);
   if (cols % 8 == 0 && cols >= 2048 && cols <= 256 * 8 * 2) {
-    rmsnorm_f16_block_kernel<2><<<rows, 256, 0, (cudaStream_t)stream>>>(
-        (const __half*)x, ldx, (__half*)y, ldy, (const __half*)weight, rows, cols, eps);
+    STLLM_CHECK_CUDA(stllm_launch(rmsnorm_f16_block_kernel<2>, dim3(rows), dim3(256), 0, (cudaStream_t)stream, (const __half*)x, ldx, (__half*)y, ldy, (const __half*)weight, rows, cols, eps));
   } else {
     const int grid = (rows + ROWS_PER_CTA - 1) / ROWS_PER_CTA;
-    rmsnorm_f16_kernel<<<grid, ROWS_PER_CTA * 32, 0, (cudaStream_t)stream>>>(
-        (const __half*)x, ldx, (__half*)y, ldy, (const __half*)weight, rows, cols, eps);
+    STLLM_CHECK_CUDA(stllm_launch(rmsnorm_f16_kernel, dim3(grid), dim3(ROWS_PER_CTA * 32), 0, (cudaStream_t)stream, (const __half*)x, ldx, (__half*)y, ldy, (const __half*)weight, rows, cols, eps));
   }
-  STLLM_CHECK_CUDA(cudaGetLastError());
-  return STLLM_OK;
+    return STLLM_OK;
 }

@@ -26,6 +26,19 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
 
 
+_gemm_ws = None
+
+
+def _ensure_gemm_workspace(device):
+    """register the (zeroed) stream-K workspace once; torch owns the memory"""
+    global _gemm_ws
+    if _gemm_ws is None or _gemm_ws.device != device:
+        lib = _lib.load()
+        n = int(lib.stllm_gemm_workspace_bytes())
+        _gemm_ws = torch.zeros(n, dtype=torch.uint8, device=device)
+        _lib.check(lib.stllm_set_gemm_workspace(ctypes.c_void_p(_gemm_ws.data_ptr()), n), "stllm_set_gemm_workspace")
+
+
 def _need_cuda(*ts):
     for t in ts:
         if t is not None and not t.is_cuda:
@@ -49,6 +62,7 @@ def gemm(a, w, bias=None, residual=None, epilogue=EPI_NONE, out=None, out_dtype=
     global launch_count
     _need_cuda(a, w, bias, residual, out)
     assert a.dtype == torch.float16 and w.dtype == torch.float16
+    _ensure_gemm_workspace(a.device)
     K = a.shape[-1]
     N = w.shape[0]
     assert w.shape[1] == K, (a.shape, w.shape)
