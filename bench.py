@@ -297,12 +297,12 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step_device()
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
+    if world > 1:
+        dist.barrier()          # all ranks enter the timed region together (after rank 0 started the clock sampler)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
