@@ -13,9 +13,9 @@
 
 namespace {
 
-constexpr int BQ = 64;    // query rows per CTA (4 warps x 16)
 constexpr int BKV = 64;   // keys per smem tile
-constexpr int ATT_THREADS = 128;
+// BQ (template): query rows per CTA = 16 per warp.  64 for most shapes; 96 for the ViT (S = 257 = 96 + 96 + 65: three
+// CTAs per (frame, head) instead of five with one of them holding a single row).
 
 struct AttnParams {
   const __half* q;
@@ -57,9 +57,10 @@ DEVI void mma_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t
 }
 
 // DH: real head dim (multiple of 8); DP: padded to a multiple of 16
-template <int DH, int DP>
-__global__ void __launch_bounds__(ATT_THREADS)
+template <int DH, int DP, int BQ>
+__global__ void __launch_bounds__(BQ * 2)
 attention_f16_kernel(const AttnParams p) {
+  constexpr int ATT_THREADS = BQ * 2;
   constexpr int LD = DP + 8;            // smem row stride in halves (conflict-free ldmatrix)
   constexpr int CHUNKS = DH / 8;        // 16-byte chunks per row actually loaded
   constexpr int KSTEPS = DP / 16;       // k-steps of QK^T
@@ -290,11 +291,12 @@ attention_f16_kernel(const AttnParams p) {
   }
 }
 
-template <int DH, int DP>
+template <int DH, int DP, int BQ>
 int launch_attention(const AttnParams& p, cudaStream_t stream) {
   constexpr int LD = DP + 8;
   constexpr int SMEM = (BQ + 4 * BKV) * LD * 2;
-  auto kern = attention_f16_kernel<DH, DP>;
+  constexpr int ATT_THREADS = BQ * 2;
+  auto kern = attention_f16_kernel<DH, DP, BQ>;
   static bool configured = false;
   if (!configured) {
     STLLM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
@@ -332,9 +334,12 @@ extern "C" int stllm_attention_f16(const void* q, const void* k, const void* v, 
   p.scale = scale; p.q_prescale = q_prescale; p.mask_value = mask_value; p.causal = causal;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   switch (D) {
-    case 64: return launch_attention<64, 64>(p, s);
-    case 88: return launch_attention<88, 96>(p, s);
-    case 128: return launch_attention<128, 128>(p, s);
+    case 64: return launch_attention<64, 64, 64>(p, s);
+    case 88:
+      // pick the row tile that wastes fewer 16-row groups (257 rows: 3 x 96 beats 5 x 64)
+      if (((Sq + 95) / 96) * 6 < ((Sq + 63) / 64) * 4 + 1) return launch_attention<88, 96, 96>(p, s);
+      return launch_attention<88, 96, 64>(p, s);
+    case 128: return launch_attention<128, 128, 64>(p, s);
     default:
       stllm_set_last_error("attention: unsupported head_dim %d (supported: 64, 88, 128)", D);
       return STLLM_ERR_UNSUPPORTED;

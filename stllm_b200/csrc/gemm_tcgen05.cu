@@ -107,7 +107,20 @@ struct SmemLayout {
 //  [3] epilogue (warp 2) waiting for an accumulator   [4] total kernel cycles of CTA 0's MMA warp   [5] launches
 __device__ unsigned long long g_gemm_prof[8];
 
-DEVI float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// GELU(erf) (nn.GELU, eva_vit.py:50 / Qformer.py:359).  erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below the
+// fp16 output rounding) with MUFU rcp/ex2: ~14 instructions instead of erff()'s ~30 -- the erf epilogue of ViT fc1 is
+// instruction-issue bound (profiles/r01_gemm_ab.md).
+DEVI float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  const float erf_abs = fmaf(-poly, __expf(-z * z), 1.0f);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
 DEVI float silu(float x) { return x / (1.0f + __expf(-x)); }
 
 // ------------------------------------------------------------------------------------------------
