@@ -161,6 +161,13 @@ def main():
     gemm_case(32, 1024, 4096, epi=ops.EPI_RELU, bias=True)
     gemm_case(1, 4096, 4096)                       # decode-like M=1
     gemm_case(300, 768, 768, bias=True, lda_pad=8) # strided A (ld != K)
+    # --- 128 x 64 tiles (small-M GEMMs of the Q-Former) ---
+    gemm_case(512, 768, 3072, bias=True, residual=True, tile_n=64)
+    gemm_case(512, 2304, 768, bias=True, tile_n=64)
+    gemm_case(512, 3072, 768, epi=ops.EPI_GELU, bias=True, tile_n=64)
+    gemm_case(100, 200, 72, tile_n=64)
+    gemm_case(32, 1024, 4096, epi=ops.EPI_RELU, bias=True, tile_n=64)
+    gemm_case(64, 1000, 512, epi=ops.EPI_SWIGLU, tile_n=64)
     # --- hybrid stream-K schedule (default for 256/512) vs pure data-parallel (257/513) ---
     for tn in (256, 512, 128):
         gemm_case(4112, 1408, 6144, bias=True, residual=True, tile_n=tn)

@@ -285,7 +285,6 @@ DEVI void dump_store(const uint32_t (&r)[32], float* slot, int chunk_global, int
 template <int EPI, int COLS>
 DEVI void epilogue_segment(const GemmParams& p, uint32_t t_row, int chunk0_global, int row, bool row_ok,
                            int row_in_slot, int col_base, bool is_tail, int n_parts, int slot_stride_ctas, int lane) {
-  static_assert(COLS % 64 == 0, "two chunks per pipeline step");
   if (is_tail) {
     float* slot = p.sk_ws + (long long)blockIdx.x * SLOT_ELEMS;
 #pragma unroll 1
@@ -840,17 +839,22 @@ extern "C" int stllm_gemm_f16(const void* A, long long lda, const void* W, long 
   if (bn & 1) { allow_sk = 0; bn -= 1; }
   const int k_blocks = (K + BK - 1) / BK;
   if (bn == 0) {
-    const int t1 = ((M + 127) / 128) * ((N + 255) / 256);
+    // cost per k-block of one tile = max(MMA cycles, operand ingest at ~64 B/clk), relative to the 128x256 tile:
+    //   128x256: max(512, 768) -> 1.00   128x128: max(256, 512) -> 0.67   128x64: max(128, 384) -> 0.50
+    //   CTA pair 256x256 (per 128 rows): 512 cycles, measured 0.89 of the one-CTA tile per FLOP
+    const int mt = (M + 127) / 128;
+    const int t256 = mt * ((N + 255) / 256), t128 = mt * ((N + 127) / 128), t64 = mt * ((N + 63) / 64);
     const int t2 = ((M + 255) / 256) * ((N + 255) / 256);
-    const double c1 = sched_cost(t1, num_sms(), k_blocks, 1.0, true);
+    double best = sched_cost(t256, num_sms(), k_blocks, 1.0, true);
+    bn = 256;
     const double c2 = sched_cost(t2, num_sms() / 2, k_blocks, 0.89, true);
-    bn = (M > 128 && c2 < c1 * 0.97) ? 512 : 256;
-    if (bn == 256 && t1 < num_sms() && choose_sk_tiles(t1, num_sms(), k_blocks) == 0) {
-      // too few 256-wide tiles and stream-K not applicable: narrower tiles fill more SMs
-      if (((M + 127) / 128) * ((N + 127) / 128) > t1) bn = 128;
-    }
+    if (M > 128 && c2 < best * 0.97) { best = c2; bn = 512; }
+    const double c128 = sched_cost(t128, num_sms(), k_blocks, 0.67, false);
+    if (c128 < best * 0.9) { best = c128; bn = 128; }
+    const double c64 = sched_cost(t64, num_sms(), k_blocks, 0.50, false);
+    if (c64 < best * 0.9) { best = c64; bn = 64; }
   }
-  STLLM_CHECK_ARG(bn == 128 || bn == 256 || bn == 512);
+  STLLM_CHECK_ARG(bn == 64 || bn == 128 || bn == 256 || bn == 512);
   CUtensorMap tmA, tmB;
   int rc = make_tmap(&tmA, A, M, K, lda, BM);
   if (rc != STLLM_OK) return rc;
@@ -878,5 +882,6 @@ extern "C" int stllm_gemm_f16(const void* A, long long lda, const void* W, long 
   p.m_tiles = (M + BM - 1) / BM;
   p.n_tiles = (N + bn - 1) / bn;
   if (bn == 256) return dispatch_epi<256, 4>(epilogue, tmA, tmB, p, allow_sk, s);
-  return dispatch_epi<128, 6>(epilogue, tmA, tmB, p, allow_sk, s);
+  if (bn == 128) return dispatch_epi<128, 6>(epilogue, tmA, tmB, p, allow_sk, s);
+  return dispatch_epi<64, 8>(epilogue, tmA, tmB, p, allow_sk, s);
 }
