@@ -14,8 +14,7 @@
 namespace {
 
 constexpr int BKV = 64;   // keys per smem tile
-// BQ (template): query rows per CTA = 16 per warp.  64 for most shapes; 96 for the ViT (S = 257 = 96 + 96 + 65: three
-// CTAs per (frame, head) instead of five with one of them holding a single row).
+// BQ (template): query rows per CTA = 16 per warp; 64 everywhere (see the note at the dispatch).
 
 struct AttnParams {
   const __half* q;
@@ -336,8 +335,8 @@ extern "C" int stllm_attention_f16(const void* q, const void* k, const void* v, 
   switch (D) {
     case 64: return launch_attention<64, 64, 64>(p, s);
     case 88:
-      // pick the row tile that wastes fewer 16-row groups (257 rows: 3 x 96 beats 5 x 64)
-      if (((Sq + 95) / 96) * 6 < ((Sq + 63) / 64) * 4 + 1) return launch_attention<88, 96, 96>(p, s);
+      // BQ = 96 (3 CTAs per (frame, head) at S = 257 instead of 5) was measured SLOWER: 168 registers x 192 threads
+      // limits occupancy to 2 CTAs/SM (ncu: 84.8 us vs 63.7 us per ViT layer, profiles/r01_ncu_summary.md)
       return launch_attention<88, 96, 64>(p, s);
     case 128: return launch_attention<128, 128, 64>(p, s);
     default:
