@@ -241,6 +241,8 @@ def main():
         print(json.dumps(line))
         return 0
 
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the single JSON line (NCCL prints its version banner there)
     import torch
     import torch.distributed as dist
     from stllm_b200 import ops
