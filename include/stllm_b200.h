@@ -66,6 +66,10 @@ int stllm_attention_f16(const void* q, const void* k, const void* v, void* out, 
                         const long long* o_strides, float scale, float q_prescale, int causal,
                         const void* key_mask, float mask_value, void* stream);
 
+/* A/B switch (default 1): route ViT / Llama prefill attention (D in {88,128}, Sq >= 32, heads contiguous) to the
+ * tcgen05 kernel; 0 = always the mma.sync kernel. */
+int stllm_set_attention_tc(int on);
+
 /* y = LayerNorm(x) with fp32 statistics; gamma/beta fp32.  eva_vit.py:157,163; blip2.py:103-109; Qformer.py:65,
  * 282,366; st_llm.py:39. */
 int stllm_layernorm_f16(const void* x, long long ldx, void* y, long long ldy, const float* gamma, const float* beta,

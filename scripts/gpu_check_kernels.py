@@ -195,15 +195,24 @@ def main():
     gemm_case(576, 22016, 4096, epi=ops.EPI_SWIGLU, tile_n=512)
     gemm_case(576, 4096, 11008, residual=True, tile_n=512)
     gemm_case(64, 32001, 4096, out_f32=True, tile_n=512)
-    # --- attention ---
-    attn_case(2, 16, 257, 257, 88, prescale=True, packed=True)   # ViT
-    attn_case(3, 12, 32, 32, 64)                                  # Q-Former self (no text)
-    attn_case(3, 12, 44, 44, 64, mask=True)                       # Q-Former self with text + padding mask
-    attn_case(3, 12, 32, 257, 64)                                 # Q-Former cross
-    attn_case(1, 32, 576, 576, 128, causal=True, packed=True)     # Llama prefill
-    attn_case(2, 32, 320, 320, 128, causal=True, mask=True)       # Llama prefill with right padding
-    attn_case(2, 32, 1, 300, 128, causal=True)                    # decode step
-    attn_case(1, 4, 130, 130, 128, causal=True)
+    # --- attention: tcgen05 kernel (ViT / Llama prefill shapes) and mma.sync kernel on the same cases ---
+    from stllm_b200 import _lib as _L
+    for tc in (1, 0):
+        _L.load().stllm_set_attention_tc(tc)
+        print(f"-- attention kernels with tcgen05 path {'ON' if tc else 'OFF'}")
+        attn_case(2, 16, 257, 257, 88, prescale=True, packed=True)   # ViT
+        attn_case(16, 16, 257, 257, 88, prescale=True, packed=True)  # ViT, config-2 size
+        attn_case(3, 12, 32, 32, 64)                                  # Q-Former self (no text)
+        attn_case(3, 12, 44, 44, 64, mask=True)                       # Q-Former self with text + padding mask
+        attn_case(3, 12, 32, 257, 64)                                 # Q-Former cross
+        attn_case(1, 32, 576, 576, 128, causal=True, packed=True)     # Llama prefill
+        attn_case(2, 32, 320, 320, 128, causal=True, mask=True)       # Llama prefill with right padding
+        attn_case(2, 32, 1, 300, 128, causal=True)                    # decode step
+        attn_case(1, 4, 130, 130, 128, causal=True)
+        attn_case(1, 2, 100, 300, 128, causal=True)                   # Sq != Skv (cached prefix)
+        attn_case(2, 3, 257, 257, 88)                                 # non-packed, no prescale
+        attn_case(1, 32, 2048, 2048, 128, causal=True, packed=True)   # max_position_embeddings
+    _L.load().stllm_set_attention_tc(1)
     # --- norms ---
     x = torch.randn(4112, 1408, device=dev, dtype=torch.float16) * 3 + 0.5
     g = torch.randn(1408, device=dev) * 0.2 + 1
@@ -271,6 +280,29 @@ def main():
         print("  FAILED:", f)
     # --- timings ---
     if "--no-time" not in sys.argv:
+        for (B_, H_, S_, D_, causal_, pre_) in ((16, 16, 257, 88, False, True), (1, 32, 576, 128, True, False),
+                                                (8, 32, 576, 128, True, False)):
+            qkv = torch.randn(B_, S_, 3, H_, D_, device=dev, dtype=torch.float16)
+            q, k, v = qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2]
+            out = torch.empty(B_, S_, H_, D_, device=dev, dtype=torch.float16)
+            res = {}
+            for tc in (1, 0, 1, 0):
+                _L.load().stllm_set_attention_tc(tc)
+                fn = lambda: ops.attention(q, k, v, 1.0 if pre_ else D_ ** -0.5, causal=causal_,
+                                           q_prescale=D_ ** -0.5 if pre_ else 0.0, out=out)
+                for _ in range(3):
+                    fn()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(20):
+                    fn()
+                e1.record()
+                torch.cuda.synchronize()
+                res.setdefault(tc, []).append(e0.elapsed_time(e1) / 20 * 1e3)
+            fl = 4.0 * B_ * H_ * S_ * S_ * D_ * (0.5 if causal_ else 1.0)
+            print(f"TIME attn B={B_} H={H_} S={S_} D={D_} causal={int(causal_)}: tcgen05 {min(res[1]):.1f}us "
+                  f"({fl/min(res[1])/1e6:.0f} TF)  mma.sync {min(res[0]):.1f}us ({fl/min(res[0])/1e6:.0f} TF)", flush=True)
+        _L.load().stllm_set_attention_tc(1)
         time_gemm(4112, 4224, 1408, bias=True)                       # ViT qkv
         time_gemm(4112, 1408, 1408, bias=True, residual=True)        # ViT proj
         time_gemm(4112, 6144, 1408, ops.EPI_GELU, bias=True)         # ViT fc1

@@ -308,6 +308,11 @@ int launch_attention(const AttnParams& p, cudaStream_t stream) {
 
 }  // namespace
 
+int stllm_attention_tc_try(const void* q, const void* k, const void* v, void* out, int B, int H, int Sq, int Skv, int D,
+                           const long long* qs, const long long* ks, const long long* vs, const long long* os,
+                           float scale, float q_prescale, int causal, const void* key_mask, float mask_value,
+                           cudaStream_t stream);
+
 extern "C" int stllm_attention_f16(const void* q, const void* k, const void* v, void* out, int B, int H, int Sq,
                                    int Skv, int D, const long long* q_strides, const long long* k_strides,
                                    const long long* v_strides, const long long* o_strides, float scale,
@@ -332,6 +337,12 @@ extern "C" int stllm_attention_f16(const void* q, const void* k, const void* v, 
   p.B = B; p.H = H; p.Sq = Sq; p.Skv = Skv;
   p.scale = scale; p.q_prescale = q_prescale; p.mask_value = mask_value; p.causal = causal;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  {
+    // prefill shapes of the ViT / Llama go to the tcgen05 kernel (attention_tc.cu); everything else stays here
+    const int rc_tc = stllm_attention_tc_try(q, k, v, out, B, H, Sq, Skv, D, q_strides, k_strides, v_strides, o_strides,
+                                             scale, q_prescale, causal, key_mask, mask_value, s);
+    if (rc_tc != STLLM_ERR_UNSUPPORTED) return rc_tc;
+  }
   switch (D) {
     case 64: return launch_attention<64, 64, 64>(p, s);
     case 88:

@@ -1,0 +1,474 @@
+// tcgen05 / TMEM attention for the two prefill shapes that carry the attention time of the path:
+//   * EVA-ViT self-attention: head_dim 88 (contracted as 96), seq 257, q pre-scaled in fp16   eva_vit.py:118-148
+//   * Llama causal self-attention: head_dim 128, key-padding mask, fp32 softmax              modeling_llama_mem.py:172-248
+// (decode steps, the Q-Former's 32-query attention and every other shape stay on attention.cu.)
+//
+// One CTA = one (batch, head, 128-query tile); 192 threads:
+//   warp 0     : TMA producer - Q once, then K/V tiles of 128 keys through a 2-stage ring (3-D tensor maps over the
+//                packed q|k|v activations: {feature, token, batch}; 128B swizzle; two 64-column boxes per operand)
+//   warp 1     : TMEM allocator + MMA issuer:  S = Q K^T (tcgen05.mma, fp32 S in TMEM columns 0..127), then
+//                O += P V with P read from shared memory (K-major) and V used in place as an MN-major B operand
+//                (no transpose of V anywhere), O in TMEM columns 128..255
+//   warps 2..5 : softmax, one thread per query row: tcgen05.ld the S row, scale/mask, online max/sum in fp32, rescale
+//                O in TMEM (tcgen05.ld/st) when the running max moved, write P (fp16) into the swizzled smem tile,
+//                finally O / l -> fp16 -> global.
+// head_dim 88: the second 64-column box of a head spills into the next head's columns; those 8 extra contraction
+// columns (88..95) are zeroed in the Q tile (so whatever K holds there is multiplied by 0) and the 8 extra output
+// columns of P V are simply not stored.
+#include <stdlib.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int TQ = 128;    // query rows per CTA
+constexpr int TKV = 128;   // keys per tile
+constexpr int TC_THREADS = 192;
+constexpr int BLK_BYTES = 128 * 128;   // one [128 rows x 64 fp16] swizzled block = 16 KB
+
+struct AttnTcParams {
+  __half* o;
+  const unsigned char* kmask;  // [B, Skv] 1 = attend, 0 = masked (additive mask_value); may be null
+  long long o_sb, o_ss, o_sh;
+  int B, H, Sq, Skv;
+  float scale;       // applied to fp32 scores (1.0 when q_prescale)
+  float q_prescale;  // if != 0: q <- fp16(q * q_prescale) before QK^T (eva_vit.py:128)
+  float mask_value;
+  int causal;
+};
+
+DEVI void tma_load_3d(const CUtensorMap* desc, uint64_t* bar, void* smem_dst, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+      " [%0], [%1, {%3, %4, %5}], [%2], %6;"
+      :
+      : "r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(desc)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2),
+        "l"(TMA_EVICT_NORMAL)
+      : "memory");
+}
+DEVI void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      :
+      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+DEVI void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// MN-major B operand (V tile [keys][64 features] blocks, 128B swizzle): LBO = distance between 64-feature blocks,
+// SBO = distance between 8-key groups (cute::UMMA canonical ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units)
+DEVI uint64_t make_sdesc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_f16_bmn(int M, int N) {   // A K-major, B MN-major
+  return (1u << 4) | (1u << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// byte offset of 16-byte chunk `c` (8 fp16) of row `r` inside a swizzled [128 x 64] block
+DEVI uint32_t sw_off(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
+
+template <int DH>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
+  constexpr int DK = (DH == 88) ? 96 : 128;   // contraction length of Q K^T
+  constexpr int DV = (DH == 88) ? 96 : 128;   // N of P V (columns >= DH are not stored)
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                       // 2 blocks
+  uint8_t* sK = sQ + 2 * BLK_BYTES;         // 2 stages x 2 blocks
+  uint8_t* sV = sK + 4 * BLK_BYTES;         // 2 stages x 2 blocks
+  uint8_t* sP = sV + 4 * BLK_BYTES;         // 2 blocks
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * BLK_BYTES);
+  uint64_t* q_full = bars + 0;
+  uint64_t* q_ready = bars + 1;
+  uint64_t* kv_full = bars + 2;    // [2]
+  uint64_t* kv_empty = bars + 4;   // [2]
+  uint64_t* s_full = bars + 6;     // [2]
+  uint64_t* p_full = bars + 8;
+  uint64_t* pv_done = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // grid = (heads, query tiles, batch): CTAs are dispatched x-fastest, so all heads of one query tile start together.
+  // Causal: the LAST query tile has the most key tiles -> dispatch it first (longest-processing-time-first);
+  // non-causal: ragged last tile (1 row of 257 in the ViT) goes last and fills the tail of the final wave.
+  const int n_qt = (int)gridDim.y;
+  const int qt = p.causal ? (n_qt - 1 - (int)blockIdx.y) : (int)blockIdx.y;
+  const int q0 = qt * TQ, h = blockIdx.x, b = blockIdx.z;
+  const int kv_off = p.Skv - p.Sq;
+  int kv_end = p.Skv;
+  if (p.causal) {
+    const int last = q0 + TQ + kv_off;
+    kv_end = last < kv_end ? last : kv_end;
+    if (kv_end < 1) kv_end = 1;
+  }
+  const int n_tiles = (kv_end + TKV - 1) / TKV;
+  const int col0 = h * DH;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    mbar_init(q_ready, 128);
+    for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+    mbar_init(&s_full[0], 1);
+    mbar_init(&s_full[1], 1);
+    mbar_init(p_full, 128);
+    mbar_init(pv_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  pdl_launch_dependents();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_wait();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 256;   // S0: 0..127, S1: 128..255, O: 256..383
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      mbar_arrive_expect_tx(q_full, 2 * BLK_BYTES);
+      tma_load_3d(&tmQ, q_full, sQ, col0, q0, b);
+      tma_load_3d(&tmQ, q_full, sQ + BLK_BYTES, col0 + 64, q0, b);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < n_tiles; ++j) {
+        mbar_wait(&kv_empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&kv_full[stage], 4 * BLK_BYTES);
+        uint8_t* k = sK + stage * 2 * BLK_BYTES;
+        uint8_t* v = sV + stage * 2 * BLK_BYTES;
+        tma_load_3d(&tmK, &kv_full[stage], k, col0, j * TKV, b);
+        tma_load_3d(&tmK, &kv_full[stage], k + BLK_BYTES, col0 + 64, j * TKV, b);
+        tma_load_3d(&tmV, &kv_full[stage], v, col0, j * TKV, b);
+        tma_load_3d(&tmV, &kv_full[stage], v + BLK_BYTES, col0 + 64, j * TKV, b);
+        if (++stage == 2) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_pv = make_idesc_f16_bmn(TQ, DV);
+      mbar_wait(q_ready, 0);
+      tc_fence_after();
+      const uint32_t aq = smem_u32(sQ);
+      // S_j = Q K_j^T into S buffer (j & 1); only ceil16(valid keys) columns are computed for a ragged last tile
+      auto issue_qk = [&](int j) {
+        const int stage = j & 1;
+        mbar_wait(&kv_full[stage], (uint32_t)((j >> 1) & 1));
+        tc_fence_after();
+        int nk = kv_end - j * TKV;
+        nk = nk > TKV ? TKV : ((nk + 15) & ~15);
+        const uint32_t idesc_qk = make_idesc_f16(TQ, nk, false);
+        const uint32_t bk = smem_u32(sK + stage * 2 * BLK_BYTES);
+#pragma unroll
+        for (int ks = 0; ks < DK / 16; ++ks) {
+          const uint32_t off = (uint32_t)((ks >> 2) * BLK_BYTES + (ks & 3) * 32);
+          umma_f16_ss(tmem_S + (uint32_t)(stage * 128), make_sdesc_k_sw128(aq + off), make_sdesc_k_sw128(bk + off),
+                      idesc_qk, ks > 0 ? 1u : 0u);
+        }
+        umma_commit(&s_full[stage]);
+      };
+      issue_qk(0);
+      for (int j = 0; j < n_tiles; ++j) {
+        const int stage = j & 1;
+        if (j + 1 < n_tiles) issue_qk(j + 1);      // overlaps the softmax of tile j
+        mbar_wait(p_full, (uint32_t)(j & 1));      // P_j written to smem, O rescaled
+        tc_fence_after();
+        int nk = kv_end - j * TKV;
+        nk = nk > TKV ? TKV : ((nk + 15) & ~15);
+        const uint32_t ap = smem_u32(sP);
+        const uint32_t bv = smem_u32(sV + stage * 2 * BLK_BYTES);
+        for (int ks = 0; ks < nk / 16; ++ks) {
+          const uint32_t aoff = (uint32_t)((ks >> 2) * BLK_BYTES + (ks & 3) * 32);
+          umma_f16_ss(tmem_O, make_sdesc_k_sw128(ap + aoff), make_sdesc_mn_sw128(bv + ks * 2048, BLK_BYTES), idesc_pv,
+                      (j > 0 || ks > 0) ? 1u : 0u);
+        }
+        umma_commit(&kv_empty[stage]);   // K/V stage free once QK^T and PV of this tile are done
+        umma_commit(pv_done);
+      }
+    }
+  } else {
+    // ===================== softmax warps: thread = query row =====================
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;                // row inside the tile == TMEM lane
+    const int qrow = q0 + r;
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    // ---- Q fix-up: optional fp16 pre-scale (ViT) and zeroing of the padded contraction columns ----
+    mbar_wait(q_full, 0);
+    if (DH == 88 || p.q_prescale != 0.f) {
+#pragma unroll 1
+      for (int c = 0; c < 16; ++c) {               // 16 chunks of 8 columns = 128 contraction columns
+        uint4* ptr = reinterpret_cast<uint4*>(sQ + (c >> 3) * BLK_BYTES + sw_off(r, c & 7));
+        if (c * 8 >= DH) {
+          if (c * 8 < DK) *ptr = make_uint4(0, 0, 0, 0);
+        } else if (p.q_prescale != 0.f) {
+          uint4 u = *ptr;
+          __half2* hh = reinterpret_cast<__half2*>(&u);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(hh[i]);
+            hh[i] = __floats2half2_rn(f.x * p.q_prescale, f.y * p.q_prescale);
+          }
+          *ptr = u;
+        }
+      }
+      fence_proxy_async_smem();
+    }
+    mbar_arrive(q_ready);
+
+    const float LOG2E = 1.4426950408889634f;
+    const float sl2 = p.scale * LOG2E;
+    const float mask_l2 = p.mask_value * LOG2E;
+    const unsigned char* kmask = p.kmask ? p.kmask + (long long)b * p.Skv : nullptr;
+    float m_run = -INFINITY, l_run = 0.f;
+    const bool warp_valid = (q0 + quad * 32) < p.Sq;   // warps whose 32 rows are all beyond Sq do no math at all
+    for (int j = 0; j < n_tiles; ++j) {
+      const int kbase = j * TKV;
+      int nk = kv_end - kbase;                         // valid keys of this tile (for this CTA)
+      nk = nk > TKV ? TKV : nk;
+      const int n_chunks = (nk + 31) >> 5;             // 32-key chunks that contain at least one valid key
+      mbar_wait(&s_full[j & 1], (uint32_t)((j >> 1) & 1));
+      tc_fence_after();
+      uint32_t s[4][32];
+      float alpha = 1.f;
+      if (warp_valid) {
+        const uint32_t s_addr = tmem_S + (uint32_t)((j & 1) * 128) + lane_addr;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          if (c < n_chunks) tmem_ld_32x32b_x32(s_addr + c * 32, s[c]);
+        tmem_ld_wait();
+        const bool need_mask = (kbase + TKV > p.Skv) || (p.causal && (kbase + TKV - 1 > q0 + kv_off)) || kmask != nullptr;
+        float mx = -INFINITY;
+        if (need_mask) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (c < n_chunks) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const int key = kbase + c * 32 + i;
+                float x = __uint_as_float(s[c][i]) * sl2;
+                if (kmask != nullptr && key < p.Skv && kmask[key] == 0) x += mask_l2;
+                if (key >= p.Skv || (p.causal && key > qrow + kv_off)) x = -INFINITY;
+                s[c][i] = __float_as_uint(x);
+                mx = fmaxf(mx, x);
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (c < n_chunks) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(s[c][i]));
+            }
+          }
+          mx *= sl2;                                   // sl2 > 0: max commutes with the scale
+        }
+        const float m_new = fmaxf(m_run, mx);
+        const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+        alpha = exp2f(m_run - m_use);
+        float sum = 0.f;
+        // ---- P = exp2(S - m) -> fp16 pairs (kept in the low 16 words of each chunk) ----
+        if (need_mask) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (c < n_chunks) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                const float p0 = exp2f(__uint_as_float(s[c][i]) - m_use);
+                const float p1 = exp2f(__uint_as_float(s[c][i + 1]) - m_use);
+                sum += p0 + p1;
+                s[c][i >> 1] = pack_half2(p0, p1);
+              }
+            }
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            if (c < n_chunks) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 2) {
+                const float p0 = exp2f(fmaf(__uint_as_float(s[c][i]), sl2, -m_use));
+                const float p1 = exp2f(fmaf(__uint_as_float(s[c][i + 1]), sl2, -m_use));
+                sum += p0 + p1;
+                s[c][i >> 1] = pack_half2(p0, p1);
+              }
+            }
+          }
+        }
+        l_run = l_run * alpha + sum;
+        m_run = m_new;
+      }
+      // ---- previous P V must be complete before O is rescaled and before sP is overwritten ----
+      if (j > 0) {
+        mbar_wait(pv_done, (uint32_t)((j - 1) & 1));
+        tc_fence_after();
+        if (warp_valid && !__all_sync(0xffffffffu, alpha == 1.f)) {   // warp-uniform: skip when no row's max moved
+#pragma unroll 1
+          for (int c = 0; c < DV; c += 32) {
+            uint32_t o[32];
+            tmem_ld_32x32b_x32(tmem_O + lane_addr + c, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32b_x32(tmem_O + lane_addr + c, o);
+          }
+          tmem_st_wait();
+        }
+      }
+      // ---- P row -> swizzled smem (A operand of P V, K-major over keys); only the 16-key groups the MMA reads ----
+      if (warp_valid) {
+        const int n_q = (((nk + 15) & ~15) + 7) >> 3;  // 8-key chunks to write
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int chunk = c * 4 + q;               // 16 chunks of 8 keys
+            if (chunk < n_q)
+              *reinterpret_cast<uint4*>(sP + (chunk >> 3) * BLK_BYTES + sw_off(r, chunk & 7)) =
+                  make_uint4(s[c][4 * q], s[c][4 * q + 1], s[c][4 * q + 2], s[c][4 * q + 3]);
+          }
+        }
+        fence_proxy_async_smem();
+      }
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    // ---- epilogue: O / l -> fp16 -> global ----
+    mbar_wait(pv_done, (uint32_t)((n_tiles - 1) & 1));
+    tc_fence_after();
+    const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+    __half* orow = p.o + (long long)b * p.o_sb + (long long)qrow * p.o_ss + (long long)h * p.o_sh;
+#pragma unroll 1
+    for (int c = 0; c < DV; c += 32) {
+      uint32_t o[32];
+      tmem_ld_32x32b_x32(tmem_O + lane_addr + c, o);
+      tmem_ld_wait();
+      if (qrow < p.Sq) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int colq = c + q * 8;
+          if (colq < DH) {
+            uint4 w;
+            w.x = pack_half2(__uint_as_float(o[8 * q + 0]) * inv, __uint_as_float(o[8 * q + 1]) * inv);
+            w.y = pack_half2(__uint_as_float(o[8 * q + 2]) * inv, __uint_as_float(o[8 * q + 3]) * inv);
+            w.z = pack_half2(__uint_as_float(o[8 * q + 4]) * inv, __uint_as_float(o[8 * q + 5]) * inv);
+            w.w = pack_half2(__uint_as_float(o[8 * q + 6]) * inv, __uint_as_float(o[8 * q + 7]) * inv);
+            *reinterpret_cast<uint4*>(orow + colq) = w;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// {features (H*D), tokens (S, stride ss), batch (B, stride sb)} fp16, box {64, 128, 1}, 128B swizzle
+int make_tmap3(CUtensorMap* tm, const void* ptr, int feat, int S, int B, long long ss, long long sb) {
+  static PFN_encodeTiled enc = nullptr;
+  if (enc == nullptr) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess) {
+      stllm_set_last_error("cuTensorMapEncodeTiled driver entry point not available");
+      return STLLM_ERR_DRIVER;
+    }
+    enc = reinterpret_cast<PFN_encodeTiled>(sym);
+  }
+  cuuint64_t gdim[3] = {(cuuint64_t)feat, (cuuint64_t)S, (cuuint64_t)B};
+  cuuint64_t gstride[2] = {(cuuint64_t)ss * 2, (cuuint64_t)(B > 1 ? sb : ss * S) * 2};
+  cuuint32_t box[3] = {64, 128, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), gdim, gstride, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    stllm_set_last_error("cuTensorMapEncodeTiled(3d) failed: CUresult %d", (int)r);
+    return STLLM_ERR_DRIVER;
+  }
+  return STLLM_OK;
+}
+
+template <int DH>
+int launch_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcParams& p,
+              cudaStream_t stream) {
+  constexpr int SMEM = 12 * BLK_BYTES + 256 + 1024;
+  auto kern = attention_tc_kernel<DH>;
+  static bool configured = false;
+  if (!configured) {
+    STLLM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    configured = true;
+  }
+  dim3 grid(p.H, (p.Sq + TQ - 1) / TQ, p.B);
+  STLLM_CHECK_CUDA(stllm_launch(kern, grid, dim3(TC_THREADS), SMEM, stream, tq, tk, tv, p));
+  return STLLM_OK;
+}
+
+}  // namespace
+
+static int g_attn_tc = -1;   // -1: read STLLM_ATTN_TC on first use (default on)
+// debug / A-B switch: 1 = use the tcgen05 attention kernel where it applies, 0 = always the mma.sync kernel
+extern "C" int stllm_set_attention_tc(int on) {
+  g_attn_tc = on ? 1 : 0;
+  return STLLM_OK;
+}
+
+// returns STLLM_ERR_UNSUPPORTED (without setting an error) when the shape/layout is not one this kernel handles
+int stllm_attention_tc_try(const void* q, const void* k, const void* v, void* out, int B, int H, int Sq, int Skv, int D,
+                           const long long* qs, const long long* ks, const long long* vs, const long long* os,
+                           float scale, float q_prescale, int causal, const void* key_mask, float mask_value,
+                           cudaStream_t stream) {
+  if (g_attn_tc < 0) {
+    const char* e = getenv("STLLM_ATTN_TC");
+    g_attn_tc = (e != nullptr && atoi(e) == 0) ? 0 : 1;
+  }
+  if (!g_attn_tc) return STLLM_ERR_UNSUPPORTED;
+  if (!(D == 88 || D == 128) || Sq < 32) return STLLM_ERR_UNSUPPORTED;
+  // heads contiguous in the feature dimension, 16-byte aligned token / batch strides
+  if (qs[2] != D || ks[2] != D || vs[2] != D) return STLLM_ERR_UNSUPPORTED;
+  if ((qs[1] % 8) || (ks[1] % 8) || (vs[1] % 8) || (qs[0] % 8) || (ks[0] % 8) || (vs[0] % 8) || (os[1] % 8) || (os[2] % 8) ||
+      (os[0] % 8))
+    return STLLM_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(out) & 15) != 0) return STLLM_ERR_UNSUPPORTED;
+  CUtensorMap tq, tk, tv;
+  int rc = make_tmap3(&tq, q, H * D, Sq, B, qs[1], qs[0]);
+  if (rc != STLLM_OK) return rc;
+  rc = make_tmap3(&tk, k, H * D, Skv, B, ks[1], ks[0]);
+  if (rc != STLLM_OK) return rc;
+  rc = make_tmap3(&tv, v, H * D, Skv, B, vs[1], vs[0]);
+  if (rc != STLLM_OK) return rc;
+  AttnTcParams p;
+  p.o = (__half*)out;
+  p.kmask = (const unsigned char*)key_mask;
+  p.o_sb = os[0]; p.o_ss = os[1]; p.o_sh = os[2];
+  p.B = B; p.H = H; p.Sq = Sq; p.Skv = Skv;
+  p.scale = scale; p.q_prescale = q_prescale; p.mask_value = mask_value; p.causal = causal;
+  if (D == 88) return launch_tc<88>(tq, tk, tv, p, stream);
+  return launch_tc<128>(tq, tk, tv, p, stream);
+}
