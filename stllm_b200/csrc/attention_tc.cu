@@ -22,9 +22,13 @@
 namespace {
 
 constexpr int TQ = 128;    // query rows per CTA
-constexpr int TKV = 128;   // keys per tile
+constexpr int TKV = 64;    // keys per tile
 constexpr int TC_THREADS = 192;
-constexpr int BLK_BYTES = 128 * 128;   // one [128 rows x 64 fp16] swizzled block = 16 KB
+constexpr int BLK_BYTES = 128 * 128;   // one [128 rows x 64 fp16] swizzled block = 16 KB (Q, P)
+constexpr int KBLK = TKV * 128;        // one [64 keys x 64 fp16] swizzled block = 8 KB (K, V)
+// shared memory: Q 2 x 16 KB | K 2 stages x 2 x 8 KB | V 2 stages x 2 x 8 KB  = 96 KB -> 2 CTAs per SM.
+// P_j (128 x 64 fp16 = 16 KB) is written over the K stage of tile j: K_j is dead once S_j = Q K_j^T has completed and
+// the stage is only handed back to the TMA producer after P_j V_j has completed.
 
 struct AttnTcParams {
   __half* o;
@@ -79,18 +83,17 @@ __host__ __device__ constexpr uint32_t make_idesc_f16_bmn(int M, int N) {   // A
 DEVI uint32_t sw_off(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
 
 template <int DH>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
   constexpr int DK = (DH == 88) ? 96 : 128;   // contraction length of Q K^T
   constexpr int DV = (DH == 88) ? 96 : 128;   // N of P V (columns >= DH are not stored)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sQ = smem;                       // 2 blocks
-  uint8_t* sK = sQ + 2 * BLK_BYTES;         // 2 stages x 2 blocks
-  uint8_t* sV = sK + 4 * BLK_BYTES;         // 2 stages x 2 blocks
-  uint8_t* sP = sV + 4 * BLK_BYTES;         // 2 blocks
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * BLK_BYTES);
+  uint8_t* sQ = smem;                       // 2 blocks of 16 KB
+  uint8_t* sK = sQ + 2 * BLK_BYTES;         // 2 stages x 2 blocks of 8 KB   (stage j&1 doubles as P_j)
+  uint8_t* sV = sK + 4 * KBLK;              // 2 stages x 2 blocks of 8 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 4 * KBLK);
   uint64_t* q_full = bars + 0;
   uint64_t* q_ready = bars + 1;
   uint64_t* kv_full = bars + 2;    // [2]
@@ -130,14 +133,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     mbar_init(pv_done, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (warp == 1) tmem_alloc(tmem_slot, 256);
   pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   pdl_wait();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 256;   // S0: 0..127, S1: 128..255, O: 256..383
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 2 * TKV;   // S0: 0..63, S1: 64..127, O: 128..255
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -149,13 +152,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       uint32_t phase = 0;
       for (int j = 0; j < n_tiles; ++j) {
         mbar_wait(&kv_empty[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&kv_full[stage], 4 * BLK_BYTES);
-        uint8_t* k = sK + stage * 2 * BLK_BYTES;
-        uint8_t* v = sV + stage * 2 * BLK_BYTES;
+        mbar_arrive_expect_tx(&kv_full[stage], 4 * KBLK);
+        uint8_t* k = sK + stage * 2 * KBLK;
+        uint8_t* v = sV + stage * 2 * KBLK;
         tma_load_3d(&tmK, &kv_full[stage], k, col0, j * TKV, b);
-        tma_load_3d(&tmK, &kv_full[stage], k + BLK_BYTES, col0 + 64, j * TKV, b);
+        tma_load_3d(&tmK, &kv_full[stage], k + KBLK, col0 + 64, j * TKV, b);
         tma_load_3d(&tmV, &kv_full[stage], v, col0, j * TKV, b);
-        tma_load_3d(&tmV, &kv_full[stage], v + BLK_BYTES, col0 + 64, j * TKV, b);
+        tma_load_3d(&tmV, &kv_full[stage], v + KBLK, col0 + 64, j * TKV, b);
         if (++stage == 2) { stage = 0; phase ^= 1; }
       }
     }
@@ -174,11 +177,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         int nk = kv_end - j * TKV;
         nk = nk > TKV ? TKV : ((nk + 15) & ~15);
         const uint32_t idesc_qk = make_idesc_f16(TQ, nk, false);
-        const uint32_t bk = smem_u32(sK + stage * 2 * BLK_BYTES);
+        const uint32_t bk = smem_u32(sK + stage * 2 * KBLK);
 #pragma unroll
         for (int ks = 0; ks < DK / 16; ++ks) {
-          const uint32_t off = (uint32_t)((ks >> 2) * BLK_BYTES + (ks & 3) * 32);
-          umma_f16_ss(tmem_S + (uint32_t)(stage * 128), make_sdesc_k_sw128(aq + off), make_sdesc_k_sw128(bk + off),
+          const uint32_t aoff = (uint32_t)((ks >> 2) * BLK_BYTES + (ks & 3) * 32);
+          const uint32_t boff = (uint32_t)((ks >> 2) * KBLK + (ks & 3) * 32);
+          umma_f16_ss(tmem_S + (uint32_t)(stage * TKV), make_sdesc_k_sw128(aq + aoff), make_sdesc_k_sw128(bk + boff),
                       idesc_qk, ks > 0 ? 1u : 0u);
         }
         umma_commit(&s_full[stage]);
@@ -191,11 +195,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tc_fence_after();
         int nk = kv_end - j * TKV;
         nk = nk > TKV ? TKV : ((nk + 15) & ~15);
-        const uint32_t ap = smem_u32(sP);
-        const uint32_t bv = smem_u32(sV + stage * 2 * BLK_BYTES);
+        const uint32_t ap = smem_u32(sK + stage * 2 * KBLK);    // P_j lives in the consumed K stage
+        const uint32_t bv = smem_u32(sV + stage * 2 * KBLK);
         for (int ks = 0; ks < nk / 16; ++ks) {
-          const uint32_t aoff = (uint32_t)((ks >> 2) * BLK_BYTES + (ks & 3) * 32);
-          umma_f16_ss(tmem_O, make_sdesc_k_sw128(ap + aoff), make_sdesc_mn_sw128(bv + ks * 2048, BLK_BYTES), idesc_pv,
+          umma_f16_ss(tmem_O, make_sdesc_k_sw128(ap + ks * 32), make_sdesc_mn_sw128(bv + ks * 2048, KBLK), idesc_pv,
                       (j > 0 || ks > 0) ? 1u : 0u);
         }
         umma_commit(&kv_empty[stage]);   // K/V stage free once QK^T and PV of this tile are done
@@ -244,19 +247,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const int n_chunks = (nk + 31) >> 5;             // 32-key chunks that contain at least one valid key
       mbar_wait(&s_full[j & 1], (uint32_t)((j >> 1) & 1));
       tc_fence_after();
-      uint32_t s[4][32];
+      constexpr int NCH = TKV / 32;
+      uint32_t s[NCH][32];
       float alpha = 1.f;
       if (warp_valid) {
-        const uint32_t s_addr = tmem_S + (uint32_t)((j & 1) * 128) + lane_addr;
+        const uint32_t s_addr = tmem_S + (uint32_t)((j & 1) * TKV) + lane_addr;
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
+        for (int c = 0; c < NCH; ++c)
           if (c < n_chunks) tmem_ld_32x32b_x32(s_addr + c * 32, s[c]);
         tmem_ld_wait();
         const bool need_mask = (kbase + TKV > p.Skv) || (p.causal && (kbase + TKV - 1 > q0 + kv_off)) || kmask != nullptr;
         float mx = -INFINITY;
         if (need_mask) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < NCH; ++c) {
             if (c < n_chunks) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
@@ -271,7 +275,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           }
         } else {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < NCH; ++c) {
             if (c < n_chunks) {
 #pragma unroll
               for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(s[c][i]));
@@ -286,7 +290,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         // ---- P = exp2(S - m) -> fp16 pairs (kept in the low 16 words of each chunk) ----
         if (need_mask) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < NCH; ++c) {
             if (c < n_chunks) {
 #pragma unroll
               for (int i = 0; i < 32; i += 2) {
@@ -299,7 +303,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           }
         } else {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
+          for (int c = 0; c < NCH; ++c) {
             if (c < n_chunks) {
 #pragma unroll
               for (int i = 0; i < 32; i += 2) {
@@ -333,14 +337,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       // ---- P row -> swizzled smem (A operand of P V, K-major over keys); only the 16-key groups the MMA reads ----
       if (warp_valid) {
+        uint8_t* sP = sK + (j & 1) * 2 * KBLK;         // the K stage of this tile: S_j = Q K_j^T has completed
         const int n_q = (((nk + 15) & ~15) + 7) >> 3;  // 8-key chunks to write
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
+        for (int c = 0; c < NCH; ++c) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const int chunk = c * 4 + q;               // 16 chunks of 8 keys
+            const int chunk = c * 4 + q;               // 8 chunks of 8 keys
             if (chunk < n_q)
-              *reinterpret_cast<uint4*>(sP + (chunk >> 3) * BLK_BYTES + sw_off(r, chunk & 7)) =
+              *reinterpret_cast<uint4*>(sP + sw_off(r, chunk)) =
                   make_uint4(s[c][4 * q], s[c][4 * q + 1], s[c][4 * q + 2], s[c][4 * q + 3]);
           }
         }
@@ -380,7 +385,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, 256);
   }
 }
 
@@ -389,7 +394,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // {features (H*D), tokens (S, stride ss), batch (B, stride sb)} fp16, box {64, 128, 1}, 128B swizzle
-int make_tmap3(CUtensorMap* tm, const void* ptr, int feat, int S, int B, long long ss, long long sb) {
+int make_tmap3(CUtensorMap* tm, const void* ptr, int feat, int S, int B, long long ss, long long sb, int box_rows) {
   static PFN_encodeTiled enc = nullptr;
   if (enc == nullptr) {
     void* sym = nullptr;
@@ -403,7 +408,7 @@ int make_tmap3(CUtensorMap* tm, const void* ptr, int feat, int S, int B, long lo
   }
   cuuint64_t gdim[3] = {(cuuint64_t)feat, (cuuint64_t)S, (cuuint64_t)B};
   cuuint64_t gstride[2] = {(cuuint64_t)ss * 2, (cuuint64_t)(B > 1 ? sb : ss * S) * 2};
-  cuuint32_t box[3] = {64, 128, 1};
+  cuuint32_t box[3] = {64, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(ptr), gdim, gstride, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -418,7 +423,7 @@ int make_tmap3(CUtensorMap* tm, const void* ptr, int feat, int S, int B, long lo
 template <int DH>
 int launch_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcParams& p,
               cudaStream_t stream) {
-  constexpr int SMEM = 12 * BLK_BYTES + 256 + 1024;
+  constexpr int SMEM = 2 * BLK_BYTES + 8 * KBLK + 128 + 1024;
   auto kern = attention_tc_kernel<DH>;
   static bool configured = false;
   if (!configured) {
@@ -457,11 +462,11 @@ int stllm_attention_tc_try(const void* q, const void* k, const void* v, void* ou
     return STLLM_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(out) & 15) != 0) return STLLM_ERR_UNSUPPORTED;
   CUtensorMap tq, tk, tv;
-  int rc = make_tmap3(&tq, q, H * D, Sq, B, qs[1], qs[0]);
+  int rc = make_tmap3(&tq, q, H * D, Sq, B, qs[1], qs[0], TQ);
   if (rc != STLLM_OK) return rc;
-  rc = make_tmap3(&tk, k, H * D, Skv, B, ks[1], ks[0]);
+  rc = make_tmap3(&tk, k, H * D, Skv, B, ks[1], ks[0], TKV);
   if (rc != STLLM_OK) return rc;
-  rc = make_tmap3(&tv, v, H * D, Skv, B, vs[1], vs[0]);
+  rc = make_tmap3(&tv, v, H * D, Skv, B, vs[1], vs[0], TKV);
   if (rc != STLLM_OK) return rc;
   AttnTcParams p;
   p.o = (__half*)out;
