@@ -8,7 +8,7 @@ import time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
-os.environ.setdefault("STLLM_GEMM_SK", "1")  # exercise the hybrid stream-K schedule in the 256/512 cases
+os.environ.setdefault("STLLM_GEMM_SK", "2")  # exercise the hybrid stream-K schedule in the 256/512 cases
 
 from stllm_b200 import ops
 
