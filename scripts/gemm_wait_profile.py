@@ -46,11 +46,10 @@ def run(M, N, K, epi, tn, bias=False, residual=False, iters=10):
           f"mma(tmem_empty)={f(c[2]):.2f} epi(tmem_full)={f(c[3]):.2f}", flush=True)
 
 
-for tn in (257, 513):
-    run(4112, 4224, 1408, ops.EPI_NONE, tn, bias=True)
-    run(4112, 6144, 1408, ops.EPI_GELU, tn, bias=True)
+for tn in (513, 257):
+    for epi, bias in ((ops.EPI_NONE, False), (ops.EPI_NONE, True), (ops.EPI_GELU, True), (ops.EPI_RELU, True)):
+        run(4112, 6144, 1408, epi, tn, bias=bias)
     run(4112, 1408, 6144, ops.EPI_NONE, tn, bias=True, residual=True)
-    run(576, 12288, 4096, ops.EPI_NONE, tn)
+    run(4112, 1408, 6144, ops.EPI_NONE, tn)
     run(576, 22016, 4096, ops.EPI_SWIGLU, tn)
-    run(576, 4096, 11008, ops.EPI_NONE, tn, residual=True)
-    run(8192, 8192, 8192, ops.EPI_NONE, tn, iters=3)
+    run(576, 22016, 4096, ops.EPI_NONE, tn)

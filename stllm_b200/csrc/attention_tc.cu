@@ -4,12 +4,12 @@
 // (decode steps, the Q-Former's 32-query attention and every other shape stay on attention.cu.)
 //
 // One CTA = one (batch, head, 128-query tile); 192 threads:
-//   warp 0     : TMA producer - Q once, then K/V tiles of 128 keys through a 2-stage ring (3-D tensor maps over the
+//   warp 4     : TMA producer - Q once, then K/V tiles of 128 keys through a 2-stage ring (3-D tensor maps over the
 //                packed q|k|v activations: {feature, token, batch}; 128B swizzle; two 64-column boxes per operand)
-//   warp 1     : TMEM allocator + MMA issuer:  S = Q K^T (tcgen05.mma, fp32 S in TMEM columns 0..127), then
+//   warp 5     : TMEM allocator + MMA issuer:  S = Q K^T (tcgen05.mma, fp32 S in TMEM columns 0..127), then
 //                O += P V with P read from shared memory (K-major) and V used in place as an MN-major B operand
 //                (no transpose of V anywhere), O in TMEM columns 128..255
-//   warps 2..5 : softmax, one thread per query row: tcgen05.ld the S row, scale/mask, online max/sum in fp32, rescale
+//   warps 0..3 : softmax, one thread per query row: tcgen05.ld the S row, scale/mask, online max/sum in fp32, rescale
 //                O in TMEM (tcgen05.ld/st) when the running max moved, write P (fp16) into the swizzled smem tile,
 //                finally O / l -> fp16 -> global.
 // head_dim 88: the second 64-column box of a head spills into the next head's columns; those 8 extra contraction
@@ -120,7 +120,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int n_tiles = (kv_end + TKV - 1) / TKV;
   const int col0 = h * DH;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 4 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
@@ -133,7 +133,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     mbar_init(pv_done, 1);
     fence_mbar_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, 256);
+  if (warp == 5) tmem_alloc(tmem_slot, 256);
   pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
@@ -142,8 +142,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 2 * TKV;   // S0: 0..63, S1: 64..127, O: 128..255
 
-  if (warp == 0) {
-    // ===================== TMA producer =====================
+  if (warp == 4) {
+    // ===================== TMA producer (warp 4: highest id on scheduler 0, see gemm_tcgen05.cu) =====================
     if (lane == 0) {
       mbar_arrive_expect_tx(q_full, 2 * BLK_BYTES);
       tma_load_3d(&tmQ, q_full, sQ, col0, q0, b);
@@ -162,8 +162,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (++stage == 2) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (warp == 5) {
+    // ===================== MMA issuer (warp 5: highest id on scheduler 1) =====================
     if (lane == 0) {
       constexpr uint32_t idesc_pv = make_idesc_f16_bmn(TQ, DV);
       mbar_wait(q_ready, 0);
@@ -383,7 +383,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 5) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 256);
   }
