@@ -217,14 +217,15 @@ def llama_forward(sd, inputs_embeds, attention_mask, num_layers, num_heads, eps=
     hidden states like output_hidden_states=True: embeddings, each layer, with the LAST entry being post-norm)."""
     B, S, C = inputs_embeds.shape
     d = C // num_heads
-    cos, sin = llama_rope_tables(d, S)
-    cos, sin = cos[None, None], sin[None, None]
-    neg = torch.finfo(inputs_embeds.dtype).min
+    dev, dt = inputs_embeds.device, inputs_embeds.dtype     # fp32 CPU in the tests; fp16 CUDA for the "reference
+    cos, sin = llama_rope_tables(d, S)                       # arithmetic in fp16 on the GPU" error-budget test
+    cos, sin = cos[None, None].to(dev, dt), sin[None, None].to(dev, dt)   # HF casts the cached tables to x.dtype
+    neg = torch.finfo(dt).min
     # _prepare_decoder_attention_mask (HF 4.28): causal (dtype-min above diagonal) + expanded padding mask
-    causal = torch.full((S, S), neg).triu(1)[None, None]
+    causal = torch.full((S, S), neg, device=dev, dtype=dt).triu(1)[None, None]
     add_mask = causal
     if attention_mask is not None:
-        pad = (1.0 - attention_mask[:, None, None, :].float()).expand(B, 1, S, S)
+        pad = (1.0 - attention_mask[:, None, None, :].to(dev, dt)).expand(B, 1, S, S)
         add_mask = causal + pad.masked_fill(pad.bool(), neg)
     x = inputs_embeds
     hs = [x]

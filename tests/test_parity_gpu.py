@@ -162,3 +162,41 @@ def test_llama_vicuna_width_vs_oracle():
     out = llm.half().cuda()(samples=None, inputs_embeds=emb.cuda().half(), attention_mask=att.cuda())
     assert_close(out.logits, ref_logits, atol=3e-2, rtol=2e-2, what="Vicuna-width logits")
     assert rel_fro(out.logits, ref_logits) < 4e-3
+
+
+# ------------------------------------------------------------------------------------------------- fp16 error budget
+def _fp16_sd(sd):
+    return {k: (v.half().cuda() if v.is_floating_point() else v.cuda()) for k, v in sd.items()}
+
+
+def test_error_vs_fp32_not_worse_than_torch_fp16_on_same_gpu():
+    """The reference runs this path in fp16 on the GPU (torch/cuBLAS eager).  Its own deviation from the fp32 result
+    is the achievable floor for ANY fp16 implementation; ours must be in the same class: for ViT-g width (2 blocks) and
+    Vicuna width (2 layers), rel. Frobenius error(ours vs fp32 oracle) <= 2 x error(torch fp16 eager vs fp32 oracle)."""
+    from stllm_b200.eva_vit import create_eva_vit_g
+    from stllm_b200.st_llm import STLLMForCausalLM, StllmConfig
+    # ---- ViT ----
+    vit = create_eva_vit_g(img_size=224, precision="fp32", depth=2)
+    sd = _seeded_sd(vit, 21)
+    vit.load_state_dict(sd)
+    frames = torch.randn(2, 3, 224, 224, generator=torch.Generator().manual_seed(99))
+    ref = O.vit_forward(sd, frames, 2, 16)
+    ours = vit.half().cuda()(frames.cuda())
+    eager = O.vit_forward(_fp16_sd(sd), frames.half().cuda(), 2, 16)
+    e_ours, e_eager = rel_fro(ours, ref), rel_fro(eager, ref)
+    print(f"ViT-g width: rel.Fro ours {e_ours:.2e}  torch-fp16 eager {e_eager:.2e}")
+    assert e_ours <= 2.0 * e_eager + 1e-4
+    # ---- Llama ----
+    cfg = StllmConfig(num_hidden_layers=2, vocab_size=512)
+    llm = STLLMForCausalLM(cfg)
+    sd = _seeded_sd(llm, 22)
+    llm.load_state_dict(sd)
+    emb = (torch.randn(1, 128, 4096, generator=torch.Generator().manual_seed(98)) * 0.5).half().float()
+    msd = {k[len("model."):]: v for k, v in sd.items() if k.startswith("model.")}
+    ref = torch.nn.functional.linear(O.llama_forward(msd, emb, None, 2, 32), sd["lm_head.weight"])
+    ours = llm.half().cuda()(samples=None, inputs_embeds=emb.cuda().half()).logits
+    hsd = _fp16_sd(msd)
+    eager = torch.nn.functional.linear(O.llama_forward(hsd, emb.half().cuda(), None, 2, 32), sd["lm_head.weight"].half().cuda())
+    e_ours, e_eager = rel_fro(ours, ref), rel_fro(eager, ref)
+    print(f"Vicuna width: rel.Fro ours {e_ours:.2e}  torch-fp16 eager {e_eager:.2e}")
+    assert e_ours <= 2.0 * e_eager + 1e-4
