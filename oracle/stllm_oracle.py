@@ -170,7 +170,10 @@ def qformer_forward(sd, query_tokens, image_embeds, num_layers, num_heads=12, cr
 def llama_rmsnorm(x, w, eps):
     """LlamaRMSNorm.forward, modeling_llama_mem.py:70-78"""
     var = x.float().pow(2).mean(-1, keepdim=True)
-    return w * (x * torch.rsqrt(var + eps))
+    h = x * torch.rsqrt(var + eps)
+    if w.dtype in (torch.float16, torch.bfloat16):       # :75-76 "convert into half-precision if necessary"
+        h = h.to(w.dtype)
+    return w * h
 
 
 def llama_rope_tables(head_dim, seq_len, base=10000.0):
