@@ -41,14 +41,24 @@ int stllm_device_sm_count(void);
  * 357,371; st_llm.py:368 (llama_proj), :38 (mvm head), :108,122 (lm_head); modeling_llama_mem.py:160-163,
  * 139-143 (q/k/v/o, gate/up/down).  K, lda, ldw multiples of 8; A, W 16-byte aligned.
  * For STLLM_EPI_SWIGLU the output has N/2 columns.  out_f32: 0 -> fp16 C, 1 -> fp32 C.
- * tile_n: 0 = auto, 128 / 256 = one-CTA tiles, 512 = CTA-pair (cta_group::2) 256x256 tiles, 1024 = stream-K. */
+ * tile_n: 0 = auto (host cost model); 64 / 128 / 256 = one-CTA tiles of that many columns; 512 = CTA-pair
+ * (cta_group::2) 256x256 tiles; 1024 + bn = CTA-pair tiles of bn columns (bn % 16 == 0, bn <= 256); 2048 + bn =
+ * CTA-pair with SWAPPED operands (C^T = W A^T: 256 features x bn tokens per tile, transposed epilogue); +1 on any
+ * code forbids the stream-K treatment of the last wave.
+ * PDL note: the first weight tiles are requested before griddepcontrol.wait -- W must not be produced by the kernel
+ * launched immediately before on the same stream with programmatic serialization (weights are static on this path);
+ * STLLM_GEMM_WPREFETCH=0 disables this. */
 int stllm_gemm_f16(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N,
                    int K, const void* bias, const void* residual, long long ldr, int epilogue, int out_f32,
                    int tile_n, void* stream);
 
+/* The configuration the cost model picks for a shape (host only, no launch): out3 = {engine: 0 one-CTA, 1 CTA pair,
+ * 2 CTA pair with swapped operands; tile columns; estimated SM cycles}. */
+int stllm_gemm_plan(int M, int N, int K, int epilogue, long long* out3);
+
 /* Stream-K scheduling of the GEMM needs a caller-owned, ZEROED device workspace of at least
  * stllm_gemm_workspace_bytes() bytes (256-byte aligned), registered once per process/device.  Passing NULL
- * unregisters it (data-parallel tiles only).  tile_n = 1024 forces stream-K, 512 the CTA-pair kernel. */
+ * unregisters it (data-parallel tiles only).  STLLM_GEMM_SK=1|2 enables the stream-K schedule (off by default). */
 long long stllm_gemm_workspace_bytes(void);
 int stllm_set_gemm_workspace(void* ptr, long long bytes);
 

@@ -104,7 +104,7 @@ def attn_case(B, H, Sq, Skv, D, causal=False, mask=False, prescale=False, packed
     return report(name, out.reshape(-1, D), ref.reshape(-1, D), atol=4e-3, rtol=1e-2)
 
 
-def time_gemm(M, N, K, epi=ops.EPI_NONE, variants=(0, 257, 256, 513, 512), rounds=5, iters=10, bias=False, residual=False):
+def time_gemm(M, N, K, epi=ops.EPI_NONE, variants=(0, 257, 513), rounds=5, iters=10, bias=False, residual=False):
     """interleaved A/B timing: every round times each variant and cuBLAS back to back (same clocks)"""
     a = torch.randn(M, K, device=dev, dtype=torch.float16)
     w = torch.randn(N, K, device=dev, dtype=torch.float16) * 0.02
@@ -132,7 +132,7 @@ def time_gemm(M, N, K, epi=ops.EPI_NONE, variants=(0, 257, 256, 513, 512), round
     fl = 2.0 * M * N * K
     txt = "  ".join(f"{k}: {med[k]:6.1f}us {fl/med[k]/1e6:6.0f}TF" for k in list(variants) + ["cublas"])
     best = min(variants, key=lambda k: med[k])
-    print(f"TIME gemm M={M} N={N} K={K} epi={epi}: {txt}  best={best}", flush=True)
+    print(f"TIME gemm M={M} N={N} K={K} epi={epi}: {txt}  best={best}  plan={ops.gemm_plan(M, N, K, epi)}", flush=True)
 
 
 def main():
@@ -195,6 +195,34 @@ def main():
     gemm_case(576, 22016, 4096, epi=ops.EPI_SWIGLU, tile_n=512)
     gemm_case(576, 4096, 11008, residual=True, tile_n=512)
     gemm_case(64, 32001, 4096, out_f32=True, tile_n=512)
+    # --- CTA-pair engine with a flexible tile width (tile_n = 1024 + bn; half chunks when bn % 32 == 16) ---
+    for bn in (16, 32, 48, 96, 112, 144, 176, 208, 240):
+        gemm_case(300, 700, 256, bias=True, residual=True, tile_n=1024 + bn)
+    gemm_case(4112, 1408, 1408, bias=True, residual=True, tile_n=1024 + 176)
+    gemm_case(4112, 6144, 1408, epi=ops.EPI_GELU, bias=True, tile_n=1024 + 240)
+    gemm_case(4112, 1408, 6144, bias=True, residual=True, tile_n=1024 + 176)
+    gemm_case(4112, 1408, 6144, bias=True, residual=True, tile_n=1024 + 176 + 1)
+    gemm_case(576, 22016, 4096, epi=ops.EPI_SWIGLU, tile_n=1024 + 144)
+    gemm_case(64, 1000, 512, epi=ops.EPI_SWIGLU, tile_n=1024 + 48)
+    gemm_case(100, 200, 72, tile_n=1024 + 80, out_f32=True)
+    # --- CTA-pair engine with swapped operands (tile_n = 2048 + bn: 256 features x bn tokens, transposed epilogue) ---
+    for bn in (16, 32, 48, 64, 96, 144, 192, 256):
+        gemm_case(300, 700, 256, bias=True, residual=True, tile_n=2048 + bn)
+    gemm_case(576, 12288, 4096, tile_n=2048 + 192)
+    gemm_case(576, 4096, 4096, residual=True, tile_n=2048 + 144)
+    gemm_case(576, 22016, 4096, epi=ops.EPI_SWIGLU, tile_n=2048 + 192)
+    gemm_case(576, 4096, 11008, residual=True, tile_n=2048 + 144)
+    gemm_case(576, 32000, 4096, tile_n=2048 + 144)
+    gemm_case(64, 32001, 4096, out_f32=True, tile_n=2048 + 64)     # odd N, fp32 out
+    gemm_case(5, 32001, 4096, tile_n=2048 + 16)                    # decode-like, odd N and odd ldc -> scalar stores
+    gemm_case(1, 4096, 4096, tile_n=2048 + 16)
+    gemm_case(512, 3072, 768, epi=ops.EPI_GELU, bias=True, tile_n=2048 + 64)
+    gemm_case(32, 1024, 4096, epi=ops.EPI_RELU, bias=True, tile_n=2048 + 32)
+    gemm_case(64, 1000, 512, epi=ops.EPI_SWIGLU, residual=True, tile_n=2048 + 32)
+    gemm_case(300, 768, 768, bias=True, lda_pad=8, tile_n=2048 + 48)
+    for _ in range(3):                                             # back-to-back launches (PDL + weight prefetch)
+        gemm_case(576, 4096, 4096, residual=True)
+        gemm_case(4112, 1408, 1408, bias=True, residual=True)
     # --- attention: tcgen05 kernel (ViT / Llama prefill shapes) and mma.sync kernel on the same cases ---
     from stllm_b200 import _lib as _L
     for tc in (1, 0):

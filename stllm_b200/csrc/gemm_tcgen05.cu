@@ -50,6 +50,8 @@ struct GemmParams {
   int M, N, K;
   int m_tiles, n_tiles;
   int out_f32;    // 0: fp16 output, 1: fp32 output
+  int bn;         // CTA-pair engine: accumulator columns per tile (multiple of 16, <= 256), chosen per shape
+  int w_prefetch; // 1: the weight operand is static -> its first stages are loaded BEFORE griddepcontrol.wait
   int sk_tiles;   // number of leading tiles scheduled stream-K (0 = pure data-parallel)
   float* sk_ws;   // per-CTA fp32 partial-tile slots [gridDim.x][SLOT_ELEMS]
   int* sk_flags;  // per-CTA arrival counters (zero between launches)
@@ -113,21 +115,35 @@ struct SmemLayout {
 //  [3] epilogue (warp 2) waiting for an accumulator   [4] total kernel cycles of CTA 0's MMA warp   [5] launches
 __device__ unsigned long long g_gemm_prof[8];
 
-// GELU(erf) (nn.GELU, eva_vit.py:50 / Qformer.py:359).  erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below the
-// fp16 output rounding) with MUFU rcp/ex2: ~14 instructions instead of erff()'s ~30 -- the erf epilogue of ViT fc1 is
-// instruction-issue bound (profiles/r01_gemm_ab.md).
+DEVI float rcp_approx(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+DEVI float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// GELU(erf) (nn.GELU, eva_vit.py:50 / Qformer.py:359):  0.5 x (1 + erf(x / sqrt2)) = h + |h| erf(|x| / sqrt2), h = x / 2.
+// erf by Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below the fp16 output rounding) with MUFU rcp/ex2 and all
+// constants folded: 13 instructions (2 MUFU) -- the erf epilogue of ViT fc1 is instruction-issue bound
+// (profiles/r01_gemm_ab.md), erff() costs ~30.
 DEVI float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  const float t = rcp_approx(fmaf(0.3275911f * 0.70710678118654752440f, fabsf(x), 1.0f));
   float poly = fmaf(t, 1.061405429f, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
   poly *= t;
-  const float erf_abs = fmaf(-poly, __expf(-z * z), 1.0f);
-  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+  const float xs = x * 0.84932180028801904272f;   // sqrt(log2(e) / 2): exp(-x^2 / 2) = 2^-(xs^2)
+  const float ex = ex2_approx(-(xs * xs));
+  const float h = 0.5f * x;
+  const float erf_abs = fmaf(-poly, ex, 1.0f);
+  return fmaf(fabsf(h), erf_abs, h);
 }
-DEVI float silu(float x) { return x / (1.0f + __expf(-x)); }
+// x * sigmoid(x) with MUFU ex2/rcp (no IEEE division): modeling_llama_mem.py:143 act_fn = SiLU
+DEVI float silu(float x) { return x * rcp_approx(1.0f + ex2_approx(-1.44269504088896340736f * x)); }
 
 // ------------------------------------------------------------------------------------------------
 // Epilogue.  One warp owns 32 accumulator rows (its TMEM lane quadrant) x `cols` columns, processed in 32-column
@@ -146,38 +162,43 @@ struct ChunkIn {
   uint32_t r[32];
   uint4 bq[4];
   uint4 rq[NC / 8];
+  int nvec;            // accumulator columns of this chunk handled by 16-byte vector accesses: 32, 16 or 0 (scalar path)
   bool bias_vec, res_vec;
 };
 
+// `col_end`: first accumulator column (global index) that does NOT belong to this tile / matrix.  A chunk is either
+// full (32 valid columns), a half chunk (exactly 16: tiles whose width is an odd multiple of 16) or ragged (scalar).
 template <int EPI>
-DEVI void chunk_issue(ChunkIn<EPI>& in, const GemmParams& p, uint32_t taddr, int row, bool row_ok, int col0,
-                      const float* part0, int chunk_global, int row_in_slot) {
+DEVI void chunk_issue(ChunkIn<EPI>& in, const GemmParams& p, uint32_t taddr, int row, bool row_ok, int col0, int col_end) {
   constexpr int NC = ChunkIn<EPI>::NC;
   const int ocol0 = (EPI == EPI_SWIGLU) ? (col0 >> 1) : col0;
-  const int n_out = (EPI == EPI_SWIGLU) ? (p.N >> 1) : p.N;
-  const bool active = row_ok && col0 < p.N;
+  const bool active = row_ok && col0 < col_end;
   tmem_ld_32x32b_x32(taddr, in.r);
-  in.bias_vec = active && p.bias != nullptr && (col0 + 32 <= p.N);
+  const int valid = col_end - col0;
+  in.nvec = !active ? 0 : (valid >= 32 ? 32 : (valid == 16 ? 16 : 0));
+  in.bias_vec = in.nvec > 0 && p.bias != nullptr;
   const __half* rp = active && p.residual != nullptr ? p.residual + (long long)row * p.ldr + ocol0 : nullptr;
-  in.res_vec = rp != nullptr && (ocol0 + NC <= n_out) && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0);
+  in.res_vec = rp != nullptr && in.nvec > 0 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0);
   if (in.bias_vec) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q) in.bq[q] = __ldg(reinterpret_cast<const uint4*>(p.bias + col0) + q);
+    for (int q = 0; q < 4; ++q)
+      if (q * 8 < in.nvec) in.bq[q] = __ldg(reinterpret_cast<const uint4*>(p.bias + col0) + q);
   }
   if (in.res_vec) {
 #pragma unroll
-    for (int q = 0; q < NC / 8; ++q) in.rq[q] = __ldg(reinterpret_cast<const uint4*>(rp) + q);
+    for (int q = 0; q < NC / 8; ++q)
+      if (q * 8 * (32 / NC) < in.nvec) in.rq[q] = __ldg(reinterpret_cast<const uint4*>(rp) + q);
   }
 }
 
 template <int EPI>
-DEVI void chunk_finish(const ChunkIn<EPI>& in, const GemmParams& p, int row, bool row_ok, int col0, const float* part0,
-                       int n_parts, long long part_stride, int chunk_global, int row_in_slot) {
+DEVI void chunk_finish(const ChunkIn<EPI>& in, const GemmParams& p, int row, bool row_ok, int col0, int col_end,
+                       const float* part0, int n_parts, long long part_stride, int chunk_global, int row_in_slot) {
   constexpr int NC = ChunkIn<EPI>::NC;
   const int ocol0 = (EPI == EPI_SWIGLU) ? (col0 >> 1) : col0;
-  const int n_out = (EPI == EPI_SWIGLU) ? (p.N >> 1) : p.N;
-  if (!(row_ok && col0 < p.N)) return;
-  const bool vec_ok = (ocol0 + NC <= n_out);
+  const int ocol_end = (EPI == EPI_SWIGLU) ? (col_end >> 1) : col_end;
+  if (!(row_ok && col0 < col_end)) return;
+  const int nvec_out = (EPI == EPI_SWIGLU) ? (in.nvec >> 1) : in.nvec;   // output columns written by vector stores
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(in.r[j]);
@@ -197,18 +218,20 @@ DEVI void chunk_finish(const ChunkIn<EPI>& in, const GemmParams& p, int row, boo
     if (in.bias_vec) {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const __half2* bh = reinterpret_cast<const __half2*>(&in.bq[q]);
+        if (q * 8 < in.nvec) {
+          const __half2* bh = reinterpret_cast<const __half2*>(&in.bq[q]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = __half22float2(bh[j]);
-          v[q * 8 + 2 * j] += f.x;
-          v[q * 8 + 2 * j + 1] += f.y;
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __half22float2(bh[j]);
+            v[q * 8 + 2 * j] += f.x;
+            v[q * 8 + 2 * j + 1] += f.y;
+          }
         }
       }
     } else {
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (col0 + j < p.N) v[j] += __half2float(p.bias[col0 + j]);
+        if (col0 + j < col_end) v[j] += __half2float(p.bias[col0 + j]);
     }
   }
   if (EPI == EPI_GELU) {
@@ -229,47 +252,52 @@ DEVI void chunk_finish(const ChunkIn<EPI>& in, const GemmParams& p, int row, boo
     if (in.res_vec) {
 #pragma unroll
       for (int q = 0; q < NC / 8; ++q) {
-        const __half2* bh = reinterpret_cast<const __half2*>(&in.rq[q]);
+        if (q * 8 < nvec_out) {
+          const __half2* bh = reinterpret_cast<const __half2*>(&in.rq[q]);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = __half22float2(bh[j]);
-          v[q * 8 + 2 * j] += f.x;
-          v[q * 8 + 2 * j + 1] += f.y;
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __half22float2(bh[j]);
+            v[q * 8 + 2 * j] += f.x;
+            v[q * 8 + 2 * j + 1] += f.y;
+          }
         }
       }
     } else {
 #pragma unroll
       for (int j = 0; j < NC; ++j)
-        if (ocol0 + j < n_out) v[j] += __half2float(rp[j]);
+        if (ocol0 + j < ocol_end) v[j] += __half2float(rp[j]);
     }
   }
   if (p.out_f32) {
     float* cp = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + ocol0;
-    if (vec_ok && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
+    if (nvec_out > 0 && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
 #pragma unroll
       for (int q = 0; q < NC / 4; ++q)
-        reinterpret_cast<float4*>(cp)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        if (q * 4 < nvec_out)
+          reinterpret_cast<float4*>(cp)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
     } else {
 #pragma unroll
       for (int j = 0; j < NC; ++j)
-        if (ocol0 + j < n_out) cp[j] = v[j];
+        if (ocol0 + j < ocol_end) cp[j] = v[j];
     }
   } else {
     __half* cp = reinterpret_cast<__half*>(p.C) + (long long)row * p.ldc + ocol0;
-    if (vec_ok && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
+    if (nvec_out > 0 && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
 #pragma unroll
       for (int q = 0; q < NC / 8; ++q) {
-        uint4 o;
-        o.x = pack_half2(v[8 * q + 0], v[8 * q + 1]);
-        o.y = pack_half2(v[8 * q + 2], v[8 * q + 3]);
-        o.z = pack_half2(v[8 * q + 4], v[8 * q + 5]);
-        o.w = pack_half2(v[8 * q + 6], v[8 * q + 7]);
-        reinterpret_cast<uint4*>(cp)[q] = o;
+        if (q * 8 < nvec_out) {
+          uint4 o;
+          o.x = pack_half2(v[8 * q + 0], v[8 * q + 1]);
+          o.y = pack_half2(v[8 * q + 2], v[8 * q + 3]);
+          o.z = pack_half2(v[8 * q + 4], v[8 * q + 5]);
+          o.w = pack_half2(v[8 * q + 6], v[8 * q + 7]);
+          reinterpret_cast<uint4*>(cp)[q] = o;
+        }
       }
     } else {
 #pragma unroll
       for (int j = 0; j < NC; ++j)
-        if (ocol0 + j < n_out) cp[j] = __float2half_rn(v[j]);
+        if (ocol0 + j < ocol_end) cp[j] = __float2half_rn(v[j]);
     }
   }
 }
@@ -282,24 +310,25 @@ DEVI void dump_store(const uint32_t (&r)[32], float* slot, int chunk_global, int
                        __uint_as_float(r[4 * q + 3])));
 }
 
-// Epilogue of one (tile, k-range) segment for one warp: COLS accumulator columns starting at TMEM address t_row.
+// Epilogue of one (tile, k-range) segment for one warp: the 32-column chunks [c_begin, c_end) of the accumulator whose
+// first column lives at TMEM address t_acc (chunk c = columns 32c..32c+31 of the tile = global columns tile_col0+32c..).
 //   tail/middle part of a split tile -> raw fp32 dump to this CTA's workspace slot + flag
 //   head of a split tile            -> wait for the contributors' flags, add their partials, fused epilogue
 //   whole tile                      -> fused epilogue
 // `slot_stride_ctas`: distance in CTA slots between consecutive contributors (1 one-CTA, 2 CTA-pair).
-// chunk0_global: index of this warp's first 32-column chunk inside the tile (for the slot layout).
-template <int EPI, int COLS>
-DEVI void epilogue_segment(const GemmParams& p, uint32_t t_row, int chunk0_global, int row, bool row_ok,
-                           int row_in_slot, int col_base, bool is_tail, int n_parts, int slot_stride_ctas, int lane) {
+template <int EPI>
+DEVI void epilogue_segment(const GemmParams& p, uint32_t t_acc, int c_begin, int c_end, int row, bool row_ok,
+                           int row_in_slot, int tile_col0, int col_end, bool is_tail, int n_parts,
+                           int slot_stride_ctas, int lane) {
   if (is_tail) {
     float* slot = p.sk_ws + (long long)blockIdx.x * SLOT_ELEMS;
 #pragma unroll 1
-    for (int c = 0; c < COLS; c += 32) {
+    for (int c = c_begin; c < c_end; ++c) {
       __syncwarp();
       uint32_t ra[32];
-      tmem_ld_32x32b_x32(t_row + c, ra);
+      tmem_ld_32x32b_x32(t_acc + 32 * c, ra);
       tmem_ld_wait();
-      dump_store(ra, slot, chunk0_global + c / 32, row_in_slot);
+      dump_store(ra, slot, c, row_in_slot);
     }
     __threadfence();
     __syncwarp();
@@ -330,12 +359,12 @@ DEVI void epilogue_segment(const GemmParams& p, uint32_t t_row, int chunk0_globa
   // one 32-column chunk at a time (a 2-deep software pipeline was measured SLOWER: it needs > 168 registers/thread,
   // the cap at 320 threads/CTA, and spills; profiles/r01_gemm_ab.md)
 #pragma unroll 1
-  for (int c = 0; c < COLS; c += 32) {
+  for (int c = c_begin; c < c_end; ++c) {
     __syncwarp();
     ChunkIn<EPI> a;
-    chunk_issue<EPI>(a, p, t_row + c, row, row_ok, col_base + c, part0, chunk0_global + c / 32, row_in_slot);
+    chunk_issue<EPI>(a, p, t_acc + 32 * c, row, row_ok, tile_col0 + 32 * c, col_end);
     tmem_ld_wait();
-    chunk_finish<EPI>(a, p, row, row_ok, col_base + c, part0, n_parts, pstride, chunk0_global + c / 32, row_in_slot);
+    chunk_finish<EPI>(a, p, row, row_ok, tile_col0 + 32 * c, col_end, part0, n_parts, pstride, c, row_in_slot);
   }
   __syncwarp();
   if (n_parts > 0 && lane == 0) {
@@ -343,6 +372,91 @@ DEVI void epilogue_segment(const GemmParams& p, uint32_t t_row, int chunk0_globa
     for (int pi = 0; pi < n_parts; ++pi) {
       int* f = p.sk_flags + blockIdx.x + (1 + pi) * slot_stride_ctas;
       if (atomicAdd(f, 1) == 2 * NUM_EPI_WARPS - 1) atomicExch(f, 0);
+    }
+  }
+}
+
+// Swapped-operand epilogue (CTA-pair engine, SWAP): the accumulator holds C^T -- TMEM lane = output FEATURE f (row of
+// W), TMEM column = TOKEN.  One warp owns 32 features x 32 tokens per chunk.  Lanes 2i / 2i+1 exchange halves so that
+// each thread ends up with 16 tokens x 2 adjacent features: half2 stores (64 contiguous bytes per token and warp), and
+// for SwiGLU (W rows interleaved gate_j, up_j) gate and up of one output land in the same thread.
+template <int EPI>
+DEVI void chunk_swap(const GemmParams& p, uint32_t taddr, int f, int tok0, int tok_end, int lane) {
+  uint32_t r[32];
+  tmem_ld_32x32b_x32(taddr, r);
+  float bias = 0.f;
+  if (p.bias != nullptr && f < p.N) bias = __half2float(__ldg(p.bias + f));
+  tmem_ld_wait();
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    v[j] = __uint_as_float(r[j]) + bias;
+    if (EPI == EPI_GELU) v[j] = gelu_erf(v[j]);
+    if (EPI == EPI_RELU) v[j] = fmaxf(v[j], 0.f);
+  }
+  const bool odd = (lane & 1) != 0;
+  float a[16], b[16];   // a: feature fe (even), b: feature fe + 1; 16 tokens starting at tokb
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    const float send = odd ? v[j] : v[16 + j];
+    const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+    a[j] = odd ? recv : v[j];
+    b[j] = odd ? v[16 + j] : recv;
+  }
+  const int fe = f & ~1;
+  const int tokb = tok0 + (odd ? 16 : 0);
+  if (fe >= p.N) return;
+  if (EPI == EPI_SWIGLU) {
+    const int fo = fe >> 1;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const int tok = tokb + j;
+      if (tok < tok_end) {
+        float o = silu(a[j]) * b[j];
+        if (p.residual != nullptr) o += __half2float(p.residual[(long long)tok * p.ldr + fo]);
+        if (p.out_f32) reinterpret_cast<float*>(p.C)[(long long)tok * p.ldc + fo] = o;
+        else reinterpret_cast<__half*>(p.C)[(long long)tok * p.ldc + fo] = __float2half_rn(o);
+      }
+    }
+  } else {
+    const bool pair_ok = fe + 1 < p.N;
+    const bool vec = pair_ok && !p.out_f32 && ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 3) == 0) &&
+                     (p.residual == nullptr || (((p.ldr & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.residual) & 3) == 0)));
+    if (vec) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int tok = tokb + j;
+        if (tok < tok_end) {
+          float x = a[j], y = b[j];
+          if (p.residual != nullptr) {
+            const float2 rr = __half22float2(*reinterpret_cast<const __half2*>(p.residual + (long long)tok * p.ldr + fe));
+            x += rr.x;
+            y += rr.y;
+          }
+          *reinterpret_cast<__half2*>(reinterpret_cast<__half*>(p.C) + (long long)tok * p.ldc + fe) = __floats2half2_rn(x, y);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int tok = tokb + j;
+        if (tok < tok_end) {
+          float x = a[j], y = b[j];
+          if (p.residual != nullptr) {
+            x += __half2float(p.residual[(long long)tok * p.ldr + fe]);
+            if (pair_ok) y += __half2float(p.residual[(long long)tok * p.ldr + fe + 1]);
+          }
+          if (p.out_f32) {
+            float* cp = reinterpret_cast<float*>(p.C) + (long long)tok * p.ldc + fe;
+            cp[0] = x;
+            if (pair_ok) cp[1] = y;
+          } else {
+            __half* cp = reinterpret_cast<__half*>(p.C) + (long long)tok * p.ldc + fe;
+            cp[0] = __float2half_rn(x);
+            if (pair_ok) cp[1] = __float2half_rn(y);
+          }
+        }
+      }
     }
   }
 }
@@ -388,7 +502,9 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  pdl_wait();   // everything above (barriers, TMEM, descriptors) overlapped the previous kernel's tail
+  // Everything above (barriers, TMEM, descriptors) overlapped the previous kernel's tail (PDL).  griddepcontrol.wait
+  // is executed per role: the producer first pre-loads the (static) WEIGHT tiles of its first stages, the MMA issuer
+  // touches no global memory and never waits, the epilogue warps wait before their first global access.
   const uint32_t tmem_base = *tmem_base_slot;
   WorkIter it((int)blockIdx.x, (int)gridDim.x, num_tiles, p.sk_tiles, k_blocks);
   int tile, kb0, kb1;
@@ -399,15 +515,31 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       int stage = 0;
       uint32_t phase = 0;
       long long w_acc = 0;
+      int n_pre = 0;   // k-blocks whose weight tile is already in flight (stages 0..n_pre-1, first work item)
+      if (p.w_prefetch) {
+        WorkIter peek = it;
+        if (peek.next(tile, kb0, kb1)) {
+          const int n_blk = tile / p.m_tiles;
+          n_pre = (kb1 - kb0 < STAGES) ? (kb1 - kb0) : STAGES;
+          for (int s = 0; s < n_pre; ++s) {
+            mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
+            tma_load_2d(&tmB, &full_bar[s], smem + s * L::STAGE_BYTES + L::A_BYTES, (kb0 + s) * BK, n_blk * BN, p.hint_b);
+          }
+        }
+      }
+      pdl_wait();
+      int issued = 0;
       while (it.next(tile, kb0, kb1)) {
         const int m_blk = tile % p.m_tiles, n_blk = tile / p.m_tiles;
-        for (int kb = kb0; kb < kb1; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb, ++issued) {
           w_acc += mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
-          mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+          if (issued >= n_pre) {
+            mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+            tma_load_2d(&tmB, &full_bar[stage], sb, kb * BK, n_blk * BN, p.hint_b);
+          }
           tma_load_2d(&tmA, &full_bar[stage], sa, kb * BK, m_blk * BM, p.hint_a);
-          tma_load_2d(&tmB, &full_bar[stage], sb, kb * BK, n_blk * BN, p.hint_b);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -456,14 +588,15 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     const int e = warp;             // epilogue warps are warps 0..7
     const int quad = warp & 3;     // TMEM lane quadrant this warp may access
     const int half_idx = e >> 2;   // which half of the BN columns
-    constexpr int COLS_PER_WARP = BN / 2;
+    constexpr int CHUNKS_PER_WARP = BN / 64;
     int acc = 0;
     uint32_t acc_phase = 0;
+    pdl_wait();
     while (it.next(tile, kb0, kb1)) {
       const int m_blk = tile % p.m_tiles, n_blk = tile / p.m_tiles;
       const int row_in_tile = quad * 32 + lane;
       const int row = m_blk * BM + row_in_tile;
-      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half_idx * COLS_PER_WARP);
+      const uint32_t t_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
       const bool split_head = (kb0 == 0 && kb1 < k_blocks);
       const int n_parts = split_head ? sk_contributors((int)blockIdx.x, (int)gridDim.x, tile, p.sk_tiles, k_blocks) : 0;
       {
@@ -471,8 +604,8 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         if (warp == 0 && lane == 0) atomicAdd(&g_gemm_prof[3], (unsigned long long)w);
       }
       tc_fence_after();
-      epilogue_segment<EPI, COLS_PER_WARP>(p, t_row, half_idx * (COLS_PER_WARP / 32), row, row < p.M, row_in_tile,
-                                           n_blk * BN + half_idx * COLS_PER_WARP, kb0 > 0, n_parts, 1, lane);
+      epilogue_segment<EPI>(p, t_acc, half_idx * CHUNKS_PER_WARP, (half_idx + 1) * CHUNKS_PER_WARP, row, row < p.M,
+                            row_in_tile, n_blk * BN, min(p.N, (n_blk + 1) * BN), kb0 > 0, n_parts, 1, lane);
       // all TMEM reads of this warp for this segment are done -> release the accumulator stage
       tc_fence_before();
       __syncwarp();
@@ -490,24 +623,32 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 }
 
 // ================================================================================================
-// CTA-pair engine (cta_group::2): a cluster of 2 CTAs computes a 256 x 256 output tile.
-//   * each CTA TMA-loads its own 128 rows of A and its own 128 rows (= half of the N tile) of W per k-block
-//   * the LEADER CTA's elected thread issues tcgen05.mma.cta_group::2 (M=256, N=256); the hardware reads A/B
-//     from both CTAs' shared memory and writes 128 accumulator rows into each CTA's TMEM.
+// CTA-pair engine (cta_group::2): a cluster of 2 CTAs computes a 256 x bn accumulator tile, bn = any multiple of 16
+// up to 256 chosen per shape by the host cost model (tile-count quantisation: e.g. N = 1408 -> 8 tiles of 176).
+//   * "lane operand" (tmA, 256 rows per tile -> TMEM lanes, 128 per CTA) and "column operand" (tmB, bn rows per tile
+//     -> TMEM columns, bn/2 per CTA).  Normal mode: lanes = tokens (A), columns = features (W).  SWAP mode computes
+//     C^T = W * A^T: lanes = features (W), columns = tokens (A) -- the token count of a prefill (e.g. 576 = 3 x 192)
+//     lands on the flexible N side of the MMA instead of being padded to 256-row tiles; the epilogue writes C
+//     transposed (chunk_swap).
+//   * each CTA TMA-loads its own 128 lane-operand rows and its own bn/2 column-operand rows per k-block
+//   * the LEADER CTA's elected thread issues tcgen05.mma.cta_group::2 (M=256, N=bn); the hardware reads both CTAs'
+//     shared memory and writes 128 accumulator rows into each CTA's TMEM.
 //   * barriers: full[s] lives in the leader (both CTAs' TMA complete_tx on it); empty[s] and tmem_full[a] are
 //     multicast-committed to both CTAs; tmem_empty[a] lives in the leader and collects both CTAs' epilogue warps.
+//   * PDL: the weight operand's first stages are requested BEFORE griddepcontrol.wait (weights are static), so their
+//     HBM latency overlaps the previous kernel's tail.
 // ================================================================================================
-constexpr int BN2 = 256;
+constexpr int BN2_MAX = 256;
 constexpr int STAGES2 = 6;
 struct SmemLayout2 {
-  static constexpr int A_BYTES = BM * BK * 2;          // 16 KB: this CTA's 128 rows of A
-  static constexpr int B_BYTES = (BN2 / 2) * BK * 2;   // 16 KB: this CTA's half of the W tile
+  static constexpr int A_BYTES = BM * BK * 2;              // 16 KB: this CTA's 128 rows of the lane operand
+  static constexpr int B_BYTES = (BN2_MAX / 2) * BK * 2;   // <= 16 KB: this CTA's half of the column operand tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFFSET = STAGES2 * STAGE_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
 };
 
-template <int EPI>
+template <int EPI, bool SWAP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                              const GemmParams p) {
@@ -526,8 +667,12 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
   const bool is_leader = cta_rank == 0;
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
-  const int num_tiles = p.m_tiles * p.n_tiles;   // 256 x 256 pair tiles
+  const int a_tiles = p.m_tiles;                 // tiles along the lane operand (256 rows each)
+  const int b_tiles = p.n_tiles;                 // tiles along the column operand (bn rows each)
+  const int num_tiles = a_tiles * b_tiles;
   const int k_blocks = (p.K + BK - 1) / BK;
+  const int bn = p.bn;
+  const uint32_t stage_tx = 2u * (uint32_t)(L::A_BYTES + (bn / 2) * BK * 2);   // bytes of both CTAs per k-block
   constexpr uint32_t TMEM_COLS = 512;            // 2 accumulator stages x 256 fp32 columns
 
   if (warp == WARP_TMA && lane == 0) {
@@ -548,10 +693,15 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
   tc_fence_before();
   cluster_sync_all();   // barriers of BOTH CTAs initialised before any remote arrive / TMA complete_tx
   tc_fence_after();
-  pdl_wait();
   const uint32_t tmem_base = *tmem_base_slot;
   WorkIter it(cluster_id, num_clusters, num_tiles, p.sk_tiles, k_blocks);
   int tile, kb0, kb1;
+  // tile -> (lane-operand block, column-operand block); the TOKEN dimension runs fastest so that concurrently running
+  // clusters share one weight tile in L2 (weights are the operand streamed from HBM)
+  auto decode = [&](int t, int& a_blk, int& b_blk) {
+    if (SWAP) { b_blk = t % b_tiles; a_blk = t / b_tiles; }
+    else      { a_blk = t % a_tiles; b_blk = t / a_tiles; }
+  };
 
   if (warp == WARP_TMA) {
     // ===================== TMA producer (both CTAs) =====================
@@ -559,17 +709,36 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
       int stage = 0;
       uint32_t phase = 0;
       long long w_acc = 0;
+      int a_blk, b_blk;
+      // operand roles: the weight operand is the lane operand in SWAP mode, the column operand otherwise
+      int n_pre = 0;
+      if (p.w_prefetch) {
+        WorkIter peek = it;
+        if (peek.next(tile, kb0, kb1)) {
+          decode(tile, a_blk, b_blk);
+          n_pre = (kb1 - kb0 < STAGES2) ? (kb1 - kb0) : STAGES2;
+          for (int s = 0; s < n_pre; ++s) {
+            uint8_t* sa = smem + s * L::STAGE_BYTES;
+            if (is_leader) mbar_arrive_expect_tx(&full_bar[s], stage_tx);
+            if (SWAP) tma_load_2d_2sm(&tmA, &full_bar[s], sa, (kb0 + s) * BK, a_blk * 256 + (int)cta_rank * 128, p.hint_a);
+            else tma_load_2d_2sm(&tmB, &full_bar[s], sa + L::A_BYTES, (kb0 + s) * BK, b_blk * bn + (int)cta_rank * (bn / 2), p.hint_b);
+          }
+        }
+      }
+      pdl_wait();
+      int issued = 0;
       while (it.next(tile, kb0, kb1)) {
-        const int m_blk = tile % p.m_tiles, n_blk = tile / p.m_tiles;
-        const int row_a = m_blk * 256 + (int)cta_rank * 128;
-        const int row_b = n_blk * BN2 + (int)cta_rank * (BN2 / 2);
-        for (int kb = kb0; kb < kb1; ++kb) {
+        decode(tile, a_blk, b_blk);
+        const int row_a = a_blk * 256 + (int)cta_rank * 128;
+        const int row_b = b_blk * bn + (int)cta_rank * (bn / 2);
+        for (int kb = kb0; kb < kb1; ++kb, ++issued) {
           w_acc += mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
-          if (is_leader) mbar_arrive_expect_tx(&full_bar[stage], 2 * L::STAGE_BYTES);  // bytes of both CTAs
-          tma_load_2d_2sm(&tmA, &full_bar[stage], sa, kb * BK, row_a, p.hint_a);
-          tma_load_2d_2sm(&tmB, &full_bar[stage], sb, kb * BK, row_b, p.hint_b);
+          const bool pre = issued < n_pre;   // weight tile of this k-block already requested
+          if (is_leader && !pre) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
+          if (!(pre && SWAP)) tma_load_2d_2sm(&tmA, &full_bar[stage], sa, kb * BK, row_a, p.hint_a);
+          if (!(pre && !SWAP)) tma_load_2d_2sm(&tmB, &full_bar[stage], sb, kb * BK, row_b, p.hint_b);
           if (++stage == STAGES2) { stage = 0; phase ^= 1; }
         }
       }
@@ -578,7 +747,7 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
   } else if (warp == WARP_MMA) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (is_leader && lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(256, BN2, false);
+      const uint32_t idesc = make_idesc_f16(256, bn, false);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -588,7 +757,7 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
       while (it.next(tile, kb0, kb1)) {
         w_acc += mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN2);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN2_MAX);
         for (int kb = kb0; kb < kb1; ++kb) {
           w_full += mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
@@ -614,20 +783,25 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
       }
     }
   } else {
-    // ===================== epilogue warps (both CTAs, 128 rows each) =====================
+    // ===================== epilogue warps (both CTAs, 128 accumulator lanes each) =====================
     const int e = warp;             // epilogue warps are warps 0..7
     const int quad = warp & 3;
     const int half_idx = e >> 2;
-    constexpr int COLS_PER_WARP = BN2 / 2;
+    const int n_chunks = (bn + 31) >> 5;                 // 32-column chunks of the tile (the last may be half)
+    const int c_split = (n_chunks + 1) >> 1;
+    const int c_begin = half_idx == 0 ? 0 : c_split;
+    const int c_end = half_idx == 0 ? c_split : n_chunks;
     int acc = 0;
     uint32_t acc_phase = 0;
     const uint32_t leader_empty0 = mapa_shared(smem_u32(&tmem_empty_bar[0]), 0);
     const uint32_t leader_empty1 = mapa_shared(smem_u32(&tmem_empty_bar[1]), 0);
+    int a_blk, b_blk;
+    pdl_wait();
     while (it.next(tile, kb0, kb1)) {
-      const int m_blk = tile % p.m_tiles, n_blk = tile / p.m_tiles;
+      decode(tile, a_blk, b_blk);
       const int row_in_slot = quad * 32 + lane;
-      const int row = m_blk * 256 + (int)cta_rank * 128 + row_in_slot;
-      const uint32_t t_row = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN2 + half_idx * COLS_PER_WARP);
+      const int row = a_blk * 256 + (int)cta_rank * 128 + row_in_slot;   // lane-operand row of this thread
+      const uint32_t t_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN2_MAX);
       const bool split_head = (kb0 == 0 && kb1 < k_blocks);
       const int n_parts = split_head ? sk_contributors(cluster_id, num_clusters, tile, p.sk_tiles, k_blocks) : 0;
       {
@@ -635,9 +809,19 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
         if (warp == 0 && lane == 0) atomicAdd(&g_gemm_prof[3], (unsigned long long)w);
       }
       tc_fence_after();
-      // contributors of this CTA's 128 rows are the same-rank CTAs of the following clusters: slot stride 2
-      epilogue_segment<EPI, COLS_PER_WARP>(p, t_row, half_idx * (COLS_PER_WARP / 32), row, row < p.M, row_in_slot,
-                                           n_blk * BN2 + half_idx * COLS_PER_WARP, kb0 > 0, n_parts, 2, lane);
+      if (SWAP) {
+        // lanes = features (rows of W), columns = tokens (rows of A)
+        const int tok_end = min(p.M, (b_blk + 1) * bn);
+#pragma unroll 1
+        for (int c = c_begin; c < c_end; ++c) {
+          __syncwarp();
+          chunk_swap<EPI>(p, t_acc + 32 * c, row, b_blk * bn + 32 * c, tok_end, lane);
+        }
+      } else {
+        // contributors of this CTA's 128 rows are the same-rank CTAs of the following clusters: slot stride 2
+        epilogue_segment<EPI>(p, t_acc, c_begin, c_end, row, row < p.M, row_in_slot, b_blk * bn,
+                              min(p.N, (b_blk + 1) * bn), kb0 > 0, n_parts, 2, lane);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(acc == 0 ? leader_empty0 : leader_empty1);  // leader's barrier
@@ -749,9 +933,9 @@ int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, in
   return STLLM_OK;
 }
 
-template <int EPI>
+template <int EPI, bool SWAP>
 int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams p, int allow_sk, cudaStream_t stream) {
-  auto kern = gemm_f16_tcgen05_2cta_kernel<EPI>;
+  auto kern = gemm_f16_tcgen05_2cta_kernel<EPI, SWAP>;
   static bool configured = false;
   if (!configured) {
     STLLM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout2::TOTAL));
@@ -760,7 +944,7 @@ int launch_gemm_2cta(const CUtensorMap& tmA, const CUtensorMap& tmB, GemmParams 
   const int tiles = p.m_tiles * p.n_tiles;
   const int k_blocks = (p.K + BK - 1) / BK;
   int clusters = num_sms() / 2;
-  p.sk_tiles = allow_sk ? choose_sk_tiles(tiles, clusters, k_blocks) : 0;
+  p.sk_tiles = (allow_sk && !SWAP) ? choose_sk_tiles(tiles, clusters, k_blocks) : 0;
   if (p.sk_tiles == 0 && tiles < clusters) clusters = tiles;
   STLLM_CHECK_CUDA(stllm_launch(kern, dim3(2 * clusters), dim3(NUM_THREADS), SmemLayout2::TOTAL, stream, tmA, tmB, p));
   return STLLM_OK;
@@ -776,27 +960,88 @@ int dispatch_epi(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const 
     default: stllm_set_last_error("unknown epilogue %d", epi); return STLLM_ERR_BAD_ARG;
   }
 }
+template <bool SWAP>
 int dispatch_epi_2cta(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int sk, cudaStream_t s) {
   switch (epi) {
-    case EPI_NONE: return launch_gemm_2cta<EPI_NONE>(tmA, tmB, p, sk, s);
-    case EPI_GELU: return launch_gemm_2cta<EPI_GELU>(tmA, tmB, p, sk, s);
-    case EPI_SWIGLU: return launch_gemm_2cta<EPI_SWIGLU>(tmA, tmB, p, sk, s);
-    case EPI_RELU: return launch_gemm_2cta<EPI_RELU>(tmA, tmB, p, sk, s);
+    case EPI_NONE: return launch_gemm_2cta<EPI_NONE, SWAP>(tmA, tmB, p, sk, s);
+    case EPI_GELU: return launch_gemm_2cta<EPI_GELU, SWAP>(tmA, tmB, p, sk, s);
+    case EPI_SWIGLU: return launch_gemm_2cta<EPI_SWIGLU, SWAP>(tmA, tmB, p, sk, s);
+    case EPI_RELU: return launch_gemm_2cta<EPI_RELU, SWAP>(tmA, tmB, p, sk, s);
     default: stllm_set_last_error("unknown epilogue %d", epi); return STLLM_ERR_BAD_ARG;
   }
 }
 
-// Cost model (units: k-block times of a 128x256 one-CTA tile).  Measured on B200 (profiles/r01_gemm_ab.log): a
-// CTA-pair tile runs ~11 % faster per FLOP than a one-CTA tile, and a stream-K'ed last wave costs its fill fraction
-// plus ~1.5 k-block times of fix-up.
-double sched_cost(int tiles, int workers, int k_blocks, double tile_cost, bool sk_possible) {
+// ------------------------------------------------------------------------------------------------
+// Cost model, in SM cycles.  Per k-block (K = 64) a tile costs max(MMA time, operand ingest):
+//   MMA:    2 * columns cycles per 128 accumulator rows (8192 FLOP/cycle/SM, measured 96 % on 8192^3)
+//   ingest: bytes TMA brings into one SM per k-block / ~80 B/cycle (one-CTA 128x256 tiles at 96 B/cycle wait 16 % of
+//           the time for data, CTA-pair 256x256 tiles at 64 B/cycle < 1 %: profiles/r01_gemm_ab.md)
+// plus a fixed cost per tile (accumulator hand-over, pipeline bubble) and the un-overlapped epilogue of the last tile.
+// Waves = ceil(tiles / workers): tile-count quantisation is the dominant loss on this path (M = 4112, 576; N = 1408),
+// which is why the CTA-pair engine takes any tile width that is a multiple of 16 and can swap the operands.
+// ------------------------------------------------------------------------------------------------
+constexpr double INGEST_B_PER_CYCLE = 80.0;
+constexpr double TILE_FIXED_CYCLES = 500.0;
+
+double kb_cycles(int cols, int bytes_per_sm) {
+  const double mma = 2.0 * cols, ing = bytes_per_sm / INGEST_B_PER_CYCLE;
+  return mma > ing ? mma : ing;
+}
+double sched_cost(int tiles, int workers, int k_blocks, double kb_cost, double epi_tail, bool sk_possible) {
   const int full = tiles / workers, rem = tiles % workers;
+  const double tile_cost = k_blocks * kb_cost + TILE_FIXED_CYCLES;
   double waves = full;
   if (rem > 0) {
     const bool sk = sk_possible && choose_sk_tiles(tiles, workers, k_blocks) > 0;
     waves += sk ? ((double)rem / workers + 1.5 / k_blocks) : 1.0;
   }
-  return waves * k_blocks * tile_cost;
+  return waves * tile_cost + epi_tail;
+}
+
+struct GemmPlan {
+  int engine;   // 0: one-CTA (bn in {64,128,256})  1: CTA pair  2: CTA pair, operands swapped
+  int bn;
+  double cost;
+};
+
+int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e != nullptr ? atoi(e) : dflt;
+}
+
+GemmPlan plan_gemm(int M, int N, int K, int epi) {
+  static const int flex = env_int("STLLM_GEMM_FLEX", 1);   // 0: round-1 selection (tiles of 64/128/256 columns only)
+  static const int swap_ok = env_int("STLLM_GEMM_SWAP", 1);
+  const int k_blocks = (K + BK - 1) / BK;
+  const int sms = num_sms(), clusters = sms / 2;
+  const int mt = (M + 127) / 128;
+  GemmPlan best = {0, 256, 1e300};
+  auto consider = [&](int engine, int bn, double cost) {
+    if (cost < best.cost) best = GemmPlan{engine, bn, cost};
+  };
+  // one-CTA engine
+  consider(0, 256, sched_cost(mt * ((N + 255) / 256), sms, k_blocks, kb_cycles(256, 16384 + 256 * 128), 8.0 * 256, true));
+  consider(0, 128, 1.03 * sched_cost(mt * ((N + 127) / 128), sms, k_blocks, kb_cycles(128, 16384 + 128 * 128), 8.0 * 128, false));
+  consider(0, 64, 1.03 * sched_cost(mt * ((N + 63) / 64), sms, k_blocks, kb_cycles(64, 16384 + 64 * 128), 8.0 * 64, false));
+  // CTA-pair engine: 256 rows x bn columns per cluster
+  const int m2 = (M + 255) / 256;
+  if (M > 128) {
+    for (int bn = flex ? 96 : 256; bn <= 256; bn += 16) {
+      const int tiles = m2 * ((N + bn - 1) / bn);
+      consider(1, bn, sched_cost(tiles, clusters, k_blocks, kb_cycles(bn, 16384 + bn * 64), 8.0 * bn, bn == 256));
+    }
+  }
+  // swapped operands: 256 features x bn tokens per cluster (transposed epilogue: slightly dearer per element)
+  if (flex && swap_ok && N >= 256 && (epi != EPI_SWIGLU || N % 2 == 0)) {
+    const int f2 = (N + 255) / 256;
+    const int m16 = ((M + 15) / 16) * 16;
+    for (int bn = 16; bn <= 256; bn += 16) {
+      if (bn > m16 && bn != 16) break;
+      const int tiles = f2 * ((M + bn - 1) / bn);
+      consider(2, bn, 1.04 * sched_cost(tiles, clusters, k_blocks, kb_cycles(bn, 16384 + bn * 64), 14.0 * bn, false));
+    }
+  }
+  return best;
 }
 
 }  // namespace
@@ -824,8 +1069,20 @@ extern "C" int stllm_gemm_debug_counters(unsigned long long* out8) {
   return STLLM_OK;
 }
 
-// tile_n: 0 = auto (cost model); 128 / 256 = one-CTA tiles; 512 = CTA-pair tiles; add 1 (129/257/513) to forbid the
-// stream-K treatment of the last wave (pure data-parallel schedule, for A/B measurements).
+// Debug / test aid: the configuration the cost model picks for a shape.  out3 = {engine (0 one-CTA, 1 CTA pair,
+// 2 CTA pair with swapped operands), tile columns, estimated cycles}.  Host only.
+extern "C" int stllm_gemm_plan(int M, int N, int K, int epilogue, long long* out3) {
+  STLLM_CHECK_ARG(out3 != nullptr && M > 0 && N > 0 && K > 0);
+  const GemmPlan pl = plan_gemm(M, N, K, epilogue);
+  out3[0] = pl.engine;
+  out3[1] = pl.bn;
+  out3[2] = (long long)pl.cost;
+  return STLLM_OK;
+}
+
+// tile_n: 0 = auto (cost model); 64 / 128 / 256 = one-CTA tiles; 512 = CTA-pair 256x256 tiles; 1024 + bn = CTA-pair
+// tiles of bn columns (bn multiple of 16, <= 256); 2048 + bn = CTA-pair with swapped operands (256 features x bn tokens);
+// add 1 (257/513/...) to forbid the stream-K treatment of the last wave (pure data-parallel schedule, for A/B runs).
 extern "C" int stllm_gemm_f16(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc,
                               int M, int N, int K, const void* bias, const void* residual, long long ldr,
                               int epilogue, int out_f32, int tile_n, void* stream) {
@@ -837,50 +1094,44 @@ extern "C" int stllm_gemm_f16(const void* A, long long lda, const void* W, long 
   STLLM_CHECK_ARG(epilogue != EPI_SWIGLU || (N % 2 == 0));
   STLLM_CHECK_ARG(ldc >= (epilogue == EPI_SWIGLU ? N / 2 : N));
   STLLM_CHECK_ARG(residual == nullptr || ldr >= (epilogue == EPI_SWIGLU ? N / 2 : N));
-  int bn = tile_n;
-  if (bn == 0) {
-    static int forced = -1;  // experiment knob: STLLM_GEMM_TILE=128|256|512 (+1: no stream-K) forces a configuration
-    if (forced < 0) {
-      const char* e = getenv("STLLM_GEMM_TILE");
-      forced = e ? atoi(e) : 0;
-    }
-    bn = forced;
+  int code = tile_n;
+  if (code == 0) {
+    static const int forced = env_int("STLLM_GEMM_TILE", 0);  // experiment knob: forces one configuration everywhere
+    code = forced;
   }
   int allow_sk = 1;
-  if (bn & 1) { allow_sk = 0; bn -= 1; }
-  const int k_blocks = (K + BK - 1) / BK;
-  if (bn == 0) {
-    // cost per k-block of one tile = max(MMA cycles, operand ingest at ~64 B/clk), relative to the 128x256 tile:
-    //   128x256: max(512, 768) -> 1.00   128x128: max(256, 512) -> 0.67   128x64: max(128, 384) -> 0.50
-    //   CTA pair 256x256 (per 128 rows): 512 cycles, measured 0.89 of the one-CTA tile per FLOP
-    const int mt = (M + 127) / 128;
-    const int t256 = mt * ((N + 255) / 256), t128 = mt * ((N + 127) / 128), t64 = mt * ((N + 63) / 64);
-    const int t2 = ((M + 255) / 256) * ((N + 255) / 256);
-    double best = sched_cost(t256, num_sms(), k_blocks, 1.0, true);
-    bn = 256;
-    const double c2 = sched_cost(t2, num_sms() / 2, k_blocks, 0.89, true);
-    if (M > 128 && c2 < best * 0.97) { best = c2; bn = 512; }
-    const double c128 = sched_cost(t128, num_sms(), k_blocks, 0.67, false);
-    if (c128 < best * 0.9) { best = c128; bn = 128; }
-    const double c64 = sched_cost(t64, num_sms(), k_blocks, 0.50, false);
-    if (c64 < best * 0.9) { best = c64; bn = 64; }
-  }
-  STLLM_CHECK_ARG(bn == 64 || bn == 128 || bn == 256 || bn == 512);
+  if (code & 1) { allow_sk = 0; code -= 1; }
+  GemmPlan pl;
+  if (code == 0) pl = plan_gemm(M, N, K, epilogue);
+  else if (code == 64 || code == 128 || code == 256) pl = GemmPlan{0, code, 0};
+  else if (code == 512) pl = GemmPlan{1, 256, 0};
+  else if (code > 1024 && code <= 1024 + 256) pl = GemmPlan{1, code - 1024, 0};
+  else if (code > 2048 && code <= 2048 + 256) pl = GemmPlan{2, code - 2048, 0};
+  else { stllm_set_last_error("stllm_gemm_f16: unknown tile_n code %d", tile_n); return STLLM_ERR_BAD_ARG; }
+  STLLM_CHECK_ARG(pl.bn >= 16 && pl.bn <= 256 && pl.bn % 16 == 0);
+  const bool swap = pl.engine == 2;
+  // lane operand (128-row boxes) and column operand (bn or bn/2-row boxes)
+  const void* lane_ptr = swap ? W : A;
+  const void* col_ptr = swap ? A : W;
+  const long long lane_rows = swap ? N : M, col_rows = swap ? M : N;
+  const long long lane_ld = swap ? ldw : lda, col_ld = swap ? lda : ldw;
   CUtensorMap tmA, tmB;
-  int rc = make_tmap(&tmA, A, M, K, lda, BM);
+  int rc = make_tmap(&tmA, lane_ptr, lane_rows, K, lane_ld, BM);
   if (rc != STLLM_OK) return rc;
-  rc = make_tmap(&tmB, W, N, K, ldw, bn == 512 ? 128 : bn);
+  rc = make_tmap(&tmB, col_ptr, col_rows, K, col_ld, pl.engine == 0 ? pl.bn : pl.bn / 2);
   if (rc != STLLM_OK) return rc;
   GemmParams p;
   {
-    static int hint_mode = -1;   // STLLM_GEMM_HINT: 0 = evict-normal for both operands, 1 = activations last / weights first
-    if (hint_mode < 0) {
-      const char* e = getenv("STLLM_GEMM_HINT");
-      hint_mode = e ? atoi(e) : 1;   // A/B (4 alternating bench runs): 743/733 vs 740/733 frames/s, GEMM -0.7 %
-    }
-    p.hint_a = hint_mode == 1 ? TMA_EVICT_LAST : TMA_EVICT_NORMAL;
-    p.hint_b = hint_mode == 1 ? TMA_EVICT_FIRST : TMA_EVICT_NORMAL;
+    // STLLM_GEMM_HINT: 0 = evict-normal for both operands, 1 = activations evict-last / weights evict-first
+    static const int hint_mode = env_int("STLLM_GEMM_HINT", 1);   // A/B (4 alternating bench runs): GEMM time -0.7 %
+    const unsigned long long h_act = hint_mode == 1 ? TMA_EVICT_LAST : TMA_EVICT_NORMAL;
+    const unsigned long long h_w = hint_mode == 1 ? TMA_EVICT_FIRST : TMA_EVICT_NORMAL;
+    p.hint_a = swap ? h_w : h_act;
+    p.hint_b = swap ? h_act : h_w;
   }
+  static const int w_prefetch = env_int("STLLM_GEMM_WPREFETCH", 1);
+  p.w_prefetch = w_prefetch;
+  p.bn = pl.bn;
   p.C = C;
   p.bias = reinterpret_cast<const __half*>(bias);
   p.residual = reinterpret_cast<const __half*>(residual);
@@ -894,14 +1145,16 @@ extern "C" int stllm_gemm_f16(const void* A, long long lda, const void* W, long 
   p.sk_ws = g_sk_ws;
   p.sk_flags = g_sk_flags;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
-  if (bn == 512) {
-    p.m_tiles = (M + 255) / 256;
-    p.n_tiles = (N + 255) / 256;
-    return dispatch_epi_2cta(epilogue, tmA, tmB, p, allow_sk, s);
+  if (pl.engine != 0) {
+    p.m_tiles = (int)((lane_rows + 255) / 256);
+    p.n_tiles = (int)((col_rows + pl.bn - 1) / pl.bn);
+    return swap ? dispatch_epi_2cta<true>(epilogue, tmA, tmB, p, 0, s)
+                : dispatch_epi_2cta<false>(epilogue, tmA, tmB, p, allow_sk, s);
   }
   p.m_tiles = (M + BM - 1) / BM;
-  p.n_tiles = (N + bn - 1) / bn;
-  if (bn == 256) return dispatch_epi<256, 4>(epilogue, tmA, tmB, p, allow_sk, s);
-  if (bn == 128) return dispatch_epi<128, 6>(epilogue, tmA, tmB, p, allow_sk, s);
+  p.n_tiles = (N + pl.bn - 1) / pl.bn;
+  if (pl.bn == 256) return dispatch_epi<256, 4>(epilogue, tmA, tmB, p, allow_sk, s);
+  if (pl.bn == 128) return dispatch_epi<128, 6>(epilogue, tmA, tmB, p, allow_sk, s);
+  STLLM_CHECK_ARG(pl.bn == 64);
   return dispatch_epi<64, 8>(epilogue, tmA, tmB, p, allow_sk, s);
 }

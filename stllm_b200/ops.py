@@ -90,6 +90,13 @@ def gemm(a, w, bias=None, residual=None, epilogue=EPI_NONE, out=None, out_dtype=
     return out
 
 
+def gemm_plan(M, N, K, epilogue=EPI_NONE):
+    """(engine, tile columns, estimated cycles) the host cost model picks: engine 0 one-CTA, 1 CTA pair, 2 swapped"""
+    out = (ctypes.c_longlong * 3)()
+    _lib.check(_lib.load().stllm_gemm_plan(M, N, K, epilogue, out), "stllm_gemm_plan")
+    return int(out[0]), int(out[1]), int(out[2])
+
+
 def _strides3(t, layout):
     """(batch, seq, head) element strides of a 4-D tensor given as 'bshd' or 'bhsd'"""
     assert t.dim() == 4 and t.stride(-1) == 1
