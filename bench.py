@@ -276,7 +276,8 @@ def main():
     def replay_gemms():
         for r in rec:
             ops.gemm(r["a"], r["w"], bias=r["bias"], residual=r["residual"], epilogue=r["epilogue"],
-                     out=scratch[(tuple(r["out"].shape), r["out"].dtype)], tile_n=r["tile_n"])
+                     out=scratch[(tuple(r["out"].shape), r["out"].dtype)], tile_n=r["tile_n"], norm=r["norm"],
+                     rs_in=r["rs_in"], col_sb=r["col_sb"], norm_eps=r["norm_eps"])
 
     replay_gemms()
     torch.cuda.synchronize()

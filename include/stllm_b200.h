@@ -52,6 +52,24 @@ int stllm_gemm_f16(const void* A, long long lda, const void* W, long long ldw, v
                    int K, const void* bias, const void* residual, long long ldr, int epilogue, int out_f32,
                    int tile_n, void* stream);
 
+/* stllm_gemm_f16 with the LayerNorm / RMSNorm in front of the Linear FOLDED into the GEMM, so that the norms of
+ * eva_vit.py:157,163 (Block.norm1/norm2) and modeling_llama_mem.py:61-78 (input / post-attention RMSNorm) need no
+ * kernel of their own.  A holds the UN-normalised rows x; W holds W' = gamma (.) W (packed once by the host);
+ *   norm_mode 1 (RMSNorm):   C = epi(rstd_m * (x W'^T) + bias)            rstd_m = rsqrt(sum x^2 / K + eps)
+ *   norm_mode 2 (LayerNorm): C = epi(rstd_m * (x W'^T - mu_m s_n) + b'_n) col_sb[n] = (s_n = sum_k W'_nk,
+ *                            b'_n = bias_n + sum_k beta_k W_nk); `bias` must be NULL
+ * The statistics come from the GEMM that PRODUCED x: rs_out_mode 1 / 2 makes its epilogue store sum(c^2) / (sum c,
+ * sum c^2) of the values it wrote (after bias, activation and residual), per row and per 128-column slot -- plain
+ * stores to distinct slots, summed in slot order by the consumer: deterministic, no atomics, no zeroing.  A
+ * statistics row is [slots][mode] floats, slots = ceil(columns / 128), with a row stride (rs_*_stride, in floats) that
+ * is a multiple of 8; padding floats must be zero.  Both features need tokens on the accumulator lanes and 256-column
+ * tiles on the producer: the planner restricts itself accordingly. */
+int stllm_gemm_norm_f16(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M,
+                        int N, int K, const void* bias, const void* residual, long long ldr, int epilogue,
+                        int out_f32, int tile_n, int norm_mode, const float* rs_in, int rs_in_stride,
+                        const float* col_sb, float norm_eps, float* rs_out, int rs_out_mode, int rs_out_stride,
+                        void* stream);
+
 /* The configuration the cost model picks for a shape (host only, no launch): out3 = {engine: 0 one-CTA, 1 CTA pair,
  * 2 CTA pair with swapped operands; tile columns; estimated SM cycles}. */
 int stllm_gemm_plan(int M, int N, int K, int epilogue, long long* out3);
@@ -65,6 +83,11 @@ int stllm_set_gemm_workspace(void* ptr, long long bytes);
 /* Debug aid: copies and resets 8 cycle counters of the GEMM kernels ([0] producer waits, [1] MMA waits for TMA data,
  * [2] MMA waits for a free accumulator, [3] epilogue waits, [4] CTA-0 kernel cycles, [5] launches).  Synchronises. */
 int stllm_gemm_debug_counters(unsigned long long* out8);
+
+/* Debug aid: per-CTA phase timestamps (%globaltimer ns) of the last 4 CTA-pair GEMM launches: out[4][160][12] =
+ * {entry, set-up done, producer past griddepcontrol.wait, first stage landed, last MMA committed, last epilogue done,
+ * exit, tiles, MMA-phase SM cycles, cycles waiting for operands, cycles waiting for an accumulator, -}.  on != 0 enables tracing for the following launches; next_slot = slot the next launch writes. */
+int stllm_gemm_debug_trace(int on, unsigned long long* out, int* next_slot);
 
 /* out[b,s,h,:] = softmax(scale * q k^T + mask) v   (flash-style, fp32 softmax).  Strides: {batch, seq, head} in
  * elements, multiples of 8.  q_prescale != 0: q <- fp16(q * q_prescale) first (eva_vit.py:128).

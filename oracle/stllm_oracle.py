@@ -82,6 +82,97 @@ def vit_forward(sd, frames, depth, num_heads, patch=14, collect=None):
     return x
 
 
+# --------------------------------------------------------------------------------------------------
+# BT-Adapter encoder  (stllm/models/eva_btadapter.py) -- the vit_model="eva_btadapter_g" encoder of the shipped
+# QA / MVBench configs: EVA-ViT-g plus a temporal+spatial branch on the last `bt_depth` blocks
+# --------------------------------------------------------------------------------------------------
+
+
+def _bt_temporal(sd, j, x, T, num_heads, eps=1e-6):
+    """BTAdapter_Temp.forward, eva_btadapter.py:291-308: attention over the T frames of each patch position,
+    temporal_fc, residual; the cls row passes through"""
+    p = f"BTAdapter_T.{j}."
+    residual = x[:, 1:, :]
+    init_cls = x[:, :1, :]
+    b, pt, m = residual.shape
+    pn = pt // T
+    q = residual.reshape(b * pn, T, m)                                            # :300 rows are (p t)-ordered
+    h = F.layer_norm(q, (m,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], eps)
+    h = vit_attention(sd, p + "attn.", h, num_heads)                              # :302 (drop_path: eval identity)
+    h = F.linear(h, sd[p + "temporal_fc.weight"], sd[p + "temporal_fc.bias"])     # :304
+    return torch.cat((init_cls, h.reshape(b, pn * T, m) + residual), 1)           # :306-307
+
+
+def _bt_spatial(sd, j, x, T, num_heads, eps=1e-6):
+    """BTAdapter_Spatial.forward, eva_btadapter.py:258-279: a ViT Block applied per frame on [cls ; patches of that
+    frame]; the cls output is averaged over frames"""
+    p = f"BTAdapter_S.{j}."
+    residual = x
+    init_cls = x[:, :1, :]
+    qs = x[:, 1:, :]
+    b, pt, m = qs.shape
+    pn = pt // T
+    cls = init_cls.unsqueeze(1).repeat(1, T, 1, 1).reshape(b * T, 1, m)           # :267
+    qs = qs.reshape(b, pn, T, m).permute(0, 2, 1, 3).reshape(b * T, pn, m)        # 'b (p t) m -> (b t) p m' :268
+    h = torch.cat((cls, qs), 1)
+    h = F.layer_norm(h, (m,), sd[p + "norm1.weight"], sd[p + "norm1.bias"], eps)
+    h = vit_attention(sd, p + "attn.", h, num_heads)                              # :271
+    cls = h[:, :1, :].reshape(b, T, 1, m).mean(1)                                 # :273
+    rs = h[:, 1:, :].reshape(b, T, pn, m).permute(0, 2, 1, 3).reshape(b, pn * T, m)   # '(b t) p m -> b (p t) m' :274
+    x = residual + torch.cat((cls, rs), 1)                                        # :276
+    h = F.layer_norm(x, (m,), sd[p + "norm2.weight"], sd[p + "norm2.bias"], eps)
+    h = F.gelu(F.linear(h, sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"]))
+    return x + F.linear(h, sd[p + "mlp.fc2.weight"], sd[p + "mlp.fc2.bias"])      # :277
+
+
+def _bt_init_input(sd, x4):
+    """EVAVisionTransformer_BTAdapter.init_input, eva_btadapter.py:203-226 (mask=None: mask_rate 0 / eval)"""
+    b, t, l1, d = x4.shape
+    cls_x = x4[:, :, 0].mean(dim=1).unsqueeze(1)                                  # :204
+    x = x4[:, :, 1:, :].reshape(b * t, l1 - 1, d)                                 # :205-207
+    cls_branch = sd["BTAdapter_cls"].expand(x.shape[0], 1, -1)                    # :209
+    x = torch.cat((cls_branch, x), dim=1) + sd["pos_embed"]                       # :210-211
+    cls_branch = x[:b, 0, :].unsqueeze(1)                                         # :214
+    x = x[:, 1:, :].reshape(b, t, l1 - 1, d).permute(0, 2, 1, 3)                  # '(b t) l d -> (b l) t d' :215
+    x = x + sd["BTAdapter_position.weight"][:t][None, None]                       # :216-218
+    x = x.reshape(b, (l1 - 1) * t, d)                                             # '(b l) t d -> b (l t) d' :220
+    cls = (cls_x + cls_branch) / 2                                                # :223
+    return torch.cat((cls, x), dim=1)
+
+
+def bt_adapter_forward(sd, frames, depth, num_heads, bt_depth=3, patch=14, collect=None):
+    """EVAVisionTransformer_BTAdapter.forward / forward_features, eva_btadapter.py:147-181,228-250.
+    frames [B,T,3,H,W] (or [T,3,H,W] = one clip, :236-238) -> [(B T), 1+P, D]"""
+    if frames.dim() == 4:
+        frames = frames[None]
+    B, T = frames.shape[:2]
+    x = vit_patch_embed(sd, frames.reshape((-1,) + frames.shape[2:]), patch)
+    x = torch.cat((sd["cls_token"].expand(x.shape[0], -1, -1), x), dim=1) + sd["pos_embed"]   # :152-156
+    branch = None
+    for i in range(depth):
+        x = vit_block(sd, i, x, num_heads)
+        if i >= depth - bt_depth:                                                 # :166-168
+            j = i + bt_depth - depth
+            x4 = x.reshape(B, T, x.shape[1], x.shape[2])                          # forward_branch :184
+            if branch is not None:
+                cls_branch = x4[:, :, 0].mean(dim=1).unsqueeze(1)                 # :186-187
+                xp = x4[:, :, 1:].permute(0, 2, 1, 3).reshape(B, -1, x.shape[2])  # 'b t l d -> b (l t) d' :188
+                z = torch.cat((cls_branch, xp), dim=1) + branch                   # :192-193
+            else:
+                z = x4
+            if j == 0:
+                z = _bt_init_input(sd, z)                                         # :195-196
+            z = _bt_temporal(sd, j, z, T, num_heads)                              # :202
+            branch = _bt_spatial(sd, j, z, T, num_heads)
+            if collect is not None:
+                collect[f"bt_branch{j}"] = branch
+    pn = x.shape[1] - 1                                                           # :178-181
+    b_cls, b_patch = branch[:, 0], branch[:, 1:]
+    b_patch = b_patch.reshape(B, pn, T, -1).permute(0, 2, 1, 3).reshape(B * T, pn, -1)   # 'b (p t) m -> (b t) p m'
+    b_cls = b_cls.repeat(1, T).view(B * T, -1).unsqueeze(1)
+    return (x + torch.cat((b_cls, b_patch), dim=1)) / 2
+
+
 def ln_vision(sd, x, eps=1e-5):
     """blip2.LayerNorm (fp32 LayerNorm, nn default eps), blip2.py:73,103-109; call site st_llm.py:331"""
     return F.layer_norm(x.float(), (x.shape[-1],), sd["weight"], sd["bias"], eps)

@@ -65,6 +65,56 @@ def gemm_case(M, N, K, epi=ops.EPI_NONE, bias=False, residual=False, tile_n=0, o
     return report(name, out, ref, atol=2e-2 if not out_f32 else 5e-3, rtol=1e-2)
 
 
+def norm_gemm_case(M, N, K, mode, epi=ops.EPI_NONE, residual=False, tile_n=0):
+    """GEMM with a folded RMSNorm (mode 1) / LayerNorm (mode 2) against norm -> fp16 -> linear in fp32 torch, with the
+    row statistics produced by a preceding GEMM's rs_out epilogue (so both halves of the fusion are exercised)"""
+    eps = 1e-6
+    # producer: x = a0 @ w0^T + r0, statistics accumulated by its epilogue
+    a0 = torch.randn(M, 256, device=dev, dtype=torch.float16)
+    w0 = torch.randn(K, 256, device=dev, dtype=torch.float16) * 0.08
+    r0 = torch.randn(M, K, device=dev, dtype=torch.float16) * 0.5 + 0.3
+    stats = ops.row_stats_buffer(1, M, K, mode, dev)[0]
+    stats.fill_(123.0)                       # every live slot must be overwritten ...
+    stats[:, ((K + 127) // 128) * mode:] = 0   # ... the padding stays zero
+    x = ops.gemm(a0, w0, residual=r0, rs_out=stats, rs_out_mode=mode)
+    xf = x.float()
+    ref_stats = torch.stack((xf.sum(1), (xf * xf).sum(1)), 1) if mode == 2 else (xf * xf).sum(1, keepdim=True)
+    got_stats = stats.view(M, -1, mode).sum(1)
+    ok1 = report(f"gemm rs_out mode={mode} M={M} K={K}", got_stats, ref_stats, atol=2e-2, rtol=2e-3)
+    stats2 = stats.clone()
+    ops.gemm(a0, w0, residual=r0, rs_out=stats2, rs_out_mode=mode)
+    report(f"gemm rs_out deterministic mode={mode} M={M}", stats2, stats, 0, 0)
+    gamma = torch.randn(K, device=dev) * 0.2 + 1.0
+    beta = torch.randn(K, device=dev) * 0.1
+    w = torch.randn(N, K, device=dev, dtype=torch.float16) * 0.05
+    b = torch.randn(N, device=dev, dtype=torch.float16) * 0.5
+    n_out = N // 2 if epi == ops.EPI_SWIGLU else N
+    r = torch.randn(M, n_out, device=dev, dtype=torch.float16) if residual else None
+    if mode == 1:
+        hn = (xf * torch.rsqrt((xf * xf).mean(-1, keepdim=True) + eps)).half().float() * gamma.half().float()
+        ref = hn.half().float() @ w.float().t()
+        w2 = (w.float() * gamma.half().float()[None, :]).half().contiguous()
+        kw = dict(norm=ops.NORM_RMS, rs_in=stats, norm_eps=eps)
+    else:
+        hn = torch.nn.functional.layer_norm(xf, (K,), gamma, beta, eps)
+        ref = hn.half().float() @ w.float().t() + b.float()
+        w2 = (w.float() * gamma[None, :]).half().contiguous()
+        sb = torch.stack((w2.float().sum(1), b.float() + w.float() @ beta), 1).contiguous()
+        kw = dict(norm=ops.NORM_LN, rs_in=stats, col_sb=sb, norm_eps=eps)
+    if epi == ops.EPI_GELU:
+        ref = torch.nn.functional.gelu(ref)
+    elif epi == ops.EPI_SWIGLU:
+        ref = torch.nn.functional.silu(ref[:, 0::2]) * ref[:, 1::2]
+    if residual:
+        ref = ref + r.float()
+    out = ops.gemm(x, w2, residual=r, epilogue=epi, tile_n=tile_n, **kw)
+    torch.cuda.synchronize()
+    # SwiGLU multiplies two O(10) numbers: the element-wise bound scales with the output range
+    ok2 = report(f"gemm folded norm mode={mode} M={M} N={N} K={K} epi={epi} res={int(residual)} tn={tile_n}", out, ref,
+                 atol=3e-2 if epi != ops.EPI_SWIGLU else 1e-3 * ref.abs().max().item(), rtol=2e-2)
+    return ok1 and ok2
+
+
 def attn_ref(q, k, v, scale, causal, key_mask, mask_value, q_prescale):
     qf, kf, vf = q.float(), k.float(), v.float()
     if q_prescale:
@@ -223,6 +273,17 @@ def main():
     for _ in range(3):                                             # back-to-back launches (PDL + weight prefetch)
         gemm_case(576, 4096, 4096, residual=True)
         gemm_case(4112, 1408, 1408, bias=True, residual=True)
+    # --- LayerNorm / RMSNorm folded into the GEMM + row statistics from the producing GEMM ---
+    norm_gemm_case(576, 12288, 4096, 1)
+    norm_gemm_case(576, 22016, 4096, 1, epi=ops.EPI_SWIGLU)
+    norm_gemm_case(576, 22016, 4096, 1, epi=ops.EPI_SWIGLU, tile_n=257)
+    norm_gemm_case(300, 700, 512, 1, residual=True, tile_n=129)
+    norm_gemm_case(5, 1024, 4096, 1)
+    norm_gemm_case(4112, 4224, 1408, 2)
+    norm_gemm_case(4112, 6144, 1408, 2, epi=ops.EPI_GELU)
+    norm_gemm_case(4112, 6144, 1408, 2, epi=ops.EPI_GELU, tile_n=257)
+    norm_gemm_case(300, 700, 512, 2, residual=True, tile_n=1024 + 176)
+    norm_gemm_case(300, 700, 512, 2, tile_n=65)
     # --- attention: tcgen05 kernel (ViT / Llama prefill shapes) and mma.sync kernel on the same cases ---
     from stllm_b200 import _lib as _L
     for tc in (1, 0):

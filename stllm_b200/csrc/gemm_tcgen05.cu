@@ -52,6 +52,22 @@ struct GemmParams {
   int out_f32;    // 0: fp16 output, 1: fp32 output
   int bn;         // CTA-pair engine: accumulator columns per tile (multiple of 16, <= 256), chosen per shape
   int w_prefetch; // 1: the weight operand is static -> its first stages are loaded BEFORE griddepcontrol.wait
+  int trace;      // debug: 1 + slot (0..3) -> per-CTA phase timestamps into g_gemm_trace[slot] (CTA-pair engine)
+  // --- normalisation folded into the GEMM (removes the standalone LayerNorm / RMSNorm launches) ---
+  //   consumer side: A holds the UN-normalised rows x, W holds gamma-scaled weights W' = gamma (.) W, and
+  //     mode 1 (RMSNorm):   C = rstd_m * (x W'^T)                              rstd_m = rsqrt(sumsq_m / K + eps)
+  //     mode 2 (LayerNorm): C = rstd_m * (x W'^T - mu_m * s_n) + b'_n          s_n = sum_k W'_nk, b'_n = b_n + beta.W_n
+  //   producer side: the kernel that writes x stores, per row and per 128-column slot, sum(x) / sum(x^2) of the
+  //   values it wrote (plain stores to distinct slots, summed in slot order by the consumer: deterministic, no
+  //   atomics, no zeroing).  Row layout: [slots][mode] floats, row stride rs_*_stride floats (multiple of 8).
+  int norm_mode;
+  const float* rs_in;
+  int rs_in_stride;
+  const float2* col_sb;   // mode 2: [N] (s_n, b'_n)
+  float norm_eps, norm_inv_k;
+  float* rs_out;
+  int rs_out_mode;        // 1: sum of squares; 2: (sum, sum of squares)
+  int rs_out_stride;
   int sk_tiles;   // number of leading tiles scheduled stream-K (0 = pure data-parallel)
   float* sk_ws;   // per-CTA fp32 partial-tile slots [gridDim.x][SLOT_ELEMS]
   int* sk_flags;  // per-CTA arrival counters (zero between launches)
@@ -107,13 +123,25 @@ struct SmemLayout {
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + alignment slack
+  static constexpr int TAB_OFFSET = BAR_OFFSET + 256;   // 2 x 256 float2: per-column (s, b') of the folded LayerNorm
+  static constexpr int TOTAL = TAB_OFFSET + 4096 + 1024;  // barriers + table + alignment slack
 };
 
 // wait-cycle counters (debug/profiling aid, read by stllm_gemm_debug_counters):
 //  [0] producer waiting for a free smem slot   [1] MMA waiting for TMA data   [2] MMA waiting for a free accumulator
 //  [3] epilogue (warp 2) waiting for an accumulator   [4] total kernel cycles of CTA 0's MMA warp   [5] launches
 __device__ unsigned long long g_gemm_prof[8];
+// debug timeline (STLLM_GEMM_TRACE=1): %globaltimer (ns) per CTA at  [0] kernel entry  [1] barriers/TMEM set up
+// [2] producer passed griddepcontrol.wait  [3] first operand stage landed (MMA starts)  [4] last MMA committed
+// [5] epilogue of the last tile done (warp 0)  [6] kernel exit;  [7] tiles processed by this CTA
+// [8] SM cycles between [3] and [4]  [9] cycles the MMA issuer waited for operand stages  [10] ... for a free accumulator
+__device__ unsigned long long g_gemm_trace[4][160][12];
+DEVI unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define TRACE(slot_idx) do { if (p.trace && blockIdx.x < 160) g_gemm_trace[p.trace - 1][blockIdx.x][slot_idx] = globaltimer_ns(); } while (0)
 
 DEVI float rcp_approx(float x) {
   float r;
@@ -156,13 +184,72 @@ DEVI long long slot_off(int chunk_global, int q, int row_in_slot) {
   return ((long long)(chunk_global * 8 + q) * 128 + row_in_slot) * 4;
 }
 
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): one full 32-byte sector per thread and instruction.  The
+// epilogue's thread-per-row layout cannot coalesce across lanes, so full-sector accesses are what keeps the L2 write
+// path efficient (16-byte stores write half sectors: twice the transactions for the same bytes).
+DEVI void ldg_nc_v8(const void* ptr, uint32_t (&r)[8]) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(ptr));
+}
+DEVI void stg_v8(void* ptr, const uint32_t (&r)[8]) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(ptr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
+// per-thread (= per output row) context of the fused epilogue for one tile
+struct RowCtx {
+  float mu, rstd;         // folded normalisation of this row (mode 0: unused)
+  float st_sum, st_sq;    // statistics of the values this thread wrote (rs_out)
+  const float2* tab;      // smem: (s_n, b'_n) of the tile's columns (mode 2)
+};
+DEVI void rowctx_begin(RowCtx& rc, const GemmParams& p, int row, bool row_ok) {
+  rc.mu = 0.f;
+  rc.rstd = 1.f;
+  rc.st_sum = 0.f;
+  rc.st_sq = 0.f;
+  if (p.norm_mode != 0 && row_ok) {
+    // fixed-order sum of the per-slot partial statistics of this row (written by the producing GEMM)
+    const float4* sp = reinterpret_cast<const float4*>(p.rs_in + (long long)row * p.rs_in_stride);
+    float s0 = 0.f, s1 = 0.f;
+    for (int i = 0; i < (p.rs_in_stride >> 2); ++i) {
+      const float4 f = __ldcg(sp + i);
+      if (p.norm_mode == 1) {
+        s1 += (f.x + f.y) + (f.z + f.w);
+      } else {
+        s0 += f.x + f.z;
+        s1 += f.y + f.w;
+      }
+    }
+    if (p.norm_mode == 1) {
+      rc.rstd = rsqrtf(s1 * p.norm_inv_k + p.norm_eps);
+    } else {
+      rc.mu = s0 * p.norm_inv_k;
+      rc.rstd = rsqrtf(fmaxf(s1 * p.norm_inv_k - rc.mu * rc.mu, 0.f) + p.norm_eps);
+    }
+  }
+}
+// `col0`: first global output column of the 128 columns this thread covered in this tile (slot = col0 / 128)
+DEVI void rowctx_end(const RowCtx& rc, const GemmParams& p, int row, bool row_ok, int col0) {
+  if (p.rs_out == nullptr || !row_ok) return;
+  const int off = (col0 >> 7) * p.rs_out_mode;
+  if (off + p.rs_out_mode > p.rs_out_stride) return;
+  float* dst = p.rs_out + (long long)row * p.rs_out_stride + off;
+  if (p.rs_out_mode == 1) {
+    dst[0] = rc.st_sq;
+  } else {
+    *reinterpret_cast<float2*>(dst) = make_float2(rc.st_sum, rc.st_sq);
+  }
+}
+
 template <int EPI>
 struct ChunkIn {
-  static constexpr int NC = (EPI == EPI_SWIGLU) ? 16 : 32;
+  static constexpr int NC = (EPI == EPI_SWIGLU) ? 16 : 32;   // output columns per 32-column accumulator chunk
   uint32_t r[32];
-  uint4 bq[4];
-  uint4 rq[NC / 8];
-  int nvec;            // accumulator columns of this chunk handled by 16-byte vector accesses: 32, 16 or 0 (scalar path)
+  uint32_t bq[2][8];        // bias: 2 groups of 16 accumulator columns (32 bytes each)
+  uint32_t rq[NC / 16][8];  // residual: groups of 16 output columns
+  int nvec;                 // accumulator columns of this chunk handled by vector accesses: 32, 16 or 0 (scalar path)
   bool bias_vec, res_vec;
 };
 
@@ -176,23 +263,24 @@ DEVI void chunk_issue(ChunkIn<EPI>& in, const GemmParams& p, uint32_t taddr, int
   tmem_ld_32x32b_x32(taddr, in.r);
   const int valid = col_end - col0;
   in.nvec = !active ? 0 : (valid >= 32 ? 32 : (valid == 16 ? 16 : 0));
-  in.bias_vec = in.nvec > 0 && p.bias != nullptr;
+  if (EPI == EPI_SWIGLU && in.nvec == 16) in.nvec = 0;   // 8 outputs: not worth a vector variant
+  in.bias_vec = in.nvec > 0 && p.bias != nullptr && ((reinterpret_cast<uintptr_t>(p.bias + col0) & 31) == 0);
   const __half* rp = active && p.residual != nullptr ? p.residual + (long long)row * p.ldr + ocol0 : nullptr;
-  in.res_vec = rp != nullptr && in.nvec > 0 && ((reinterpret_cast<uintptr_t>(rp) & 15) == 0);
+  in.res_vec = rp != nullptr && in.nvec > 0 && ((reinterpret_cast<uintptr_t>(rp) & 31) == 0);
   if (in.bias_vec) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-      if (q * 8 < in.nvec) in.bq[q] = __ldg(reinterpret_cast<const uint4*>(p.bias + col0) + q);
+    for (int g = 0; g < 2; ++g)
+      if (g * 16 < in.nvec) ldg_nc_v8(p.bias + col0 + g * 16, in.bq[g]);
   }
   if (in.res_vec) {
 #pragma unroll
-    for (int q = 0; q < NC / 8; ++q)
-      if (q * 8 * (32 / NC) < in.nvec) in.rq[q] = __ldg(reinterpret_cast<const uint4*>(rp) + q);
+    for (int g = 0; g < NC / 16; ++g)
+      if (g * 16 * (32 / NC) < in.nvec) ldg_nc_v8(rp + g * 16, in.rq[g]);
   }
 }
 
 template <int EPI>
-DEVI void chunk_finish(const ChunkIn<EPI>& in, const GemmParams& p, int row, bool row_ok, int col0, int col_end,
+DEVI void chunk_finish(const ChunkIn<EPI>& in, const GemmParams& p, RowCtx& rc, int row, bool row_ok, int col0, int col_end,
                        const float* part0, int n_parts, long long part_stride, int chunk_global, int row_in_slot) {
   constexpr int NC = ChunkIn<EPI>::NC;
   const int ocol0 = (EPI == EPI_SWIGLU) ? (col0 >> 1) : col0;
@@ -214,17 +302,29 @@ DEVI void chunk_finish(const ChunkIn<EPI>& in, const GemmParams& p, int row, boo
       }
     }
   }
+  if (p.norm_mode == 1) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] *= rc.rstd;
+  } else if (p.norm_mode == 2) {
+    const float4* t4 = reinterpret_cast<const float4*>(rc.tab + chunk_global * 32);   // broadcast LDS.128: 2 columns
+    const float nmu = -rc.mu;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float4 sb = t4[j];
+      v[2 * j] = fmaf(rc.rstd, fmaf(nmu, sb.x, v[2 * j]), sb.y);
+      v[2 * j + 1] = fmaf(rc.rstd, fmaf(nmu, sb.z, v[2 * j + 1]), sb.w);
+    }
+  }
   if (p.bias != nullptr) {
     if (in.bias_vec) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (q * 8 < in.nvec) {
-          const __half2* bh = reinterpret_cast<const __half2*>(&in.bq[q]);
+      for (int g = 0; g < 2; ++g) {
+        if (g * 16 < in.nvec) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 f = __half22float2(bh[j]);
-            v[q * 8 + 2 * j] += f.x;
-            v[q * 8 + 2 * j + 1] += f.y;
+          for (int j = 0; j < 8; ++j) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&in.bq[g][j]));
+            v[g * 16 + 2 * j] += f.x;
+            v[g * 16 + 2 * j + 1] += f.y;
           }
         }
       }
@@ -251,14 +351,13 @@ DEVI void chunk_finish(const ChunkIn<EPI>& in, const GemmParams& p, int row, boo
     const __half* rp = p.residual + (long long)row * p.ldr + ocol0;
     if (in.res_vec) {
 #pragma unroll
-      for (int q = 0; q < NC / 8; ++q) {
-        if (q * 8 < nvec_out) {
-          const __half2* bh = reinterpret_cast<const __half2*>(&in.rq[q]);
+      for (int g = 0; g < NC / 16; ++g) {
+        if (g * 16 < nvec_out) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float2 f = __half22float2(bh[j]);
-            v[q * 8 + 2 * j] += f.x;
-            v[q * 8 + 2 * j + 1] += f.y;
+          for (int j = 0; j < 8; ++j) {
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&in.rq[g][j]));
+            v[g * 16 + 2 * j] += f.x;
+            v[g * 16 + 2 * j + 1] += f.y;
           }
         }
       }
@@ -268,13 +367,28 @@ DEVI void chunk_finish(const ChunkIn<EPI>& in, const GemmParams& p, int row, boo
         if (ocol0 + j < ocol_end) v[j] += __half2float(rp[j]);
     }
   }
+  if (p.rs_out != nullptr) {
+    const int nvalid = ocol_end - ocol0;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      if (j < nvalid) {
+        rc.st_sum += v[j];
+        rc.st_sq = fmaf(v[j], v[j], rc.st_sq);
+      }
+    }
+  }
   if (p.out_f32) {
     float* cp = reinterpret_cast<float*>(p.C) + (long long)row * p.ldc + ocol0;
-    if (nvec_out > 0 && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
+    if (nvec_out > 0 && ((reinterpret_cast<uintptr_t>(cp) & 31) == 0)) {
 #pragma unroll
-      for (int q = 0; q < NC / 4; ++q)
-        if (q * 4 < nvec_out)
-          reinterpret_cast<float4*>(cp)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      for (int g = 0; g < NC / 8; ++g) {
+        if (g * 8 < nvec_out) {
+          uint32_t o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = __float_as_uint(v[g * 8 + j]);
+          stg_v8(cp + g * 8, o);
+        }
+      }
     } else {
 #pragma unroll
       for (int j = 0; j < NC; ++j)
@@ -282,16 +396,14 @@ DEVI void chunk_finish(const ChunkIn<EPI>& in, const GemmParams& p, int row, boo
     }
   } else {
     __half* cp = reinterpret_cast<__half*>(p.C) + (long long)row * p.ldc + ocol0;
-    if (nvec_out > 0 && ((reinterpret_cast<uintptr_t>(cp) & 15) == 0)) {
+    if (nvec_out > 0 && ((reinterpret_cast<uintptr_t>(cp) & 31) == 0)) {
 #pragma unroll
-      for (int q = 0; q < NC / 8; ++q) {
-        if (q * 8 < nvec_out) {
-          uint4 o;
-          o.x = pack_half2(v[8 * q + 0], v[8 * q + 1]);
-          o.y = pack_half2(v[8 * q + 2], v[8 * q + 3]);
-          o.z = pack_half2(v[8 * q + 4], v[8 * q + 5]);
-          o.w = pack_half2(v[8 * q + 6], v[8 * q + 7]);
-          reinterpret_cast<uint4*>(cp)[q] = o;
+      for (int g = 0; g < NC / 16; ++g) {
+        if (g * 16 < nvec_out) {
+          uint32_t o[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) o[j] = pack_half2(v[g * 16 + 2 * j], v[g * 16 + 2 * j + 1]);
+          stg_v8(cp + g * 16, o);
         }
       }
     } else {
@@ -317,7 +429,7 @@ DEVI void dump_store(const uint32_t (&r)[32], float* slot, int chunk_global, int
 //   whole tile                      -> fused epilogue
 // `slot_stride_ctas`: distance in CTA slots between consecutive contributors (1 one-CTA, 2 CTA-pair).
 template <int EPI>
-DEVI void epilogue_segment(const GemmParams& p, uint32_t t_acc, int c_begin, int c_end, int row, bool row_ok,
+DEVI void epilogue_segment(const GemmParams& p, RowCtx& rc, uint32_t t_acc, int c_begin, int c_end, int row, bool row_ok,
                            int row_in_slot, int tile_col0, int col_end, bool is_tail, int n_parts,
                            int slot_stride_ctas, int lane) {
   if (is_tail) {
@@ -364,7 +476,7 @@ DEVI void epilogue_segment(const GemmParams& p, uint32_t t_acc, int c_begin, int
     ChunkIn<EPI> a;
     chunk_issue<EPI>(a, p, t_acc + 32 * c, row, row_ok, tile_col0 + 32 * c, col_end);
     tmem_ld_wait();
-    chunk_finish<EPI>(a, p, row, row_ok, tile_col0 + 32 * c, col_end, part0, n_parts, pstride, c, row_in_slot);
+    chunk_finish<EPI>(a, p, rc, row, row_ok, tile_col0 + 32 * c, col_end, part0, n_parts, pstride, c, row_in_slot);
   }
   __syncwarp();
   if (n_parts > 0 && lane == 0) {
@@ -380,12 +492,26 @@ DEVI void epilogue_segment(const GemmParams& p, uint32_t t_acc, int c_begin, int
 // W), TMEM column = TOKEN.  One warp owns 32 features x 32 tokens per chunk.  Lanes 2i / 2i+1 exchange halves so that
 // each thread ends up with 16 tokens x 2 adjacent features: half2 stores (64 contiguous bytes per token and warp), and
 // for SwiGLU (W rows interleaved gate_j, up_j) gate and up of one output land in the same thread.
+// predicated 2-byte read-only load as ONE asm statement: nvcc speculates plain `if (ptr) x = __ldg(ptr + i)` loads
+// when it hoists them out of a loop (observed: an unconditional LDG.CONSTANT through a null bias pointer)
+DEVI float ldg_half_if(const __half* ptr, bool pred) {
+  unsigned short raw;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %2, 0;\n\t"
+      "mov.b16 %0, 0;\n\t"
+      "@q ld.global.nc.b16 %0, [%1];\n\t"
+      "}"
+      : "=h"(raw)
+      : "l"(ptr), "r"((int)pred));
+  return __half2float(__ushort_as_half(raw));
+}
+
 template <int EPI>
-DEVI void chunk_swap(const GemmParams& p, uint32_t taddr, int f, int tok0, int tok_end, int lane) {
+DEVI void chunk_swap(const GemmParams& p, uint32_t taddr, int f, float bias, int tok0, int tok_end, int lane) {
   uint32_t r[32];
   tmem_ld_32x32b_x32(taddr, r);
-  float bias = 0.f;
-  if (p.bias != nullptr && f < p.N) bias = __half2float(__ldg(p.bias + f));
   tmem_ld_wait();
   float v[32];
 #pragma unroll
@@ -604,8 +730,18 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         if (warp == 0 && lane == 0) atomicAdd(&g_gemm_prof[3], (unsigned long long)w);
       }
       tc_fence_after();
-      epilogue_segment<EPI>(p, t_acc, half_idx * CHUNKS_PER_WARP, (half_idx + 1) * CHUNKS_PER_WARP, row, row < p.M,
+      RowCtx rc;
+      rowctx_begin(rc, p, row, row < p.M);
+      if (p.norm_mode == 2) {   // (s, b') of this tile's columns -> smem table of this accumulator stage
+        float2* tab = reinterpret_cast<float2*>(smem + L::TAB_OFFSET) + acc * 256;
+        const int t = threadIdx.x, col = n_blk * BN + t;
+        if (t < BN) tab[t] = col < p.N ? __ldg(p.col_sb + col) : make_float2(0.f, 0.f);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        rc.tab = tab;
+      }
+      epilogue_segment<EPI>(p, rc, t_acc, half_idx * CHUNKS_PER_WARP, (half_idx + 1) * CHUNKS_PER_WARP, row, row < p.M,
                             row_in_tile, n_blk * BN, min(p.N, (n_blk + 1) * BN), kb0 > 0, n_parts, 1, lane);
+      if (kb0 == 0) rowctx_end(rc, p, row, row < p.M, n_blk * BN + half_idx * CHUNKS_PER_WARP * 32);
       // all TMEM reads of this warp for this segment are done -> release the accumulator stage
       tc_fence_before();
       __syncwarp();
@@ -645,7 +781,8 @@ struct SmemLayout2 {
   static constexpr int B_BYTES = (BN2_MAX / 2) * BK * 2;   // <= 16 KB: this CTA's half of the column operand tile
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFFSET = STAGES2 * STAGE_BYTES;
-  static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;
+  static constexpr int TAB_OFFSET = BAR_OFFSET + 256;
+  static constexpr int TOTAL = TAB_OFFSET + 4096 + 1024;
 };
 
 template <int EPI, bool SWAP>
@@ -663,6 +800,7 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) TRACE(0);
   const uint32_t cta_rank = cluster_ctarank();
   const bool is_leader = cta_rank == 0;
   const int cluster_id = blockIdx.x >> 1;
@@ -693,6 +831,7 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
   tc_fence_before();
   cluster_sync_all();   // barriers of BOTH CTAs initialised before any remote arrive / TMA complete_tx
   tc_fence_after();
+  if (threadIdx.x == 0) TRACE(1);
   const uint32_t tmem_base = *tmem_base_slot;
   WorkIter it(cluster_id, num_clusters, num_tiles, p.sk_tiles, k_blocks);
   int tile, kb0, kb1;
@@ -726,6 +865,7 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
         }
       }
       pdl_wait();
+      TRACE(2);
       int issued = 0;
       while (it.next(tile, kb0, kb1)) {
         decode(tile, a_blk, b_blk);
@@ -754,12 +894,15 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
       uint32_t acc_phase = 0;
       long long w_full = 0, w_acc = 0;
       const long long t_start = clock64();
+      bool first = true;
+      long long c_first = 0, w_full_first = 0;
       while (it.next(tile, kb0, kb1)) {
         w_acc += mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN2_MAX);
         for (int kb = kb0; kb < kb1; ++kb) {
           w_full += mbar_wait(&full_bar[stage], phase);
+          if (first) { TRACE(3); first = false; c_first = clock64(); w_full_first = w_full; }
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
           const uint32_t sb = sa + L::A_BYTES;
@@ -774,6 +917,12 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
         }
         umma_commit_2sm(&tmem_full_bar[acc], 3);   // accumulators of both CTAs complete
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      TRACE(4);
+      if (p.trace && blockIdx.x < 160) {
+        g_gemm_trace[p.trace - 1][blockIdx.x][8] = (unsigned long long)(clock64() - c_first);
+        g_gemm_trace[p.trace - 1][blockIdx.x][9] = (unsigned long long)(w_full - w_full_first);
+        g_gemm_trace[p.trace - 1][blockIdx.x][10] = (unsigned long long)w_acc;
       }
       atomicAdd(&g_gemm_prof[1], (unsigned long long)w_full);
       atomicAdd(&g_gemm_prof[2], (unsigned long long)w_acc);
@@ -796,6 +945,7 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
     const uint32_t leader_empty0 = mapa_shared(smem_u32(&tmem_empty_bar[0]), 0);
     const uint32_t leader_empty1 = mapa_shared(smem_u32(&tmem_empty_bar[1]), 0);
     int a_blk, b_blk;
+    int n_done = 0;
     pdl_wait();
     while (it.next(tile, kb0, kb1)) {
       decode(tile, a_blk, b_blk);
@@ -812,20 +962,36 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
       if (SWAP) {
         // lanes = features (rows of W), columns = tokens (rows of A)
         const int tok_end = min(p.M, (b_blk + 1) * bn);
+        const float bias = ldg_half_if(p.bias + row, p.bias != nullptr && row < p.N);   // one feature per thread
 #pragma unroll 1
         for (int c = c_begin; c < c_end; ++c) {
           __syncwarp();
-          chunk_swap<EPI>(p, t_acc + 32 * c, row, b_blk * bn + 32 * c, tok_end, lane);
+          chunk_swap<EPI>(p, t_acc + 32 * c, row, bias, b_blk * bn + 32 * c, tok_end, lane);
         }
       } else {
         // contributors of this CTA's 128 rows are the same-rank CTAs of the following clusters: slot stride 2
-        epilogue_segment<EPI>(p, t_acc, c_begin, c_end, row, row < p.M, row_in_slot, b_blk * bn,
+        RowCtx rc;
+        rowctx_begin(rc, p, row, row < p.M);
+        if (p.norm_mode == 2) {   // (s, b') of this tile's columns -> smem table of this accumulator stage
+          float2* tab = reinterpret_cast<float2*>(smem + L::TAB_OFFSET) + acc * 256;
+          const int t = threadIdx.x, col = b_blk * bn + t;
+          if (t < bn) tab[t] = col < p.N ? __ldg(p.col_sb + col) : make_float2(0.f, 0.f);
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          rc.tab = tab;
+        }
+        epilogue_segment<EPI>(p, rc, t_acc, c_begin, c_end, row, row < p.M, row_in_slot, b_blk * bn,
                               min(p.N, (b_blk + 1) * bn), kb0 > 0, n_parts, 2, lane);
+        if (kb0 == 0) rowctx_end(rc, p, row, row < p.M, b_blk * bn + c_begin * 32);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(acc == 0 ? leader_empty0 : leader_empty1);  // leader's barrier
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      ++n_done;
+    }
+    if (threadIdx.x == 0) {
+      TRACE(5);
+      if (p.trace && blockIdx.x < 160) g_gemm_trace[p.trace - 1][blockIdx.x][7] = (unsigned long long)n_done;
     }
   }
 
@@ -835,6 +1001,7 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
     tc_fence_after();
     tmem_dealloc_2sm(tmem_base, TMEM_COLS);
   }
+  if (threadIdx.x == 0) TRACE(6);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -890,6 +1057,8 @@ int num_sms() {
   return g_num_sms;
 }
 
+int g_trace_on = 0;
+int g_trace_launch = 0;
 float* g_sk_ws = nullptr;
 int* g_sk_flags = nullptr;
 
@@ -972,20 +1141,22 @@ int dispatch_epi_2cta(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, c
 }
 
 // ------------------------------------------------------------------------------------------------
-// Cost model, in SM cycles.  Per k-block (K = 64) a tile costs max(MMA time, operand ingest):
-//   MMA:    2 * columns cycles per 128 accumulator rows (8192 FLOP/cycle/SM, measured 96 % on 8192^3)
-//   ingest: bytes TMA brings into one SM per k-block / ~80 B/cycle (one-CTA 128x256 tiles at 96 B/cycle wait 16 % of
-//           the time for data, CTA-pair 256x256 tiles at 64 B/cycle < 1 %: profiles/r01_gemm_ab.md)
-// plus a fixed cost per tile (accumulator hand-over, pipeline bubble) and the un-overlapped epilogue of the last tile.
-// Waves = ceil(tiles / workers): tile-count quantisation is the dominant loss on this path (M = 4112, 576; N = 1408),
-// which is why the CTA-pair engine takes any tile width that is a multiple of 16 and can swap the operands.
+// Cost model, in SM cycles -- from the per-CTA timelines measured on B200 (profiles/r01_gemm_timeline.md):
+//   * CTA-pair engine: one k-block (K = 64) of a 256 x bn tile takes ~555 cycles for EVERY bn in 128..256 (and for the
+//     swapped 144 / 192-token tiles): the tensor pipe is paced by the 128-row A operand of each MMA, not by N, so only
+//     N = 256 tiles reach the pipe's peak (92 % measured) and narrower tiles cost the same time for less work.
+//   * one-CTA engine: 128 x 256 tiles are operand-ingest bound (48 KB per k-block and SM at ~73 B/cycle = 675 cycles).
+//   * the MMA issuer never waits for operands (0.0 % measured) -- time = (k-blocks on the busiest CTA) x k-block time
+//     + ~2 us dependency resolution + ~0.8 us first operand round trip + ~3.6 us un-overlapped last epilogue.
+// => minimise waves x k-blocks; narrower or swapped tiles only pay when they remove a whole wave.
 // ------------------------------------------------------------------------------------------------
-constexpr double INGEST_B_PER_CYCLE = 80.0;
-constexpr double TILE_FIXED_CYCLES = 500.0;
+constexpr double PAIR_KB_CYCLES = 555.0;
+constexpr double INGEST_B_PER_CYCLE = 73.0;
+constexpr double TILE_FIXED_CYCLES = 400.0;
 
 double kb_cycles(int cols, int bytes_per_sm) {
-  const double mma = 2.0 * cols, ing = bytes_per_sm / INGEST_B_PER_CYCLE;
-  return mma > ing ? mma : ing;
+  const double ing = bytes_per_sm / INGEST_B_PER_CYCLE;
+  return ing > PAIR_KB_CYCLES ? ing : PAIR_KB_CYCLES;
 }
 double sched_cost(int tiles, int workers, int k_blocks, double kb_cost, double epi_tail, bool sk_possible) {
   const int full = tiles / workers, rem = tiles % workers;
@@ -1009,7 +1180,7 @@ int env_int(const char* name, int dflt) {
   return e != nullptr ? atoi(e) : dflt;
 }
 
-GemmPlan plan_gemm(int M, int N, int K, int epi) {
+GemmPlan plan_gemm(int M, int N, int K, int epi, bool allow_swap = true, bool only_256 = false) {
   static const int flex = env_int("STLLM_GEMM_FLEX", 1);   // 0: round-1 selection (tiles of 64/128/256 columns only)
   static const int swap_ok = env_int("STLLM_GEMM_SWAP", 1);
   const int k_blocks = (K + BK - 1) / BK;
@@ -1020,25 +1191,25 @@ GemmPlan plan_gemm(int M, int N, int K, int epi) {
     if (cost < best.cost) best = GemmPlan{engine, bn, cost};
   };
   // one-CTA engine
-  consider(0, 256, sched_cost(mt * ((N + 255) / 256), sms, k_blocks, kb_cycles(256, 16384 + 256 * 128), 8.0 * 256, true));
-  consider(0, 128, 1.03 * sched_cost(mt * ((N + 127) / 128), sms, k_blocks, kb_cycles(128, 16384 + 128 * 128), 8.0 * 128, false));
-  consider(0, 64, 1.03 * sched_cost(mt * ((N + 63) / 64), sms, k_blocks, kb_cycles(64, 16384 + 64 * 128), 8.0 * 64, false));
+  consider(0, 256, sched_cost(mt * ((N + 255) / 256), sms, k_blocks, kb_cycles(256, 16384 + 256 * 128), 14.0 * 256, true));
+  if (!only_256) consider(0, 128, 1.03 * sched_cost(mt * ((N + 127) / 128), sms, k_blocks, kb_cycles(128, 16384 + 128 * 128), 14.0 * 128, false));
+  if (!only_256) consider(0, 64, 1.03 * sched_cost(mt * ((N + 63) / 64), sms, k_blocks, kb_cycles(64, 16384 + 64 * 128), 14.0 * 64, false));
   // CTA-pair engine: 256 rows x bn columns per cluster
   const int m2 = (M + 255) / 256;
   if (M > 128) {
-    for (int bn = flex ? 96 : 256; bn <= 256; bn += 16) {
+    for (int bn = 256; bn >= ((flex && !only_256) ? 96 : 256); bn -= 16) {   // widest first: ties go to the wider tile
       const int tiles = m2 * ((N + bn - 1) / bn);
-      consider(1, bn, sched_cost(tiles, clusters, k_blocks, kb_cycles(bn, 16384 + bn * 64), 8.0 * bn, bn == 256));
+      const double c = sched_cost(tiles, clusters, k_blocks, kb_cycles(bn, 16384 + bn * 64), 14.0 * bn, bn == 256);
+      consider(1, bn, bn == 256 ? c : 1.03 * c);
     }
   }
   // swapped operands: 256 features x bn tokens per cluster (transposed epilogue: slightly dearer per element)
-  if (flex && swap_ok && N >= 256 && (epi != EPI_SWIGLU || N % 2 == 0)) {
+  if (flex && swap_ok && allow_swap && N >= 256 && (epi != EPI_SWIGLU || N % 2 == 0)) {
     const int f2 = (N + 255) / 256;
     const int m16 = ((M + 15) / 16) * 16;
-    for (int bn = 16; bn <= 256; bn += 16) {
-      if (bn > m16 && bn != 16) break;
+    for (int bn = m16 < 256 ? m16 : 256; bn >= 16; bn -= 16) {
       const int tiles = f2 * ((M + bn - 1) / bn);
-      consider(2, bn, 1.04 * sched_cost(tiles, clusters, k_blocks, kb_cycles(bn, 16384 + bn * 64), 14.0 * bn, false));
+      consider(2, bn, 1.05 * sched_cost(tiles, clusters, k_blocks, kb_cycles(bn, 16384 + bn * 64), 20.0 * bn, false));
     }
   }
   return best;
@@ -1056,6 +1227,16 @@ extern "C" int stllm_set_gemm_workspace(void* ptr, long long bytes) {
   STLLM_CHECK_ARG(bytes >= stllm_gemm_workspace_bytes() && ((uintptr_t)ptr & 255) == 0);
   g_sk_flags = reinterpret_cast<int*>(ptr);                               // first 4 KB: flags
   g_sk_ws = reinterpret_cast<float*>(reinterpret_cast<char*>(ptr) + 4096);
+  return STLLM_OK;
+}
+
+// debug: phase timestamps of the last 4 CTA-pair launches (see g_gemm_trace); on != 0 enables tracing for the
+// following launches, out (host, 4*160*8 u64, may be null) receives the current contents; synchronises.
+extern "C" int stllm_gemm_debug_trace(int on, unsigned long long* out, int* next_slot) {
+  STLLM_CHECK_CUDA(cudaDeviceSynchronize());
+  if (out != nullptr) STLLM_CHECK_CUDA(cudaMemcpyFromSymbol(out, g_gemm_trace, sizeof(unsigned long long) * 4 * 160 * 12));
+  if (next_slot != nullptr) *next_slot = g_trace_launch & 3;
+  g_trace_on = on;
   return STLLM_OK;
 }
 
@@ -1083,9 +1264,62 @@ extern "C" int stllm_gemm_plan(int M, int N, int K, int epilogue, long long* out
 // tile_n: 0 = auto (cost model); 64 / 128 / 256 = one-CTA tiles; 512 = CTA-pair 256x256 tiles; 1024 + bn = CTA-pair
 // tiles of bn columns (bn multiple of 16, <= 256); 2048 + bn = CTA-pair with swapped operands (256 features x bn tokens);
 // add 1 (257/513/...) to forbid the stream-K treatment of the last wave (pure data-parallel schedule, for A/B runs).
+namespace {
+struct NormArgs {
+  int norm_mode = 0;
+  const float* rs_in = nullptr;
+  int rs_in_stride = 0;
+  const float2* col_sb = nullptr;
+  float eps = 0.f;
+  float* rs_out = nullptr;
+  int rs_out_mode = 0;
+  int rs_out_stride = 0;
+};
+int gemm_impl(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N, int K,
+              const void* bias, const void* residual, long long ldr, int epilogue, int out_f32, int tile_n,
+              const NormArgs& na, void* stream);
+}  // namespace
+
 extern "C" int stllm_gemm_f16(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc,
                               int M, int N, int K, const void* bias, const void* residual, long long ldr,
                               int epilogue, int out_f32, int tile_n, void* stream) {
+  return gemm_impl(A, lda, W, ldw, C, ldc, M, N, K, bias, residual, ldr, epilogue, out_f32, tile_n, NormArgs(), stream);
+}
+
+// GEMM with a LayerNorm / RMSNorm of the A rows folded in, and/or per-row statistics of C written for the NEXT folded
+// GEMM (see GemmParams).  norm_mode 0: none; 1: RMSNorm; 2: LayerNorm (col_sb = [N][2] (s_n, b'_n), `bias` must be
+// NULL).  Statistics rows: [slots][mode] floats with slots = ceil(columns / 128), row stride rs_*_stride floats
+// (multiple of 8, >= slots * mode; padding must be zero).  rs_out_mode 0: none; 1: sum c^2; 2: (sum c, sum c^2).
+// W must already be scaled by the norm weight (W' = gamma (.) W).
+extern "C" int stllm_gemm_norm_f16(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc,
+                                   int M, int N, int K, const void* bias, const void* residual, long long ldr,
+                                   int epilogue, int out_f32, int tile_n, int norm_mode, const float* rs_in,
+                                   int rs_in_stride, const float* col_sb, float norm_eps, float* rs_out,
+                                   int rs_out_mode, int rs_out_stride, void* stream) {
+  STLLM_CHECK_ARG(norm_mode >= 0 && norm_mode <= 2 && rs_out_mode >= 0 && rs_out_mode <= 2);
+  STLLM_CHECK_ARG(norm_mode == 0 || (rs_in != nullptr && ((uintptr_t)rs_in & 31) == 0 && rs_in_stride % 8 == 0 &&
+                                     rs_in_stride >= norm_mode * ((K + 127) / 128)));
+  STLLM_CHECK_ARG(norm_mode != 2 || (col_sb != nullptr && bias == nullptr && ((uintptr_t)col_sb & 7) == 0));
+  STLLM_CHECK_ARG((rs_out_mode == 0) == (rs_out == nullptr));
+  const int n_out = epilogue == EPI_SWIGLU ? N / 2 : N;
+  STLLM_CHECK_ARG(rs_out == nullptr || (((uintptr_t)rs_out & 31) == 0 && rs_out_stride % 8 == 0 &&
+                                        rs_out_stride >= rs_out_mode * ((n_out + 127) / 128) && epilogue != EPI_SWIGLU));
+  NormArgs na;
+  na.norm_mode = norm_mode;
+  na.rs_in = rs_in;
+  na.rs_in_stride = rs_in_stride;
+  na.col_sb = reinterpret_cast<const float2*>(col_sb);
+  na.eps = norm_eps;
+  na.rs_out = rs_out;
+  na.rs_out_mode = rs_out_mode;
+  na.rs_out_stride = rs_out_stride;
+  return gemm_impl(A, lda, W, ldw, C, ldc, M, N, K, bias, residual, ldr, epilogue, out_f32, tile_n, na, stream);
+}
+
+namespace {
+int gemm_impl(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M, int N, int K,
+              const void* bias, const void* residual, long long ldr, int epilogue, int out_f32, int tile_n,
+              const NormArgs& na, void* stream) {
   STLLM_CHECK_ARG(A != nullptr && W != nullptr && C != nullptr);
   STLLM_CHECK_ARG(M > 0 && N > 0 && K > 0);
   STLLM_CHECK_ARG(K % 8 == 0 && lda % 8 == 0 && ldw % 8 == 0);  // TMA: 16-byte global strides
@@ -1101,8 +1335,9 @@ extern "C" int stllm_gemm_f16(const void* A, long long lda, const void* W, long 
   }
   int allow_sk = 1;
   if (code & 1) { allow_sk = 0; code -= 1; }
+  const bool fused_rows = na.norm_mode != 0 || na.rs_out != nullptr;   // per-row epilogue state: lanes must be tokens
   GemmPlan pl;
-  if (code == 0) pl = plan_gemm(M, N, K, epilogue);
+  if (code == 0) pl = plan_gemm(M, N, K, epilogue, !fused_rows, na.rs_out != nullptr);
   else if (code == 64 || code == 128 || code == 256) pl = GemmPlan{0, code, 0};
   else if (code == 512) pl = GemmPlan{1, 256, 0};
   else if (code > 1024 && code <= 1024 + 256) pl = GemmPlan{1, code - 1024, 0};
@@ -1110,6 +1345,8 @@ extern "C" int stllm_gemm_f16(const void* A, long long lda, const void* W, long 
   else { stllm_set_last_error("stllm_gemm_f16: unknown tile_n code %d", tile_n); return STLLM_ERR_BAD_ARG; }
   STLLM_CHECK_ARG(pl.bn >= 16 && pl.bn <= 256 && pl.bn % 16 == 0);
   const bool swap = pl.engine == 2;
+  STLLM_CHECK_ARG(!(swap && fused_rows));
+  STLLM_CHECK_ARG(na.rs_out == nullptr || pl.bn == 256);   // statistics slots are 128 columns = one warp's share of a 256 tile
   // lane operand (128-row boxes) and column operand (bn or bn/2-row boxes)
   const void* lane_ptr = swap ? W : A;
   const void* col_ptr = swap ? A : W;
@@ -1131,6 +1368,16 @@ extern "C" int stllm_gemm_f16(const void* A, long long lda, const void* W, long 
   }
   static const int w_prefetch = env_int("STLLM_GEMM_WPREFETCH", 1);
   p.w_prefetch = w_prefetch;
+  p.trace = g_trace_on ? 1 + (g_trace_launch++ & 3) : 0;
+  p.norm_mode = na.norm_mode;
+  p.rs_in = na.rs_in;
+  p.col_sb = na.col_sb;
+  p.norm_eps = na.eps;
+  p.norm_inv_k = 1.0f / (float)K;
+  p.rs_in_stride = na.rs_in_stride;
+  p.rs_out = na.rs_out;
+  p.rs_out_mode = na.rs_out_mode;
+  p.rs_out_stride = na.rs_out_stride;
   p.bn = pl.bn;
   p.C = C;
   p.bias = reinterpret_cast<const __half*>(bias);
@@ -1158,3 +1405,4 @@ extern "C" int stllm_gemm_f16(const void* A, long long lda, const void* W, long 
   STLLM_CHECK_ARG(pl.bn == 64);
   return dispatch_epi<64, 8>(epilogue, tmA, tmB, p, allow_sk, s);
 }
+}  // namespace

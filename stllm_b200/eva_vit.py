@@ -10,6 +10,7 @@ forward() runs entirely in libstllm_b200.so:
 All frames of all clips are flattened to one token matrix [(B*T)*257, 1408], so each launch covers every frame.
 """
 import math
+import os
 from functools import partial
 
 import torch
@@ -71,6 +72,63 @@ class Block(nn.Module):
         self.gamma_1, self.gamma_2 = None, None
 
 
+def pack_block(blk, dev, D, fold_norm1=False, fold_norm2=False):
+    """device-side weights of one Block.  fold_norm*: the LayerNorm in front of qkv / fc1 is folded into that GEMM
+    (ops.gemm norm=NORM_LN): W' = fp16(gamma (.) W), col_sb[n] = (sum_k W'[n, k], bias[n] + sum_k beta[k] W[n, k]),
+    so that  LN(x) W^T + b = rstd (x W'^T - mu s) + b'  with the row statistics accumulated by the producing GEMM."""
+    f16 = lambda t: t.detach().to(device=dev, dtype=torch.float16).contiguous()
+    f32 = lambda t: t.detach().to(device=dev, dtype=torch.float32).contiguous()
+    a = blk.attn
+    if a.q_bias is not None:
+        qkv_bias = torch.cat((f16(a.q_bias), torch.zeros(D, dtype=torch.float16, device=dev), f16(a.v_bias)))
+    else:
+        qkv_bias = None
+
+    def fold(w, bias, gamma, beta):
+        wf = w.float()
+        w2 = (wf * gamma[None, :]).to(torch.float16).contiguous()
+        b2 = wf @ beta
+        if bias is not None:
+            b2 = b2 + bias.float()
+        return w2, torch.stack((w2.float().sum(1), b2), dim=1).contiguous()
+    bw = dict(g1=f32(blk.norm1.weight), b1=f32(blk.norm1.bias), g2=f32(blk.norm2.weight), b2=f32(blk.norm2.bias),
+              w_qkv=f16(a.qkv.weight), qkv_bias=qkv_bias, w_proj=f16(a.proj.weight), b_proj=f16(a.proj.bias),
+              w_fc1=f16(blk.mlp.fc1.weight), b_fc1=f16(blk.mlp.fc1.bias),
+              w_fc2=f16(blk.mlp.fc2.weight), b_fc2=f16(blk.mlp.fc2.bias), qkv_sb=None, fc1_sb=None)
+    if fold_norm1:
+        bw["w_qkv"], bw["qkv_sb"] = fold(bw["w_qkv"], qkv_bias, bw["g1"], bw["b1"])
+    if fold_norm2:
+        bw["w_fc1"], bw["fc1_sb"] = fold(bw["w_fc1"], bw["b_fc1"], bw["g2"], bw["b2"])
+    return bw
+
+
+def run_block(bw, xt, h, B, n_tok, Hh, d, eps, stats_in=None, stats_mid=None, stats_out=None):
+    """Block.forward (eva_vit.py:173-180) in place on the token matrix xt [B * n_tok, D]; h = scratch of that shape.
+    stats_in: (sum, sumsq) rows of xt from the producing GEMM (needs bw['qkv_sb']), else norm1 runs standalone;
+    stats_mid: zeroed buffer for the rows after proj (needs bw['fc1_sb']); stats_out: zeroed buffer for the rows
+    after fc2 (consumed by the next block's folded norm1)."""
+    D = Hh * d
+    if stats_in is not None and bw["qkv_sb"] is not None:
+        qkv = ops.gemm(xt, bw["w_qkv"], norm=ops.NORM_LN, rs_in=stats_in, col_sb=bw["qkv_sb"], norm_eps=eps)
+    else:
+        assert bw["qkv_sb"] is None, "block packed with a folded norm1 needs the row statistics of its input"
+        ops.layernorm(xt, bw["g1"], bw["b1"], eps, out=h)
+        qkv = ops.gemm(h, bw["w_qkv"], bias=bw["qkv_bias"])
+    qkv = qkv.view(B, n_tok, 3, Hh, d)
+    a = ops.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], scale=1.0, q_prescale=d ** -0.5)
+    if bw["fc1_sb"] is not None:
+        ops.gemm(a.view(B * n_tok, D), bw["w_proj"], bias=bw["b_proj"], residual=xt, out=xt, rs_out=stats_mid,
+                 rs_out_mode=2)
+        m = ops.gemm(xt, bw["w_fc1"], epilogue=ops.EPI_GELU, norm=ops.NORM_LN, rs_in=stats_mid, col_sb=bw["fc1_sb"],
+                     norm_eps=eps)
+    else:
+        ops.gemm(a.view(B * n_tok, D), bw["w_proj"], bias=bw["b_proj"], residual=xt, out=xt)
+        ops.layernorm(xt, bw["g2"], bw["b2"], eps, out=h)
+        m = ops.gemm(h, bw["w_fc1"], bias=bw["b_fc1"], epilogue=ops.EPI_GELU)
+    ops.gemm(m, bw["w_fc2"], bias=bw["b_fc2"], residual=xt, out=xt, rs_out=stats_out,
+             rs_out_mode=2 if stats_out is not None else 0)
+
+
 class VisionTransformer(nn.Module):
     """eva_vit.py:244-349.  Options the ST-LLM path never enables (rel-pos bias, layer-scale, drop-path > 0 in
     eval, checkpointing) are rejected loudly rather than silently ignored."""
@@ -103,6 +161,7 @@ class VisionTransformer(nn.Module):
         self.apply(self._init_weights)
         self.fix_init_weight()
         self._packed = None
+        self._stats = None
 
     def fix_init_weight(self):
         for layer_id, layer in enumerate(self.blocks):
@@ -140,20 +199,11 @@ class VisionTransformer(nn.Module):
         kpad = (kreal + 63) // 64 * 64
         w_patch = torch.zeros(D, kpad, dtype=torch.float16, device=dev)
         w_patch[:, :kreal] = f16(pw).reshape(D, kreal)
-        blocks = []
-        for blk in self.blocks:
-            a = blk.attn
-            if a.q_bias is not None:
-                qkv_bias = torch.cat((f16(a.q_bias), torch.zeros(D, dtype=torch.float16, device=dev), f16(a.v_bias)))
-            else:
-                qkv_bias = None
-            blocks.append(dict(
-                g1=f32(blk.norm1.weight), b1=f32(blk.norm1.bias), g2=f32(blk.norm2.weight), b2=f32(blk.norm2.bias),
-                w_qkv=f16(a.qkv.weight), qkv_bias=qkv_bias, w_proj=f16(a.proj.weight), b_proj=f16(a.proj.bias),
-                w_fc1=f16(blk.mlp.fc1.weight), b_fc1=f16(blk.mlp.fc1.bias),
-                w_fc2=f16(blk.mlp.fc2.weight), b_fc2=f16(blk.mlp.fc2.bias)))
+        fuse = os.environ.get("STLLM_FUSE_NORM", "1") != "0"
+        blocks = [pack_block(blk, dev, D, fold_norm1=fuse and i > 0, fold_norm2=fuse) for i, blk in enumerate(self.blocks)]
         self._packed = dict(w_patch=w_patch, kpad=kpad, kreal=kreal, b_patch=f16(self.patch_embed.proj.bias),
-                            cls=f16(self.cls_token).reshape(-1), pos=f16(self.pos_embed).reshape(-1, D), blocks=blocks)
+                            cls=f16(self.cls_token).reshape(-1), pos=f16(self.pos_embed).reshape(-1, D), blocks=blocks,
+                            fuse=fuse)
 
     # ---- forward --------------------------------------------------------------------------------
     @torch.no_grad()
@@ -174,14 +224,18 @@ class VisionTransformer(nn.Module):
         xt = ops.vit_assemble(patches, P["cls"], P["pos"], B, self.patch_embed.num_patches).view(B * n_tok, D)
         outs = []
         h = torch.empty_like(xt)
-        for bw in P["blocks"]:
-            ops.layernorm(xt, bw["g1"], bw["b1"], self.ln_eps, out=h)
-            qkv = ops.gemm(h, bw["w_qkv"], bias=bw["qkv_bias"]).view(B, n_tok, 3, Hh, d)
-            a = ops.attention(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2], scale=1.0, q_prescale=d ** -0.5)
-            ops.gemm(a.view(B * n_tok, D), bw["w_proj"], bias=bw["b_proj"], residual=xt, out=xt)
-            ops.layernorm(xt, bw["g2"], bw["b2"], self.ln_eps, out=h)
-            m = ops.gemm(h, bw["w_fc1"], bias=bw["b_fc1"], epilogue=ops.EPI_GELU)
-            ops.gemm(m, bw["w_fc2"], bias=bw["b_fc2"], residual=xt, out=xt)
+        nb = len(P["blocks"])
+        # folded LayerNorms: (sum, sum of squares) per token row after proj (slot 2i) and after fc2 (slot 2i + 1)
+        stats = None
+        if P["fuse"]:
+            if self._stats is None or self._stats.shape[1] != B * n_tok or self._stats.device != xt.device:
+                self._stats = ops.row_stats_buffer(2 * nb, B * n_tok, D, 2, xt.device)
+            stats = self._stats
+        for i, bw in enumerate(P["blocks"]):
+            run_block(bw, xt, h, B, n_tok, Hh, d, self.ln_eps,
+                      stats_in=stats[2 * i - 1] if (stats is not None and i > 0) else None,
+                      stats_mid=stats[2 * i] if stats is not None else None,
+                      stats_out=stats[2 * i + 1] if (stats is not None and i + 1 < nb) else None)
             if return_block_outputs:
                 outs.append(xt.view(B, n_tok, D).clone())
         out = xt.view(B, n_tok, D)

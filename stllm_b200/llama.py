@@ -8,6 +8,8 @@ input_layernorm, post_attention_layernorm}, model.norm, lm_head) and runs:
   -> o_proj GEMM (+residual) -> RMSNorm -> gate|up GEMM with SwiGLU epilogue (interleaved rows) -> down GEMM
   (+residual); final RMSNorm; lm_head GEMM.                     modeling_llama_mem.py:61-144,172-316,464-594
 """
+import os
+
 import torch
 import torch.nn as nn
 
@@ -129,6 +131,7 @@ class LlamaModel(nn.Module):
         self.norm = LlamaRMSNorm(config.hidden_size, eps=config.rms_norm_eps)
         self._packed = None
         self._rope = None
+        self._stats = None
         std = config.initializer_range
         for m in self.modules():
             if isinstance(m, (nn.Linear, nn.Embedding)):
@@ -150,16 +153,29 @@ class LlamaModel(nn.Module):
     def _pack(self):
         dev = self.norm.weight.device
         f16 = lambda t: t.detach().to(device=dev, dtype=torch.float16).contiguous()
+        # RMSNorm folded into the consuming GEMM (ops.gemm norm=NORM_RMS): the packed q|k|v and gate|up copies carry
+        # the norm weight, W' = fp16(w_norm (.) W); the row scale rsqrt(mean(x^2) + eps) is applied in the epilogue from
+        # the sum of squares the producing o_proj / down_proj GEMM accumulated.  Layer 0's input norm has no producing
+        # GEMM (inputs_embeds) and the final norm's output is returned to the caller: both stay standalone kernels.
+        fuse = os.environ.get("STLLM_FUSE_NORM", "1") != "0"
+
+        def fold(w, g):
+            return (w.float() * g.float()[None, :]).to(torch.float16).contiguous()
         layers = []
-        for lyr in self.layers:
+        for li, lyr in enumerate(self.layers):
             a, m = lyr.self_attn, lyr.mlp
             w_qkv = torch.cat([f16(a.q_proj.weight), f16(a.k_proj.weight), f16(a.v_proj.weight)], 0)
             # interleave rows: 2j = gate_j, 2j+1 = up_j  (SwiGLU epilogue pairs adjacent accumulator columns)
             w_gu = torch.stack([f16(m.gate_proj.weight), f16(m.up_proj.weight)], dim=1).reshape(
                 2 * m.gate_proj.weight.shape[0], m.gate_proj.weight.shape[1]).contiguous()
+            ln1, ln2 = f16(lyr.input_layernorm.weight), f16(lyr.post_attention_layernorm.weight)
+            if fuse:
+                if li > 0:
+                    w_qkv = fold(w_qkv, ln1)
+                w_gu = fold(w_gu, ln2)
             layers.append(dict(w_qkv=w_qkv, w_o=f16(a.o_proj.weight), w_gu=w_gu, w_down=f16(m.down_proj.weight),
-                               ln1=f16(lyr.input_layernorm.weight), ln2=f16(lyr.post_attention_layernorm.weight)))
-        self._packed = dict(layers=layers, norm=f16(self.norm.weight))
+                               ln1=ln1, ln2=ln2))
+        self._packed = dict(layers=layers, norm=f16(self.norm.weight), fuse=fuse)
 
     def _rope_tables(self, device):
         if self._rope is None or self._rope[0].device != device:
@@ -214,9 +230,20 @@ class LlamaModel(nn.Module):
         hs = [x.view(B, S, C).clone()] if output_hidden_states else None
         h = torch.empty_like(x)
         eps = cfg.rms_norm_eps
+        fuse = P["fuse"]
+        nL = len(P["layers"])
+        # per-row sum of squares of the residual stream after o_proj (slot 2*li) and after down_proj (slot 2*li + 1)
+        stats = None
+        if fuse:
+            if self._stats is None or self._stats.shape[1] != B * S or self._stats.device != dev:
+                self._stats = ops.row_stats_buffer(2 * nL, B * S, C, 1, dev)
+            stats = self._stats
         for li, L in enumerate(P["layers"]):
-            ops.rmsnorm(x, L["ln1"], eps, out=h)
-            qkv = ops.gemm(h, L["w_qkv"])
+            if fuse and li > 0:
+                qkv = ops.gemm(x, L["w_qkv"], norm=ops.NORM_RMS, rs_in=stats[2 * li - 1], norm_eps=eps)
+            else:
+                ops.rmsnorm(x, L["ln1"], eps, out=h)
+                qkv = ops.gemm(h, L["w_qkv"])
             ops.rope_(qkv, pos, cos_t, sin_t, 2 * H, d)
             qkv5 = qkv.view(B, S, 3, H, d)
             q, k, v = qkv5[:, :, 0], qkv5[:, :, 1], qkv5[:, :, 2]
@@ -225,10 +252,17 @@ class LlamaModel(nn.Module):
                 cache.v[li][:, past:past + S] = v
                 k, v = cache.k[li][:, :past + S], cache.v[li][:, :past + S]
             a = ops.attention(q, k, v, scale=scale, causal=True, key_mask=key_mask, mask_value=-65504.0)
-            ops.gemm(a.view(B * S, C), L["w_o"], residual=x, out=x)
-            ops.rmsnorm(x, L["ln2"], eps, out=h)
-            g = ops.gemm(h, L["w_gu"], epilogue=ops.EPI_SWIGLU)
-            ops.gemm(g, L["w_down"], residual=x, out=x)
+            if fuse:
+                ops.gemm(a.view(B * S, C), L["w_o"], residual=x, out=x, rs_out=stats[2 * li], rs_out_mode=1)
+                g = ops.gemm(x, L["w_gu"], epilogue=ops.EPI_SWIGLU, norm=ops.NORM_RMS, rs_in=stats[2 * li], norm_eps=eps)
+                last = li + 1 == nL
+                ops.gemm(g, L["w_down"], residual=x, out=x, rs_out=None if last else stats[2 * li + 1],
+                         rs_out_mode=0 if last else 1)
+            else:
+                ops.gemm(a.view(B * S, C), L["w_o"], residual=x, out=x)
+                ops.rmsnorm(x, L["ln2"], eps, out=h)
+                g = ops.gemm(h, L["w_gu"], epilogue=ops.EPI_SWIGLU)
+                ops.gemm(g, L["w_down"], residual=x, out=x)
             if output_hidden_states and li + 1 < len(P["layers"]):
                 hs.append(x.view(B, S, C).clone())
         out = ops.rmsnorm(x, P["norm"], eps).view(B, S, C)

@@ -56,11 +56,20 @@ def _rows2d(t):
     return t2.shape[0], t2.stride(0)
 
 
-def gemm(a, w, bias=None, residual=None, epilogue=EPI_NONE, out=None, out_dtype=torch.float16, tile_n=0, k_real=None):
+NORM_NONE, NORM_RMS, NORM_LN = 0, 1, 2
+
+
+def gemm(a, w, bias=None, residual=None, epilogue=EPI_NONE, out=None, out_dtype=torch.float16, tile_n=0, k_real=None,
+         norm=NORM_NONE, rs_in=None, col_sb=None, norm_eps=0.0, rs_out=None, rs_out_mode=0):
     """out = epi(a @ w.T + bias) (+ residual).  a: [..., K] fp16, w: [N, K] fp16 (nn.Linear layout).
-    k_real: un-padded K, only used for algorithmic-FLOP accounting (patch-embed 588 of 640)."""
+    k_real: un-padded K, only used for algorithmic-FLOP accounting (patch-embed 588 of 640).
+
+    Folded normalisation (no standalone LayerNorm / RMSNorm launch): with norm=NORM_RMS / NORM_LN, `a` holds the
+    UN-normalised rows, `w` the gamma-scaled weights and rs_in the per-row statistics buffer (see row_stats_buffer)
+    that the producing GEMM filled through rs_out / rs_out_mode (1: sum c^2, 2: (sum c, sum c^2)).  NORM_LN
+    additionally takes col_sb [N, 2] = (sum_k w[n, k], folded bias)."""
     global launch_count
-    _need_cuda(a, w, bias, residual, out)
+    _need_cuda(a, w, bias, residual, out, rs_in, col_sb, rs_out)
     assert a.dtype == torch.float16 and w.dtype == torch.float16
     _ensure_gemm_workspace(a.device)
     K = a.shape[-1]
@@ -79,15 +88,38 @@ def gemm(a, w, bias=None, residual=None, epilogue=EPI_NONE, out=None, out_dtype=
         assert Mr == M
     if bias is not None:
         assert bias.dtype == torch.float16 and bias.numel() == N and bias.is_contiguous()
-    rc = _lib.load().stllm_gemm_f16(_ptr(a), lda, _ptr(w), w.stride(0), _ptr(out), ldc, M, N, K, _ptr(bias),
-                                    _ptr(residual), ldr, epilogue, 1 if out.dtype == torch.float32 else 0, tile_n,
-                                    _stream())
-    _lib.check(rc, "stllm_gemm_f16")
+    lib = _lib.load()
+    if norm == NORM_NONE and rs_out is None:
+        rc = lib.stllm_gemm_f16(_ptr(a), lda, _ptr(w), w.stride(0), _ptr(out), ldc, M, N, K, _ptr(bias),
+                                _ptr(residual), ldr, epilogue, 1 if out.dtype == torch.float32 else 0, tile_n,
+                                _stream())
+        _lib.check(rc, "stllm_gemm_f16")
+    else:
+        if norm != NORM_NONE:
+            assert rs_in.dtype == torch.float32 and rs_in.is_contiguous() and rs_in.dim() == 2 and rs_in.shape[0] == M
+        if norm == NORM_LN:
+            assert bias is None and col_sb.dtype == torch.float32 and col_sb.is_contiguous() and col_sb.shape == (N, 2)
+        if rs_out is not None:
+            assert rs_out.dtype == torch.float32 and rs_out.is_contiguous() and rs_out.dim() == 2 and rs_out.shape[0] == M
+        rc = lib.stllm_gemm_norm_f16(_ptr(a), lda, _ptr(w), w.stride(0), _ptr(out), ldc, M, N, K, _ptr(bias),
+                                     _ptr(residual), ldr, epilogue, 1 if out.dtype == torch.float32 else 0, tile_n,
+                                     norm, _ptr(rs_in), rs_in.shape[1] if rs_in is not None else 0, _ptr(col_sb),
+                                     float(norm_eps), _ptr(rs_out), rs_out_mode if rs_out is not None else 0,
+                                     rs_out.shape[1] if rs_out is not None else 0, _stream())
+        _lib.check(rc, "stllm_gemm_norm_f16")
     launch_count += 1
     if gemm_recorder is not None:
         gemm_recorder.append(dict(a=a, w=w, bias=bias, residual=residual, epilogue=epilogue, out=out, tile_n=tile_n,
-                                  M=M, N=N, K=k_real or K))
+                                  M=M, N=N, K=k_real or K, norm=norm, rs_in=rs_in, col_sb=col_sb, norm_eps=norm_eps))
     return out
+
+
+def row_stats_buffer(n_buffers, rows, cols, mode, device):
+    """zeroed per-row statistics buffers [n_buffers, rows, stride] for the folded norms: `cols` = width of the
+    normalised rows, one slot of `mode` floats per 128 columns, row stride padded to 8 floats.  Every slot is rewritten
+    by the producing GEMM on each forward, the padding stays zero: no per-step zeroing is needed."""
+    stride = (((cols + 127) // 128) * mode + 7) // 8 * 8
+    return torch.zeros(n_buffers, rows, stride, dtype=torch.float32, device=device)
 
 
 def gemm_plan(M, N, K, epilogue=EPI_NONE):
