@@ -140,6 +140,32 @@ int stllm_mean_frames_f16(const void* x, void* y, int B, int T, long long inner,
 int stllm_residual_merge_f16(const void* x, const void* g, const long long* idx, void* out, int B, int T, int R,
                              long long inner, void* stream);
 
+/* Frame preprocessing on the GPU, bit-exact with the reference's CPU pipeline GroupScale(224, BICUBIC) ->
+ * GroupCenterCrop(224) -> Stack -> ToTorchFormatTensor -> GroupNormalize (conversation.py:192-200,274-278;
+ * video_transforms.py:66-71,94-123,367-406), i.e. Pillow's 8-bit two-pass bicubic resampler (22-bit fixed-point
+ * weights, rounding and clamping to uint8 after each pass) followed by x/255 and (x - mean)/std in fp32.
+ * frames [n,H,W,3] uint8 -> out [n,3,S,S] fp16.  xbounds/xcoef [new_w][2]/[new_w][kx], ybounds/ycoef
+ * [new_h][2]/[new_h][ky]: int32 DEVICE tables of the resampling windows (first input index, tap count / weights),
+ * computed by the host in double precision as Pillow's precompute_coeffs does.  crop_left/crop_top: offset of the
+ * centre crop in the resized image; [y_first, y_last): input rows the cropped rows read.  tmp: scratch of
+ * n*(y_last-y_first)*S*3 bytes.  mean3/std3: HOST pointers. */
+int stllm_preprocess_frames_u8(const void* frames, int n_img, int H, int W, int S, const int* xbounds,
+                               const int* xcoef, int kx, int crop_left, const int* ybounds, const int* ycoef, int ky,
+                               int crop_top, int y_first, int y_last, const float* mean3, const float* std3, void* tmp,
+                               long long tmp_bytes, void* out, void* stream);
+
+/* BT-Adapter encoder (eva_btadapter.py; vit_model "eva_btadapter_g").  ViT stream x: rows (b*T + t)*(P+1) + l, l = 0
+ * the cls token.  Branch z: rows [0,B) one cls token per clip, then B + (b*P + l)*T + t ('b (p t) m').
+ *   stllm_bt_vit_to_branch_f16: z_out = transpose(x) + z_prev, the cls row = fp16(mean_t x_cls) + z_prev_cls
+ *     (forward_branch :184-193; also the residual of BTAdapter_Spatial :273-276 with x = the spatial attention output).
+ *     z_prev == NULL: init_input (:203-226): patch rows + pos[1+l] + time_emb[t], cls = (mean_t x_cls + bt_cls + pos[0])/2.
+ *     z_out may alias z_prev.
+ *   stllm_bt_branch_to_vit_avg_f16: out = (x + transpose^-1(z)) / 2 (forward_features :178-181); out may alias x. */
+int stllm_bt_vit_to_branch_f16(const void* x, const void* z_prev, void* z_out, const void* pos, const void* time_emb,
+                               const void* bt_cls, int B, int T, int P, int dim, void* stream);
+int stllm_bt_branch_to_vit_avg_f16(const void* x, const void* z, void* out, int B, int T, int P, int dim,
+                                   void* stream);
+
 /* out_sum[0] = mean_rows(2 - 2 cos(a_row, b_row)).  st_llm.py:89-91. */
 int stllm_cosine_loss_f16(const void* a, long long lda, const void* b, long long ldb, int rows, int cols,
                           float* out_sum, void* stream);

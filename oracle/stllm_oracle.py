@@ -103,9 +103,10 @@ def _bt_temporal(sd, j, x, T, num_heads, eps=1e-6):
     return torch.cat((init_cls, h.reshape(b, pn * T, m) + residual), 1)           # :306-307
 
 
-def _bt_spatial(sd, j, x, T, num_heads, eps=1e-6):
+def _bt_spatial(sd, j, x, T, num_heads, eps=1e-5):
     """BTAdapter_Spatial.forward, eva_btadapter.py:258-279: a ViT Block applied per frame on [cls ; patches of that
-    frame]; the cls output is averaged over frames"""
+    frame]; the cls output is averaged over frames.  LN eps is 1e-5 here: the class is built with Block's DEFAULT
+    norm_layer=nn.LayerNorm (eva_btadapter.py:255, eva_vit.py:152), unlike the ViT's own blocks (eps 1e-6)"""
     p = f"BTAdapter_S.{j}."
     residual = x
     init_cls = x[:, :1, :]
@@ -145,7 +146,9 @@ def bt_adapter_forward(sd, frames, depth, num_heads, bt_depth=3, patch=14, colle
     frames [B,T,3,H,W] (or [T,3,H,W] = one clip, :236-238) -> [(B T), 1+P, D]"""
     if frames.dim() == 4:
         frames = frames[None]
-    B, T = frames.shape[:2]
+    elif frames.shape[1] == 3:
+        frames = frames.permute(0, 2, 1, 3, 4)                                    # [B,C,T,H,W] input, :231-233 (also
+    B, T = frames.shape[:2]                                                       # taken by a [B,T=3,C,H,W] clip!)
     x = vit_patch_embed(sd, frames.reshape((-1,) + frames.shape[2:]), patch)
     x = torch.cat((sd["cls_token"].expand(x.shape[0], -1, -1), x), dim=1) + sd["pos_embed"]   # :152-156
     branch = None
@@ -367,9 +370,14 @@ def encode_img(w, image, cfg, text_ids=None, text_mask=None, collect=None):
     image [B,T,3,H,W] or [T,3,H,W].  Returns inputs_llama [B,T,Q,4096] or [T,Q,4096]."""
     infer = image.dim() == 4
     T = image.shape[1]
-    if not infer:
-        image = image.reshape((-1,) + tuple(image.shape[2:]))                    # 'B T C H W -> (B T) C H W' :328
-    x = vit_forward(w["vit"], image, cfg["vit_depth"], cfg["vit_heads"], cfg.get("patch", 14), collect)
+    if cfg.get("vit_model", "eva_clip_g") == "eva_btadapter_g":
+        # :327 -- only eva_clip_g gets the flattened frames; the BT-Adapter encoder takes the clip tensor as is
+        x = bt_adapter_forward(w["vit"], image, cfg["vit_depth"], cfg["vit_heads"], cfg.get("bt_depth", 3),
+                               cfg.get("patch", 14), collect)
+    else:
+        if not infer:
+            image = image.reshape((-1,) + tuple(image.shape[2:]))                # 'B T C H W -> (B T) C H W' :328
+        x = vit_forward(w["vit"], image, cfg["vit_depth"], cfg["vit_heads"], cfg.get("patch", 14), collect)
     x = ln_vision(w["ln_vision"], x)                                             # :331
     if collect is not None:
         collect["ln_vision"] = x

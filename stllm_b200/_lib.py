@@ -38,6 +38,12 @@ SIGNATURES = {
                               c_void_p],
     "stllm_mean_frames_f16": [c_void_p, c_void_p, c_int, c_int, c_ll, c_void_p],
     "stllm_residual_merge_f16": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_ll, c_void_p],
+    "stllm_preprocess_frames_u8": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p,
+                                   c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_ll, c_void_p,
+                                   c_void_p],
+    "stllm_bt_vit_to_branch_f16": [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int,
+                                   c_int, c_void_p],
+    "stllm_bt_branch_to_vit_avg_f16": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "stllm_cosine_loss_f16": [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p],
     "stllm_cross_entropy_f16": [c_void_p, c_ll, c_void_p, c_int, c_int, c_ll, c_void_p, c_void_p],
 }

@@ -237,7 +237,165 @@ int grid_for(long long total, int block) {
   return (int)(g < cap ? (g > 0 ? g : 1) : cap);
 }
 
+// ------------------------------------------------------------------------------------------------
+// BT-Adapter layout changes (eva_btadapter.py).  The ViT stream x is frame-major: row (b*T + t)*(P+1) + l (l = 0 the
+// cls token).  The adapter branch z is patch-major:  rows [0, B) = one cls token per clip, then row B + (b*P + l)*T + t
+// = patch l of frame t  ('b (p t) m', eva_btadapter.py:188,220), so the temporal attention of one patch position is a
+// contiguous run of T rows.  Every row is `dim` contiguous fp16 values: the transposes move whole rows (coalesced).
+// ------------------------------------------------------------------------------------------------
+// z_out = T(x) + z_prev          (forward_branch :184-193 and the residual of BTAdapter_Spatial :273-276)
+//   patch rows: z_out = x_row + z_prev_row                         cls rows: z_out = fp16(mean_t x_cls) + z_prev_row
+// init (z_prev == nullptr, init_input :203-226):
+//   patch rows: z_out = fp16(fp16(x_row + pos[1+l]) + time[t])     cls rows: (fp16(mean_t x_cls) + fp16(bt_cls + pos[0])) / 2
+__global__ void bt_vit_to_branch_kernel(const __half* __restrict__ x, const __half* z_prev, __half* z_out,
+                                        const __half* __restrict__ pos, const __half* __restrict__ time_emb,
+                                        const __half* __restrict__ bt_cls, int B, int T, int P, int dim) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int dv = dim >> 3;
+  const long long rows = (long long)B * (1 + (long long)P * T);
+  const long long total = rows * dv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % dv);
+    const long long zr = i / dv;
+    float v[8];
+    if (zr < B) {
+      // cls row of clip b: mean over the T frames of the ViT cls tokens (fp32 accumulate, one fp16 rounding)
+      const long long b = zr;
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int t = 0; t < T; ++t) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + ((b * T + t) * (long long)(P + 1)) * dim) + c);
+        const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(h[j]);
+          acc[2 * j] += f.x;
+          acc[2 * j + 1] += f.y;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = __half2float(__float2half_rn(acc[j] / (float)T));
+      if (z_prev != nullptr) {
+        const uint4 u = *(reinterpret_cast<const uint4*>(z_prev + zr * dim) + c);
+        const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(h[j]);
+          v[2 * j] += f.x;
+          v[2 * j + 1] += f.y;
+        }
+      } else {
+        const uint4 uc = __ldg(reinterpret_cast<const uint4*>(bt_cls) + c);
+        const uint4 up = __ldg(reinterpret_cast<const uint4*>(pos) + c);
+        const __half2* hc = reinterpret_cast<const __half2*>(&uc);
+        const __half2* hp = reinterpret_cast<const __half2*>(&up);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(__hadd2(hc[j], hp[j]));     // cls_branch = fp16(BTAdapter_cls + pos[0])
+          v[2 * j] = __half2float(__float2half_rn(v[2 * j] + f.x)) * 0.5f;
+          v[2 * j + 1] = __half2float(__float2half_rn(v[2 * j + 1] + f.y)) * 0.5f;
+        }
+      }
+    } else {
+      const long long pr = zr - B;
+      const int t = (int)(pr % T);
+      const int l = (int)((pr / T) % P);
+      const long long b = pr / ((long long)T * P);
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(x + ((b * T + t) * (long long)(P + 1) + 1 + l) * dim) + c);
+      const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = __half22float2(h[j]);
+        v[2 * j] = f.x;
+        v[2 * j + 1] = f.y;
+      }
+      if (z_prev != nullptr) {
+        const uint4 uz = *(reinterpret_cast<const uint4*>(z_prev + zr * dim) + c);
+        const __half2* hz = reinterpret_cast<const __half2*>(&uz);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(hz[j]);
+          v[2 * j] += f.x;
+          v[2 * j + 1] += f.y;
+        }
+      } else {
+        const uint4 up = __ldg(reinterpret_cast<const uint4*>(pos + (long long)(1 + l) * dim) + c);
+        const uint4 ut = __ldg(reinterpret_cast<const uint4*>(time_emb + (long long)t * dim) + c);
+        const __half2* hp = reinterpret_cast<const __half2*>(&up);
+        const __half2* ht = reinterpret_cast<const __half2*>(&ut);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 fp = __half22float2(hp[j]);
+          const float2 ft = __half22float2(ht[j]);
+          v[2 * j] = __half2float(__float2half_rn(v[2 * j] + fp.x)) + ft.x;
+          v[2 * j + 1] = __half2float(__float2half_rn(v[2 * j + 1] + fp.y)) + ft.y;
+        }
+      }
+    }
+    uint4 o;
+    o.x = pack_half2(v[0], v[1]);
+    o.y = pack_half2(v[2], v[3]);
+    o.z = pack_half2(v[4], v[5]);
+    o.w = pack_half2(v[6], v[7]);
+    reinterpret_cast<uint4*>(z_out + zr * dim)[c] = o;
+  }
+}
+
+// out = (x + T^-1(z)) / 2   (forward_features :178-181): patch rows take their branch row, every frame's cls row takes
+// the clip's branch cls row.  out may alias x.
+__global__ void bt_branch_to_vit_avg_kernel(const __half* x, const __half* __restrict__ z, __half* out, int B, int T,
+                                            int P, int dim) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int dv = dim >> 3;
+  const long long rows = (long long)B * T * (P + 1);
+  const long long total = rows * dv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % dv);
+    const long long xr = i / dv;
+    const int l1 = (int)(xr % (P + 1));
+    const long long bt = xr / (P + 1);
+    const int t = (int)(bt % T);
+    const long long b = bt / T;
+    const long long zr = (l1 == 0) ? b : (long long)B + (b * P + (l1 - 1)) * T + t;
+    const uint4 ux = *(reinterpret_cast<const uint4*>(x + xr * dim) + c);
+    const uint4 uz = __ldg(reinterpret_cast<const uint4*>(z + zr * dim) + c);
+    const __half2* hx = reinterpret_cast<const __half2*>(&ux);
+    const __half2* hz = reinterpret_cast<const __half2*>(&uz);
+    uint4 o;
+    __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) oh[j] = __hmul2(__hadd2(hx[j], hz[j]), __float2half2_rn(0.5f));
+    reinterpret_cast<uint4*>(out + xr * dim)[c] = o;
+  }
+}
+
 }  // namespace
+
+extern "C" int stllm_bt_vit_to_branch_f16(const void* x, const void* z_prev, void* z_out, const void* pos,
+                                          const void* time_emb, const void* bt_cls, int B, int T, int P, int dim,
+                                          void* stream) {
+  STLLM_CHECK_ARG(x && z_out && B > 0 && T > 0 && P > 0 && dim > 0 && dim % 8 == 0);
+  STLLM_CHECK_ARG(z_prev != nullptr || (pos != nullptr && time_emb != nullptr && bt_cls != nullptr));
+  const long long total = (long long)B * (1 + (long long)P * T) * (dim / 8);
+  const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  STLLM_CHECK_CUDA(stllm_launch(bt_vit_to_branch_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream,
+                                (const __half*)x, (const __half*)z_prev, (__half*)z_out, (const __half*)pos,
+                                (const __half*)time_emb, (const __half*)bt_cls, B, T, P, dim));
+  return STLLM_OK;
+}
+
+extern "C" int stllm_bt_branch_to_vit_avg_f16(const void* x, const void* z, void* out, int B, int T, int P, int dim,
+                                              void* stream) {
+  STLLM_CHECK_ARG(x && z && out && B > 0 && T > 0 && P > 0 && dim > 0 && dim % 8 == 0);
+  const long long total = (long long)B * T * (P + 1) * (dim / 8);
+  const int grid = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
+  STLLM_CHECK_CUDA(stllm_launch(bt_branch_to_vit_avg_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream,
+                                (const __half*)x, (const __half*)z, (__half*)out, B, T, P, dim));
+  return STLLM_OK;
+}
 
 extern "C" int stllm_im2col_patch(const void* img, int img_is_f32, void* out, int n_img, int C, int H, int W, int P,
                                   int kpad, void* stream) {

@@ -281,6 +281,41 @@ def residual_merge(x, g, idx):
     return out
 
 
+def bt_vit_to_branch(x, B, T, P, z_prev=None, out=None, pos=None, time_emb=None, bt_cls=None):
+    """ViT stream x [(B*T)*(P+1), D] -> BT-Adapter branch layout [B + B*P*T, D] (+ z_prev), see include/stllm_b200.h"""
+    global launch_count
+    _need_cuda(x, z_prev, out, pos, time_emb, bt_cls)
+    D = x.shape[-1]
+    assert x.is_contiguous() and x.dtype == torch.float16 and x.numel() == B * T * (P + 1) * D
+    if out is None:
+        out = torch.empty(B + B * P * T, D, dtype=torch.float16, device=x.device)
+    assert out.is_contiguous() and out.shape == (B + B * P * T, D)
+    if z_prev is not None:
+        assert z_prev.is_contiguous() and z_prev.shape == out.shape
+    else:
+        assert pos.is_contiguous() and pos.shape == (P + 1, D) and time_emb.is_contiguous() and time_emb.shape[0] >= T
+        assert bt_cls.numel() == D
+    rc = _lib.load().stllm_bt_vit_to_branch_f16(_ptr(x), _ptr(z_prev), _ptr(out), _ptr(pos), _ptr(time_emb),
+                                                _ptr(bt_cls), B, T, P, D, _stream())
+    _lib.check(rc, "stllm_bt_vit_to_branch_f16")
+    launch_count += 1
+    return out
+
+
+def bt_branch_to_vit_avg(x, z, B, T, P, out=None):
+    """(x + branch rows back in ViT order) / 2, x [(B*T)*(P+1), D], z [B + B*P*T, D]"""
+    global launch_count
+    _need_cuda(x, z, out)
+    D = x.shape[-1]
+    assert x.is_contiguous() and z.is_contiguous() and z.shape == (B + B * P * T, D)
+    if out is None:
+        out = torch.empty_like(x)
+    rc = _lib.load().stllm_bt_branch_to_vit_avg_f16(_ptr(x), _ptr(z), _ptr(out), B, T, P, D, _stream())
+    _lib.check(rc, "stllm_bt_branch_to_vit_avg_f16")
+    launch_count += 1
+    return out
+
+
 def cosine_loss(a, b):
     """mean over rows of 2 - 2 cos(a_row, b_row); a, b [rows, C] fp16 -> fp32 scalar tensor"""
     global launch_count

@@ -80,7 +80,8 @@ class STLLMModel(nn.Module):
                  tokenizer=None, llama_tokenizer=None, vit_depth=39, qformer_config=None, vit_checkpoint=None,
                  llama_hidden=4096):
         super().__init__()
-        assert vit_model == "eva_clip_g", "vit model must be eva_clip_g (eva_btadapter_g is outside this build's scope)"
+        assert vit_model in ["eva_clip_g", "eva_btadapter_g"], \
+            "vit model must be eva_clip_g for current version of MiniGPT-4"          # blip2.py:65
         if not has_qformer:
             raise NotImplementedError("has_qformer=False is not used by any shipped config (SURVEY a15')")
         self.tokenizer = tokenizer
@@ -104,6 +105,9 @@ class STLLMModel(nn.Module):
         self.vit_model = vit_model
         self.visual_encoder = create_eva_vit_g(img_size, drop_path_rate, use_grad_checkpoint, vit_precision,
                                                checkpoint_path=vit_checkpoint, depth=vit_depth)
+        if vit_model == "eva_btadapter_g":                                          # blip2.py:66-71
+            from .eva_btadapter import create_eva_btadapter
+            self.visual_encoder = create_eva_btadapter(vit_precision, clip=self.visual_encoder)
         self.ln_vision = LayerNorm(self.visual_encoder.num_features)
         self.has_qformer = has_qformer
         qcfg = qformer_config or BertConfig()

@@ -121,6 +121,70 @@ def golden_llama(ref):
           **_sd_arrays("w.", sd))
 
 
+@torch.no_grad()
+def golden_btadapter(ref):
+    """The reference's EVAVisionTransformer_BTAdapter (eva_btadapter.py) at a small width.  Its constructor hard-codes
+    create_eva_vit_g(224, 0, False, "fp16") (a 1 B-parameter ViT-g, :52-54); for the fixture that ONE factory call is
+    pointed at a small VisionTransformer of the same reference class -- every line of the BT-Adapter code (init_weights,
+    forward_features, forward_branch, init_input, BTAdapter_Spatial / BTAdapter_Temp) runs unmodified."""
+    import sys
+    bt = sys.modules.get("stllm.models.eva_btadapter")
+    assert bt is not None, "eva_btadapter is imported by blip2.py"
+    torch.manual_seed(3)
+    small = lambda *a, **k: ref_shim.build_vit(ref, img_size=56, embed_dim=176, depth=4, num_heads=2)
+    orig = bt.create_eva_vit_g
+    bt.create_eva_vit_g = small
+    try:
+        model = bt.EVAVisionTransformer_BTAdapter(depth=3).eval()
+    finally:
+        bt.create_eva_vit_g = orig
+    for n, p in model.named_parameters():
+        if n.endswith("bias") or n.endswith("q_bias") or n.endswith("v_bias"):
+            p.data.normal_(0, 0.05)
+        elif "norm" in n and n.endswith("weight"):
+            p.data.add_(torch.randn_like(p) * 0.1)
+        elif "temporal_fc.weight" in n:
+            p.data.normal_(0, 0.05)            # zero-init in the reference (:297) would hide the temporal branch
+        elif n in ("BTAdapter_cls",):
+            p.data.normal_(0, 0.05)
+    sd = _round_fp16_(model)
+    frames = torch.randn(2, 4, 3, 56, 56, generator=torch.Generator().manual_seed(1234))   # B=2 clips, T=4 frames
+    out = model(frames)
+    out1 = model(frames[0])                                                                  # 4-D: one clip
+    _save("btadapter_small.npz", frames=frames.numpy(), out=out.numpy(), out_clip0=out1.numpy(), depth=4, heads=2,
+          bt_depth=3, **_sd_arrays("w.", sd))
+
+
+def golden_preprocess():
+    """Chat.transform (conversation.py:192-200) built from the reference's OWN transform classes
+    (stllm/test/video_transforms.py, loaded from /root/reference) on seeded synthetic RGB frames: down-scaling
+    landscape, down-scaling portrait and an up-scaling case.  Third-party arithmetic underneath: Pillow's resampler and
+    torchvision's Resize / CenterCrop size rules (versions installed here: see oracle/preprocess_oracle.py)."""
+    import importlib.util
+    import torchvision.transforms as T
+    from PIL import Image
+    from torchvision.transforms import InterpolationMode
+    spec = importlib.util.spec_from_file_location("ref_video_transforms",
+                                                  os.path.join(ref_shim.REF, "stllm/test/video_transforms.py"))
+    vt = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(vt)
+    mean, std = [0.48145466, 0.4578275, 0.40821073], [0.26862954, 0.26130258, 0.27577711]
+    tr = T.Compose([vt.GroupScale(int(224), interpolation=InterpolationMode.BICUBIC), vt.GroupCenterCrop(224),
+                    vt.Stack(), vt.ToTorchFormatTensor(), vt.GroupNormalize(mean, std)])
+    rng = np.random.default_rng(1234)
+    out = {}
+    for name, (h, w) in {"land": (270, 480), "port": (300, 250), "up": (120, 200)}.items():
+        yy, xx = np.mgrid[0:h, 0:w]
+        base = np.stack([(np.sin(xx / 7.0) * 0.5 + 0.5) * 255, (np.cos(yy / 5.0 + xx / 11.0) * 0.5 + 0.5) * 255,
+                         ((xx * 3 + yy * 5) % 256)], -1)
+        frame = np.clip(base + rng.normal(0, 20, base.shape), 0, 255).astype(np.uint8)
+        video = tr([Image.fromarray(frame)])
+        bt, hh, ww = video.size()
+        out[f"{name}_frame"] = frame
+        out[f"{name}_out"] = video.view(bt // 3, 3, hh, ww).numpy()        # conversation.py:277
+    _save("preprocess_frames.npz", **out)
+
+
 def golden_mask(ref):
     """RandomMaskingGenerator (utils.py:4-16) + the rate draw (st_llm.py:484-485) under fixed numpy seeds"""
     out = {}
@@ -175,7 +239,7 @@ def golden_flow(ref):
 
 if __name__ == "__main__":
     ref = ref_shim.load_reference()
-    which = sys.argv[1:] or ["vit", "qformer", "qformer_text", "llama", "mask", "flow"]
+    which = sys.argv[1:] or ["vit", "qformer", "qformer_text", "llama", "mask", "flow", "btadapter", "preprocess"]
     if "vit" in which:
         golden_vit(ref)
     if "qformer" in which:
@@ -188,3 +252,7 @@ if __name__ == "__main__":
         golden_mask(ref)
     if "flow" in which:
         golden_flow(ref)
+    if "btadapter" in which:
+        golden_btadapter(ref)
+    if "preprocess" in which:
+        golden_preprocess()

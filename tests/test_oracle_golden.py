@@ -62,3 +62,13 @@ def test_mask_and_residual_index_bit_exact():
     assert O.get_residual_index(4, 64).tolist() == [8, 24, 40, 56]
     assert O.get_residual_index(4, 16).tolist() == [2, 6, 10, 14]
     assert O.get_residual_index(16, 64).tolist() == [2 + 4 * i for i in range(16)]
+
+
+def test_btadapter_matches_reference():
+    """eva_btadapter.py: oracle vs the reference's own EVAVisionTransformer_BTAdapter"""
+    sd, g = load_golden("btadapter_small.npz")
+    frames = torch.from_numpy(g["frames"])
+    out = O.bt_adapter_forward(sd, frames, int(g["depth"]), int(g["heads"]), bt_depth=int(g["bt_depth"]))
+    assert_close(out, g["out"], 3e-5, 1e-5, "bt-adapter out [B,T]")
+    out1 = O.bt_adapter_forward(sd, frames[0], int(g["depth"]), int(g["heads"]), bt_depth=int(g["bt_depth"]))
+    assert_close(out1, g["out_clip0"], 3e-5, 1e-5, "bt-adapter out, 4-D single clip")

@@ -41,6 +41,77 @@ def _seeded_sd(module, seed, std=0.02):
     return sd
 
 
+# ------------------------------------------------------------------------------------------------- BT-Adapter
+def _btadapter(embed_dim, depth, heads, img):
+    from functools import partial
+    from stllm_b200.eva_btadapter import EVAVisionTransformer_BTAdapter
+    from stllm_b200.eva_vit import VisionTransformer
+    clip = VisionTransformer(img_size=img, patch_size=14, use_mean_pooling=False, embed_dim=embed_dim, depth=depth,
+                             num_heads=heads, mlp_ratio=4.3637, qkv_bias=True,
+                             norm_layer=partial(torch.nn.LayerNorm, eps=1e-6))
+    return EVAVisionTransformer_BTAdapter(depth=3, clip=clip)
+
+
+def test_btadapter_small_vs_reference_golden():
+    """eva_btadapter.py (vit_model 'eva_btadapter_g'): CUDA path vs the output of the reference's own class"""
+    sd, g = load_golden("btadapter_small.npz")
+    model = _btadapter(176, 4, 2, 56)
+    model.load_state_dict(sd, strict=True)
+    model = model.half().cuda()
+    frames = torch.from_numpy(g["frames"]).cuda()
+    out = model(frames)
+    assert model.T == 4 and tuple(out.shape) == tuple(g["out"].shape)
+    assert_close(out, g["out"], atol=4e-2, rtol=2e-2, what="bt-adapter small vs reference")
+    assert rel_fro(out, g["out"]) < 5e-3
+    out1 = model(frames[0])                                                   # 4-D input = one clip (:236-238)
+    assert_close(out1, g["out_clip0"], atol=4e-2, rtol=2e-2, what="bt-adapter small, single clip")
+    assert torch.equal(out1, model(frames[:1]))
+
+
+def test_btadapter_g_width_vs_oracle():
+    """ViT-g width (1408, 16 heads x 88, 257 tokens), 4 ViT blocks + 3 adapter layers, B=2 clips x T=4 frames"""
+    model = _btadapter(1408, 4, 16, 224)
+    sd = _seeded_sd(model, 11)
+    model.load_state_dict(sd, strict=True)
+    model = model.half().cuda()
+    frames = torch.randn(2, 4, 3, 224, 224, generator=torch.Generator().manual_seed(12))
+    col = {}
+    ref = O.bt_adapter_forward(sd, frames, 4, 16, bt_depth=3, collect=col)
+    out, branches = model.forward_features(frames.reshape(-1, 3, 224, 224).cuda(), 2, 4, return_branches=True)
+    for j in range(3):
+        assert rel_fro(branches[j], col[f"bt_branch{j}"]) < 5e-3, j
+    assert_close(out, ref, atol=4e-2, rtol=2e-2, what="bt-adapter ViT-g width vs oracle")
+    assert rel_fro(out, ref) < 5e-3
+
+
+def test_encode_img_with_btadapter_encoder():
+    """st_llm.py:321-377 with vit_model='eva_btadapter_g': the 5-D clip goes to the encoder un-flattened (:327)"""
+    from stllm_b200.st_llm import STLLMForCausalLM
+    from stllm_b200.qformer import BertConfig
+    torch.manual_seed(0)
+    cfg = dict(llama_config=dict(vocab_size=64, hidden_size=4096, intermediate_size=256, num_hidden_layers=1,
+                                 num_attention_heads=32), vit_model="eva_btadapter_g", vit_depth=4, video_input="all",
+               qformer_config=BertConfig(num_hidden_layers=2), vit_precision="fp16")
+    old = torch.get_default_dtype()
+    torch.set_default_dtype(torch.float16)
+    try:
+        with torch.device("cuda"):
+            model = STLLMForCausalLM.from_config(cfg).eval()
+    finally:
+        torch.set_default_dtype(old)
+    sm = model.get_model().stllm_model
+    for blk in sm.visual_encoder.BTAdapter_T:
+        blk.temporal_fc.weight.data.normal_(0, 0.02)
+    sm.visual_encoder._packed = None
+    frames = torch.randn(2, 4, 3, 224, 224, generator=torch.Generator().manual_seed(5))
+    out, atts, use_image = sm.encode_img(frames.cuda())
+    assert tuple(out.shape) == (2, 4, 32, 4096) and use_image is False and sm.visual_encoder.T == 4
+    w = O.split_state_dict(model.state_dict())
+    ref = O.encode_img(w, frames, dict(vit_depth=4, vit_heads=16, qf_layers=2, vit_model="eva_btadapter_g", bt_depth=3))
+    assert tuple(ref.shape) == (2, 4, 32, 4096)
+    assert rel_fro(out, ref) < 6e-3
+
+
 # ------------------------------------------------------------------------------------------------- ViT
 def test_vit_small_vs_reference_golden():
     from stllm_b200.eva_vit import VisionTransformer
