@@ -69,23 +69,38 @@ __global__ void rope_kernel(__half* __restrict__ x, long long ldx, const int* __
   pdl_launch_dependents();
   pdl_wait();
   const int half_d = D >> 1;
-  const long long total = (long long)rows * nheads * (half_d >> 1);  // 2 pairs per thread (half2)
+  const int groups = half_d >> 3;                                   // 8 rotation pairs (16 bytes + 16 bytes) per thread
+  const long long total = (long long)rows * nheads * groups;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int j = (int)(i % (half_d >> 1)) * 2;
-    const long long rh = i / (half_d >> 1);
+    const int j = (int)(i % groups) * 8;
+    const long long rh = i / groups;
     const int h = (int)(rh % nheads);
     const long long row = rh / nheads;
     const int ppos = pos[row];
     __half* base = x + row * ldx + (long long)h * D;
-    const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(base + j));
-    const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(base + j + half_d));
-    const float2 c = *reinterpret_cast<const float2*>(cos_t + (long long)ppos * half_d + j);
-    const float2 s = *reinterpret_cast<const float2*>(sin_t + (long long)ppos * half_d + j);
-    // out_lo = lo*cos - hi*sin ; out_hi = hi*cos + lo*sin   (cos/sin identical for j and j + D/2)
-    *reinterpret_cast<__half2*>(base + j) = __floats2half2_rn(lo.x * c.x - hi.x * s.x, lo.y * c.y - hi.y * s.y);
-    *reinterpret_cast<__half2*>(base + j + half_d) =
-        __floats2half2_rn(hi.x * c.x + lo.x * s.x, hi.y * c.y + lo.y * s.y);
+    const uint4 ulo = *reinterpret_cast<const uint4*>(base + j);
+    const uint4 uhi = *reinterpret_cast<const uint4*>(base + j + half_d);
+    const float4* cp = reinterpret_cast<const float4*>(cos_t + (long long)ppos * half_d + j);
+    const float4* sp = reinterpret_cast<const float4*>(sin_t + (long long)ppos * half_d + j);
+    const float4 c0 = __ldg(cp), c1 = __ldg(cp + 1), s0 = __ldg(sp), s1 = __ldg(sp + 1);
+    const float c[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    const float sn[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    const __half2* hlo = reinterpret_cast<const __half2*>(&ulo);
+    const __half2* hhi = reinterpret_cast<const __half2*>(&uhi);
+    uint4 olo, ohi;
+    uint32_t* plo = reinterpret_cast<uint32_t*>(&olo);
+    uint32_t* phi = reinterpret_cast<uint32_t*>(&ohi);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float2 lo = __half22float2(hlo[q]);
+      const float2 hi = __half22float2(hhi[q]);
+      // out_lo = lo*cos - hi*sin ; out_hi = hi*cos + lo*sin   (cos/sin identical for j and j + D/2)
+      plo[q] = pack_half2(lo.x * c[2 * q] - hi.x * sn[2 * q], lo.y * c[2 * q + 1] - hi.y * sn[2 * q + 1]);
+      phi[q] = pack_half2(hi.x * c[2 * q] + lo.x * sn[2 * q], hi.y * c[2 * q + 1] + lo.y * sn[2 * q + 1]);
+    }
+    *reinterpret_cast<uint4*>(base + j) = olo;
+    *reinterpret_cast<uint4*>(base + j + half_d) = ohi;
   }
 }
 
@@ -420,9 +435,9 @@ extern "C" int stllm_vit_assemble_f16(const void* patches, long long ldp, const 
 
 extern "C" int stllm_rope_f16(void* x, long long ldx, const int* pos, const float* cos_t, const float* sin_t, int rows,
                               int nheads, int head_dim, int max_pos, void* stream) {
-  STLLM_CHECK_ARG(x && pos && cos_t && sin_t && rows > 0 && nheads > 0 && head_dim % 4 == 0 && ldx % 2 == 0);
-  STLLM_CHECK_ARG(max_pos > 0 && (((uintptr_t)x) & 3) == 0 && (((uintptr_t)cos_t | (uintptr_t)sin_t) & 7) == 0);
-  const long long total = (long long)rows * nheads * (head_dim / 4);
+  STLLM_CHECK_ARG(x && pos && cos_t && sin_t && rows > 0 && nheads > 0 && head_dim % 16 == 0 && ldx % 8 == 0);
+  STLLM_CHECK_ARG(max_pos > 0 && (((uintptr_t)x) & 15) == 0 && (((uintptr_t)cos_t | (uintptr_t)sin_t) & 15) == 0);
+  const long long total = (long long)rows * nheads * (head_dim / 16);
   STLLM_CHECK_CUDA(stllm_launch(rope_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, (__half*)x, ldx, pos, cos_t, sin_t, rows, nheads,
                                                                       head_dim));
     return STLLM_OK;
