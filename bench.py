@@ -217,7 +217,7 @@ def main():
     config = {"workload": workload, "frames_per_clip": T_FRAMES, "clips_per_gpu": args.batch, "seq_len": S,
               "parallelism": f"clip-parallel dp{world}" if world > 1 else "single GPU",
               "l2": "weights streamed per step (15.9 GB fp16) >> 126 MB L2; no explicit flush needed",
-              "cuda_graph": not args.no_graph}
+              "cuda_graph": not args.no_graph, "norms_folded_into_gemm": os.environ.get("STLLM_FUSE_NORM", "1") != "0"}
 
     if args.impl == "reference":
         if rank != 0:
@@ -225,7 +225,7 @@ def main():
         warm = max(args.warmup, 0)
         vals = []
         sample = ""
-        cpu = CpuReference()
+        cpu = CpuReference(budget_frames=2, llama_layers_timed=2)
         for i in range(warm + args.steps):
             fps, sample, t_clip = cpu.run()
             if i >= warm:
@@ -375,7 +375,8 @@ def main():
     if os.path.exists(tp):
         with open(tp) as f:
             traffic = json.load(f).get("dram_bytes_per_launch")
-    roofline = {"bound": "tensor", "kernel": "gemm_f16_tcgen05_kernel (tcgen05.mma kind::f16, TMA, TMEM)",
+    roofline = {"bound": "tensor", "kernel": "gemm_f16_tcgen05_2cta_kernel / gemm_f16_tcgen05_kernel (tcgen05.mma "
+                "kind::f16 cta_group::2 / ::1, TMA, TMEM; LayerNorm/RMSNorm, bias, GELU, SwiGLU, residual in the epilogue)",
                 "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
                 "frac": achieved / peaks["tf_sustained"], "traffic": traffic, "peak_source": peaks["source"] +
                 " bf16 dense sustained (kernel timed inside a long step); burst = %.0f" % peaks["tf_burst"],
@@ -395,7 +396,7 @@ def main():
             "gpu_launches": pipe.launches_per_step * args.steps, "launches_per_step": pipe.launches_per_step,
             "roofline": roofline}
     if world == 1 and not args.skip_cpu_baseline:
-        cpu = CpuReference(budget_frames=1, llama_layers_timed=1)
+        cpu = CpuReference(budget_frames=2, llama_layers_timed=2)
         cpu.run()  # warm-up
         fps, sample, _ = cpu.run()
         line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cpu.threads, "kind": "port",

@@ -235,9 +235,12 @@ class LlamaModel(nn.Module):
         # per-row sum of squares of the residual stream after o_proj (slot 2*li) and after down_proj (slot 2*li + 1)
         stats = None
         if fuse:
-            if self._stats is None or self._stats.shape[1] != B * S or self._stats.device != dev:
-                self._stats = ops.row_stats_buffer(2 * nL, B * S, C, 1, dev)
-            stats = self._stats
+            key = (B * S, str(dev))                      # prefill and decode steps alternate: one buffer per row count
+            if self._stats is None:
+                self._stats = {}
+            if key not in self._stats:
+                self._stats[key] = ops.row_stats_buffer(2 * nL, B * S, C, 1, dev)
+            stats = self._stats[key]
         for li, L in enumerate(P["layers"]):
             if fuse and li > 0:
                 qkv = ops.gemm(x, L["w_qkv"], norm=ops.NORM_RMS, rs_in=stats[2 * li - 1], norm_eps=eps)
