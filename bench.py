@@ -34,7 +34,7 @@ T_FRAMES, IMG, PROMPT_LEN, VOCAB, Q_TOK = 16, 224, 64, 32000, 32
 
 
 # ---------------------------------------------------------------------------------------------- FLOP accounting
-def algorithmic_flops(n_frames, S, vocab=VOCAB, llama_layers=32, vit_depth=39, qf_layers=12):
+def algorithmic_flops(n_frames, S, vocab=VOCAB, llama_layers=32, vit_depth=39, qf_layers=12, n_clips=1):
     """SURVEY.md 8(d) formulas (multiply-add = 2; causal attention = half of dense; padding FLOPs not counted)"""
     f_vit = 2 * 256 * 588 * 1408 + vit_depth * (2 * 257 * 1408 * (4224 + 1408 + 2 * 6144) + 4 * 257 ** 2 * 1408)
     n_cross = (qf_layers + 1) // 2
@@ -42,8 +42,8 @@ def algorithmic_flops(n_frames, S, vocab=VOCAB, llama_layers=32, vit_depth=39, q
         n_cross * (2 * 32 * 768 * 2 * 768 + 2 * 257 * 1408 * 2 * 768 + 4 * 32 * 257 * 768)
     f_proj = 2 * 32 * 768 * 4096
     f_llm = llama_layers * (2 * S * 4096 * (4 * 4096 + 3 * 11008) + 2 * S ** 2 * 4096) + 2 * S * 4096 * vocab
-    return dict(vit=n_frames * f_vit, qformer=n_frames * f_qf, proj=n_frames * f_proj, llm=f_llm,
-                total=n_frames * (f_vit + f_qf + f_proj) + f_llm)
+    return dict(vit=n_frames * f_vit, qformer=n_frames * f_qf, proj=n_frames * f_proj, llm=n_clips * f_llm,
+                total=n_frames * (f_vit + f_qf + f_proj) + n_clips * f_llm)
 
 
 def measured_peaks():
@@ -167,6 +167,18 @@ class CpuReference:
         self.frames = torch.randn(budget_frames, 3, IMG, IMG, generator=g)
         self.emb = torch.randn(1, S, H, generator=g)
 
+    @classmethod
+    def sized_for(cls, seconds_per_step):
+        """bounded sample: as many of the 16 frames / 32 Llama layers as fit ~seconds_per_step on this host (probed
+        with 1 frame + 1 layer); the rest is extrapolated linearly and the sample string says so"""
+        probe = cls(budget_frames=1, llama_layers_timed=1)
+        probe.run()
+        _, _, _ = probe.run()
+        t_frame, t_layer = probe.last_t_frame, probe.last_t_layer
+        frames = max(1, min(T_FRAMES, int(0.7 * seconds_per_step / max(t_frame, 1e-3))))
+        layers = max(1, min(8, int(0.3 * seconds_per_step / max(t_layer, 1e-3))))
+        return cls(budget_frames=frames, llama_layers_timed=layers)
+
     def run(self):
         """one bounded sample -> (frames/s of the full config-2 clip, description, s/clip)"""
         torch = self.torch
@@ -186,6 +198,7 @@ class CpuReference:
             t0 = time.perf_counter()
             _ = torch.nn.functional.linear(hid, self.w_head)
             t_head = time.perf_counter() - t0
+        self.last_t_frame, self.last_t_layer = t_vit + t_qf, t_layers
         t_clip = T_FRAMES * (t_vit + t_qf) + 32 * t_layers + t_head
         sample = (f"oracle port (fp32 torch CPU, {self.threads} threads): ViT-g 39 blocks on {self.nf} frame(s) "
                   f"{t_vit*self.nf:.2f}s, ln_vision+12-layer Q-Former+llama_proj {t_qf*self.nf:.2f}s, {self.nl} "
@@ -225,11 +238,15 @@ def main():
         warm = max(args.warmup, 0)
         vals = []
         sample = ""
-        cpu = CpuReference(budget_frames=2, llama_layers_timed=2)
+        cpu = CpuReference.sized_for(seconds_per_step=4.0)
+        t_start = time.time()
         for i in range(warm + args.steps):
             fps, sample, t_clip = cpu.run()
             if i >= warm:
                 vals.append(fps)
+            if time.time() - t_start > 170.0 and vals:      # keep the whole arm within a few minutes on slow hosts
+                sample += f"; stopped after {len(vals)} of {args.steps} timed steps (170 s budget)"
+                break
         v = statistics.median(vals)
         line = {"impl": "reference", "metric": "video frames/sec (16f, 224^2, Vicuna-7B prefill)", "value": v,
                 "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -368,7 +385,8 @@ def main():
     value = frames_per_step / (ms_step / 1e3)
     e2e_value = frames_per_step / (ms_e2e / 1e3)
     peaks = measured_peaks()
-    fl = algorithmic_flops(args.batch * T_FRAMES, S, VOCAB, args.llama_layers, args.vit_depth, args.qformer_layers)
+    fl = algorithmic_flops(args.batch * T_FRAMES, S, VOCAB, args.llama_layers, args.vit_depth, args.qformer_layers,
+                           n_clips=args.batch)
     achieved = gemm_flops / (ms_gemm / 1e3) / 1e12
     traffic = None
     tp = os.path.join(ROOT, "profiles", "gemm_traffic.json")
@@ -396,7 +414,7 @@ def main():
             "gpu_launches": pipe.launches_per_step * args.steps, "launches_per_step": pipe.launches_per_step,
             "roofline": roofline}
     if world == 1 and not args.skip_cpu_baseline:
-        cpu = CpuReference(budget_frames=2, llama_layers_timed=2)
+        cpu = CpuReference.sized_for(seconds_per_step=6.0)
         cpu.run()  # warm-up
         fps, sample, _ = cpu.run()
         line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cpu.threads, "kind": "port",
