@@ -220,6 +220,8 @@ def main():
     ap.add_argument("--vit-depth", type=int, default=39)
     ap.add_argument("--qformer-layers", type=int, default=12)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=1,
+                    help="experiment: independent steps replayed round-robin on this many CUDA streams (value only)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -230,7 +232,8 @@ def main():
     config = {"workload": workload, "frames_per_clip": T_FRAMES, "clips_per_gpu": args.batch, "seq_len": S,
               "parallelism": f"clip-parallel dp{world}" if world > 1 else "single GPU",
               "l2": "weights streamed per step (15.9 GB fp16) >> 126 MB L2; no explicit flush needed",
-              "cuda_graph": not args.no_graph, "norms_folded_into_gemm": os.environ.get("STLLM_FUSE_NORM", "1") != "0"}
+              "cuda_graph": not args.no_graph, "norms_folded_into_gemm": os.environ.get("STLLM_FUSE_NORM", "1") != "0",
+              "streams": args.streams}
 
     if args.impl == "reference":
         if rank != 0:
@@ -309,13 +312,39 @@ def main():
     if world > 1:
         gather_buf = torch.empty(world * args.batch, VOCAB, dtype=torch.float16, device=dev)
 
+    # experiment (--streams N > 1): N pipelines (own activations / graphs, shared weights) on N streams; consecutive,
+    # independent steps overlap, each step still runs the whole path.  The default (1) is the contract's plain loop.
+    extra = []
+    if args.streams > 1 and world == 1:
+        for _ in range(args.streams - 1):
+            p2 = VideoPrefillPipeline(model, args.batch, T_FRAMES, PROMPT_LEN, IMG, use_graph=not args.no_graph)
+            p2.frames.copy_(frames_host)
+            p2.prompt_ids.copy_(ids_host)
+            p2.capture()
+            extra.append(p2)
+    pipes = [pipe] + extra
+    side = [torch.cuda.Stream() for _ in pipes]
+    step_no = [0]
+
     def step_device():
-        pipe.run()
+        if len(pipes) == 1:
+            pipe.run()
+        else:
+            i = step_no[0] % len(pipes)
+            step_no[0] += 1
+            side[i].wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side[i]):
+                pipes[i].run()
         if world > 1:
             dist.all_gather_into_tensor(gather_buf, pipe.last_logits)
 
-    for _ in range(max(args.warmup, 3)):
+    def join_streams():
+        for st in side:
+            torch.cuda.current_stream().wait_stream(st)
+
+    for _ in range(max(args.warmup, 3) * len(pipes)):
         step_device()
+    join_streams()
     torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -330,6 +359,7 @@ def main():
     e0.record()
     for _ in range(args.steps):
         step_device()
+    join_streams()
     e1.record()
     torch.cuda.synchronize()
     torch.cuda.profiler.stop()

@@ -76,7 +76,6 @@ class EVAVisionTransformer_BTAdapter(nn.Module):
         self.T = 1
         self._packed = None
         self._idx = {}
-        self._stats = None
 
     def init_weights(self):
         """eva_btadapter.py:89-99: the spatial adapters start as copies of the last `depth` ViT blocks"""
@@ -162,9 +161,7 @@ class EVAVisionTransformer_BTAdapter(nn.Module):
         nb = len(P["blocks"])
         stats = None
         if P["fuse"]:
-            if self._stats is None or self._stats.shape[1] != n_img * n_tok or self._stats.device != xt.device:
-                self._stats = ops.row_stats_buffer(2 * nb, n_img * n_tok, D, 2, xt.device)
-            stats = self._stats
+            stats = ops.cached_row_stats(self, 2 * nb, n_img * n_tok, D, 2, xt.device)
         z = None
         zh = None
         branches = []

@@ -161,7 +161,6 @@ class VisionTransformer(nn.Module):
         self.apply(self._init_weights)
         self.fix_init_weight()
         self._packed = None
-        self._stats = None
 
     def fix_init_weight(self):
         for layer_id, layer in enumerate(self.blocks):
@@ -228,9 +227,7 @@ class VisionTransformer(nn.Module):
         # folded LayerNorms: (sum, sum of squares) per token row after proj (slot 2i) and after fc2 (slot 2i + 1)
         stats = None
         if P["fuse"]:
-            if self._stats is None or self._stats.shape[1] != B * n_tok or self._stats.device != xt.device:
-                self._stats = ops.row_stats_buffer(2 * nb, B * n_tok, D, 2, xt.device)
-            stats = self._stats
+            stats = ops.cached_row_stats(self, 2 * nb, B * n_tok, D, 2, xt.device)
         for i, bw in enumerate(P["blocks"]):
             run_block(bw, xt, h, B, n_tok, Hh, d, self.ln_eps,
                       stats_in=stats[2 * i - 1] if (stats is not None and i > 0) else None,

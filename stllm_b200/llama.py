@@ -131,7 +131,6 @@ class LlamaModel(nn.Module):
         self.norm = LlamaRMSNorm(config.hidden_size, eps=config.rms_norm_eps)
         self._packed = None
         self._rope = None
-        self._stats = None
         std = config.initializer_range
         for m in self.modules():
             if isinstance(m, (nn.Linear, nn.Embedding)):
@@ -235,12 +234,7 @@ class LlamaModel(nn.Module):
         # per-row sum of squares of the residual stream after o_proj (slot 2*li) and after down_proj (slot 2*li + 1)
         stats = None
         if fuse:
-            key = (B * S, str(dev))                      # prefill and decode steps alternate: one buffer per row count
-            if self._stats is None:
-                self._stats = {}
-            if key not in self._stats:
-                self._stats[key] = ops.row_stats_buffer(2 * nL, B * S, C, 1, dev)
-            stats = self._stats[key]
+            stats = ops.cached_row_stats(self, 2 * nL, B * S, C, 1, dev)   # prefill / decode: one buffer per row count
         for li, L in enumerate(P["layers"]):
             if fuse and li > 0:
                 qkv = ops.gemm(x, L["w_qkv"], norm=ops.NORM_RMS, rs_in=stats[2 * li - 1], norm_eps=eps)

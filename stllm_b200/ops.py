@@ -3,6 +3,7 @@
 torch is used only for device memory and the current CUDA stream; all arithmetic happens in the sm_100a
 kernels of ``libstllm_b200.so``.  Every wrapper raises on non-CUDA tensors: there is no CPU fallback.
 """
+import collections
 import ctypes
 import math
 
@@ -120,6 +121,29 @@ def row_stats_buffer(n_buffers, rows, cols, mode, device):
     by the producing GEMM on each forward, the padding stays zero: no per-step zeroing is needed."""
     stride = (((cols + 127) // 128) * mode + 7) // 8 * 8
     return torch.zeros(n_buffers, rows, stride, dtype=torch.float32, device=device)
+
+
+# Concurrent forwards (two pipelines replaying their CUDA graphs on two streams, bench.py --streams) must not share
+# statistics buffers: the pipeline sets `stats_context` to its own id while it records / runs a step.
+stats_context = 0
+_stats_cache = collections.OrderedDict()
+_STATS_CACHE_EAGER_MAX = 16
+
+
+def cached_row_stats(owner, n_buffers, rows, cols, mode, device):
+    """row_stats_buffer cached per (module, stats_context, shape): allocated once, rewritten on every forward.
+    Eager calls (context 0: varying prompt lengths, decode steps) share a small LRU; buffers of a pipeline context are
+    kept for the life of the process because its CUDA graph holds their addresses."""
+    key = (id(owner), stats_context, n_buffers, rows, cols, mode, str(device))
+    buf = _stats_cache.get(key)
+    if buf is None:
+        buf = _stats_cache[key] = row_stats_buffer(n_buffers, rows, cols, mode, device)
+        eager = [k for k in _stats_cache if k[1] == 0]
+        if len(eager) > _STATS_CACHE_EAGER_MAX:
+            del _stats_cache[eager[0]]
+    else:
+        _stats_cache.move_to_end(key)
+    return buf
 
 
 def gemm_plan(M, N, K, epilogue=EPI_NONE):

@@ -42,7 +42,11 @@ def build_model(llama_layers=32, vit_depth=39, qformer_layers=12, vocab_size=320
 class VideoPrefillPipeline:
     """frames [B,T,3,H,W] (fp16, device) + prompt ids [B,P] -> logits [B,S,V]; optionally graph-captured."""
 
+    _next_context = 0
+
     def __init__(self, model, batch, frames, prompt_len, img_size=224, use_graph=True):
+        VideoPrefillPipeline._next_context += 1
+        self.context = VideoPrefillPipeline._next_context   # private row-statistics buffers (ops.stats_context)
         self.model = model
         self.sm = model.get_model().stllm_model
         self.B, self.T, self.P = batch, frames, prompt_len
@@ -56,6 +60,13 @@ class VideoPrefillPipeline:
         self.use_graph = use_graph
 
     def _step(self):
+        prev, ops.stats_context = ops.stats_context, self.context
+        try:
+            return self._step_impl()
+        finally:
+            ops.stats_context = prev
+
+    def _step_impl(self):
         sm = self.sm
         emb, _, _ = sm.encode_img(self.frames)                       # [B,T,Q,D]
         vid = sm.aggregate_video(emb)                                # [B,1,L,D]
