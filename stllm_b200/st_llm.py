@@ -529,10 +529,15 @@ class STLLMForCausalLM(nn.Module):
                 new.weight.data[:min(n, old.out_features)] = old.weight.data[:min(n, old.out_features)]
                 model.lm_head = new
                 model.vocab_size = n
-        ckpt_path = cfg.get("ckpt", "")
+        ckpt_path = cfg.get("ckpt", "")                                   # st_llm.py:188-201
         if ckpt_path:
-            ckpt = cls.get_state_dict(ckpt_path)
-            for key in list(ckpt.keys()):                                 # st_llm.py:196-200
+            if os.path.isdir(ckpt_path):
+                ckpt = cls.get_state_dict(ckpt_path)                      # sharded pytorch_model-N-of-M.bin
+            else:
+                ckpt = torch.load(ckpt_path, map_location="cpu")          # a single MiniGPT-4 / BLIP-2 style file
+            if "model" in ckpt:
+                ckpt = ckpt["model"]
+            for key in list(ckpt.keys()):                                 # :197-199 (the released files say llm_proj)
                 if "llm_proj" in key:
                     ckpt[key.replace("llm_proj", "llama_proj")] = ckpt.pop(key)
             model.load_state_dict(ckpt, strict=False)

@@ -104,3 +104,47 @@ def test_encode_img_asserts_like_reference():
     sm = model.model.stllm_model
     with pytest.raises(AssertionError):   # eva_vit.py:201-202 image-size assert (raised before any kernel launch)
         sm.visual_encoder(torch.zeros(1, 3, 64, 64))
+
+
+def test_from_config_loads_hf_shards_and_stllm_checkpoint(tmp_path):
+    """st_llm.py:149-203: `llama_model` = HF directory (config.json + pytorch_model-N-of-M.bin shards), `ckpt` = a
+    directory of shards or a single file, optionally wrapped in {'model': ...}, with the llm_proj -> llama_proj rename"""
+    import json as _json
+    from stllm_b200.qformer import BertConfig
+    from stllm_b200.st_llm import STLLMForCausalLM
+    from tests.flow_fixture import FLOW, flow_tokenizers
+    btok, ltok = flow_tokenizers()
+    hf_dir = tmp_path / "vicuna"
+    hf_dir.mkdir()
+    hf_cfg = dict(vocab_size=FLOW["vocab"], hidden_size=256, intermediate_size=512, num_hidden_layers=2,
+                  num_attention_heads=2, max_position_embeddings=2048, rms_norm_eps=1e-6)
+    (hf_dir / "config.json").write_text(_json.dumps(hf_cfg))
+    g = torch.Generator().manual_seed(5)
+    shard1 = {"model.layers.0.self_attn.q_proj.weight": torch.randn(256, 256, generator=g),
+              "model.embed_tokens.weight": torch.randn(FLOW["vocab"], 256, generator=g)}
+    shard2 = {"model.layers.1.mlp.down_proj.weight": torch.randn(256, 512, generator=g),
+              "lm_head.weight": torch.randn(FLOW["vocab"], 256, generator=g)}
+    torch.save(shard1, hf_dir / "pytorch_model-00001-of-00002.bin")
+    torch.save(shard2, hf_dir / "pytorch_model-00002-of-00002.bin")
+    ck = {"model": {"model.stllm_model.llm_proj.weight": torch.randn(256, 768, generator=g),
+                    "model.stllm_model.llm_proj.bias": torch.randn(256, generator=g),
+                    "model.stllm_model.query_tokens": torch.randn(1, 32, 768, generator=g)}}
+    ck_file = tmp_path / "stllm_ckpt.pth"
+    torch.save(ck, ck_file)
+    cfg = dict(llama_model=str(hf_dir), ckpt=str(ck_file), vit_depth=1, video_input="all", llama_hidden=256,
+               qformer_config=BertConfig(num_hidden_layers=2, vocab_size=FLOW["bert_vocab"]), tokenizer=btok,
+               llama_tokenizer=ltok)
+    model = STLLMForCausalLM.from_config(cfg)
+    assert model.config.hidden_size == 256 and len(model.model.layers) == 2
+    sd = model.state_dict()
+    for k, v in {**shard1, **shard2}.items():
+        assert torch.equal(sd[k].float(), v), k
+    assert torch.equal(sd["model.stllm_model.llama_proj.weight"].float(), ck["model"]["model.stllm_model.llm_proj.weight"])
+    assert torch.equal(sd["model.stllm_model.query_tokens"].float(), ck["model"]["model.stllm_model.query_tokens"])
+    # the same checkpoint as a directory of shards (the layout the released ST-LLM weights use)
+    ck_dir = tmp_path / "stllm_ckpt_dir"
+    ck_dir.mkdir()
+    torch.save(ck["model"], ck_dir / "pytorch_model-00001-of-00001.bin")
+    model2 = STLLMForCausalLM.from_config(dict(cfg, ckpt=str(ck_dir)))
+    assert torch.equal(model2.state_dict()["model.stllm_model.llama_proj.bias"].float(),
+                       ck["model"]["model.stllm_model.llm_proj.bias"])
