@@ -174,6 +174,45 @@ int stllm_cosine_loss_f16(const void* a, long long lda, const void* b, long long
 int stllm_cross_entropy_f16(const void* logits, long long ldl, const long long* labels, int rows, int V,
                             long long ignore_index, float* out_sum_count, void* stream);
 
+/* ---- Single-token decode step (HF generate() as called at conversation.py:231-243,
+ * mvbench_conversation.py:114-125).  R <= 8 rows (beams) per step: the step is bound by streaming the weights from
+ * HBM once per token, so these are byte-moving kernels (16-byte streaming loads, fp32 accumulate), not 128-row MMA
+ * tiles. ---- */
+
+/* y[R,N] = epi(norm(x)[R,K] * W[N,K]^T) (+ residual[R,N_out]); R <= 8, K % 32 == 0 (else STLLM_ERR_UNSUPPORTED).
+ * norm_mode 0: none.  1: RMSNorm folded into W (W = gamma (.) W as packed for stllm_gemm_norm_f16): y = rstd_r * (x W^T),
+ * rstd_r = rsqrt(mean(x_r^2) + eps) computed in the prologue.  2: explicit RMSNorm, x' = norm_weight (.) fp16(x rstd)
+ * (modeling_llama_mem.py:61-78), then x' W^T.  epilogue: STLLM_EPI_NONE or STLLM_EPI_SWIGLU (N/2 outputs).
+ * y may alias residual (each element is read before it is written); y must not alias x.
+ * Replaces the q/k/v/o, gate/up/down and lm_head nn.Linear calls of a cached decode step
+ * (modeling_llama_mem.py:139-143,160-163; st_llm.py:108,122). */
+int stllm_decode_linear_f16(const void* x, long long ldx, const void* W, long long ldw, void* y, long long ldy, int R,
+                            int N, int K, int norm_mode, const void* norm_weight, float norm_eps,
+                            const void* residual, long long ldr, int epilogue, void* stream);
+
+/* One new token per beam.  qkv [R, 3*H*D] (row stride ldq): rotate-half RoPE at position prefix_len + *n_gen on q (in
+ * place) and on k; the roped k and v are stored in the suffix caches k_suffix / v_suffix [rows][l_max][H*D] (strides in
+ * elements) at (row r, token *n_gen), and src[r*src_ld + *n_gen] = r records where beam r's new token lives.
+ * n_gen is a DEVICE scalar (tokens generated before this step) so that a captured CUDA graph can be replayed.
+ * modeling_llama_mem.py:81-127 (RoPE), 205-217 (cache append). */
+int stllm_decode_rope_append_f16(void* qkv, long long ldq, const float* cos_t, const float* sin_t, int max_pos,
+                                 int prefix_len, const int* n_gen, void* k_suffix, void* v_suffix,
+                                 long long s_beam_stride, long long s_tok_stride, int l_max, int* src, int src_ld, int R,
+                                 int H, int D, void* stream);
+
+/* out[r, h*D + :] = softmax(scale q_r K^T) V over the keys [prompt (prefix_len, ONE copy shared by all beams; optional
+ * uint8 key mask, 0 = padded) || generated tokens 0 .. *n_gen of beam r], the generated ones read through the ancestry
+ * table: token j of beam r is row src[r*src_ld + j] of the suffix caches (a beam re-ordering permutes rows of `src`;
+ * HF _reorder_cache copies the whole cache).  D = 128.  The keys are split n_split ways (grid = H x n_split) and merged
+ * by a second kernel; workspace: stllm_decode_attention_workspace_bytes(H, n_split) bytes, 16-byte aligned.
+ * modeling_llama_mem.py:205-244 with q_len = 1. */
+long long stllm_decode_attention_workspace_bytes(int H, int n_split);
+int stllm_decode_attention_f16(const void* q, long long ldq, const void* k_prefix, const void* v_prefix,
+                               long long p_stride, const void* prefix_mask, int prefix_len, const void* k_suffix,
+                               const void* v_suffix, long long s_beam_stride, long long s_tok_stride, int l_max,
+                               const int* src, int src_ld, const int* n_gen, void* out, long long ldo, void* workspace,
+                               long long workspace_bytes, int R, int H, int D, int n_split, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,6 +46,14 @@ SIGNATURES = {
     "stllm_bt_branch_to_vit_avg_f16": [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "stllm_cosine_loss_f16": [c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p],
     "stllm_cross_entropy_f16": [c_void_p, c_ll, c_void_p, c_int, c_int, c_ll, c_void_p, c_void_p],
+    "stllm_decode_linear_f16": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_void_p,
+                                c_float, c_void_p, c_ll, c_int, c_void_p],
+    "stllm_decode_rope_append_f16": [c_void_p, c_ll, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                     c_ll, c_ll, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
+    "stllm_decode_attention_workspace_bytes": [c_int, c_int],
+    "stllm_decode_attention_f16": [c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_void_p, c_int, c_void_p, c_void_p, c_ll,
+                                   c_ll, c_int, c_void_p, c_int, c_void_p, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int,
+                                   c_int, c_int, c_float, c_void_p],
 }
 
 
@@ -71,6 +79,7 @@ def load():
         fn.argtypes = argtypes
         fn.restype = c_int
     lib.stllm_gemm_workspace_bytes.restype = c_ll
+    lib.stllm_decode_attention_workspace_bytes.restype = c_ll
     lib.stllm_last_error.argtypes = []
     lib.stllm_last_error.restype = ctypes.c_char_p
     _lib = lib

@@ -1,0 +1,641 @@
+// Single-token decode step of the Llama decoder for sm_100a (the `generate` loop every harness of the
+// reference runs after the prefill: conversation.py:231-243, mvbench_conversation.py:114-125).
+//
+// A decode step multiplies R <= 8 activation rows (R = beams) with every weight matrix once: the step is bound by
+// STREAMING THE WEIGHTS FROM HBM (13.5 GB per token for Vicuna-7B), not by the tensor pipe.  The kernels here are
+// therefore byte movers: 16-byte streaming loads with many bytes in flight per SM, fp32 accumulation, no reshaping into
+// 128-row MMA tiles.
+//
+//   decode_linear_kernel      y[R,N] = epi(norm(x)[R,K] * W[N,K]^T) (+ residual)      modeling_llama_mem.py:61-78 (RMSNorm),
+//                             160-163 (q/k/v/o), 139-143 (gate/up/down, SiLU);          st_llm.py:108,122 (lm_head)
+//       persistent CTAs of 16 warps; a CTA owns 16 weight rows at a time, its warps split K (interleaved 32-element
+//       steps -> adjacent warps read adjacent 64-byte pieces of the same rows); the products run on mma.sync m16n8k16 with
+//       the ACTIVATIONS as the 16-row operand (rows >= R unused) and 8 weight rows as the n operand, so one lane loads 16
+//       contiguous bytes of a weight row and feeds two MMAs (the k permutation inside a step is the same for both
+//       operands).  The RMSNorm in front of the Linear is part of the prologue: either explicit (w (.) fp16(x rstd), the
+//       reference's rounding) or folded (the packed weights already carry the norm weight; the result is scaled by rstd).
+//   decode_rope_append_kernel RoPE on q (in place) and k, k/v of the new token appended to the per-beam suffix cache
+//                                                                                      modeling_llama_mem.py:81-127,205-217
+//   decode_attention_kernel   softmax(scale q K^T) V for one query token per beam over [shared prompt KV || per-beam
+//       generated KV]; the prompt's K/V is ONE copy read once for all beams (HF 4.28 prefills and re-reads num_beams
+//       copies); generated K/V is addressed through an ancestry table src[beam][j] so a beam re-ordering permutes a few
+//       ints instead of copying the cache (HF _reorder_cache index_selects all of it).  Split over keys (grid = heads x
+//       splits), merged by decode_attention_combine_kernel.                              modeling_llama_mem.py:205-244
+#include "common.cuh"
+
+namespace {
+
+constexpr int DL_THREADS = 512;
+constexpr int DL_WARPS = DL_THREADS / 32;
+constexpr int DL_RMAX = 8;
+constexpr int DL_UNROLL = 4;
+
+struct DecLinParams {
+  const __half* x;
+  long long ldx;
+  const __half* W;
+  long long ldw;
+  __half* y;
+  long long ldy;
+  const __half* residual;
+  long long ldr;
+  const __half* norm_w;
+  int R, N, K, Kp;   // Kp: row stride (halves) of the staged activations; (2 Kp) % 128 == 64 -> conflict-free LDS.128
+  int norm_mode;     // 0 none | 1 folded RMSNorm (result * rstd) | 2 explicit RMSNorm (norm_w (.) fp16(x rstd))
+  int epi;           // 0 none | 2 SwiGLU (rows interleaved gate_j, up_j; N/2 outputs)
+  float eps;
+  int prefetch;
+};
+
+DEVI void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+// weights are read exactly once per token and are far larger than L2: streaming (evict-first) loads
+DEVI uint4 ld_stream(const __half* p) {
+  uint4 v;
+  asm volatile("ld.global.cs.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+DEVI void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+DEVI float dec_silu(float x) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.44269504088896340736f * x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return x * r;   // same arithmetic as the SwiGLU epilogue of the prefill GEMM (gemm_tcgen05.cu: silu)
+}
+
+__global__ void __launch_bounds__(DL_THREADS, 2) decode_linear_kernel(const DecLinParams p) {
+  extern __shared__ __align__(16) uint8_t dl_smem[];
+  __half* xs = reinterpret_cast<__half*>(dl_smem);                                   // [R][Kp]
+  float* part = reinterpret_cast<float*>(dl_smem + (size_t)p.R * p.Kp * 2);          // [2][16 warps][8 x 16]
+  float* ssq_s = part + 2 * DL_WARPS * 128;                                          // [16]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
+  const int nblk = (p.N + 15) >> 4;
+  const int nsteps = p.K >> 5;
+  pdl_launch_dependents();
+  // The weights do not depend on the previous kernel: start pulling this CTA's first 16 rows into L2 while the
+  // predecessor drains and the activations are staged.
+  if (p.prefetch && (int)blockIdx.x < nblk) {
+    const int sectors_per_row = p.K >> 4;   // 32-byte sectors
+    const int total = 16 * sectors_per_row;
+    const int n0 = (int)blockIdx.x << 4;
+    for (int i = tid; i < total; i += DL_THREADS) {
+      const int r = i / sectors_per_row, s = i - r * sectors_per_row;
+      if (n0 + r < p.N) prefetch_l2(p.W + (long long)(n0 + r) * p.ldw + (s << 4));
+    }
+  }
+  pdl_wait();
+  // ---- stage the activations (and their row statistics): warp w -> row w & 7, half (w >> 3) of the row ----
+  {
+    const int r = warp & 7, hh = warp >> 3;
+    const int nvec = p.K >> 3;
+    const int v0 = hh ? (nvec >> 1) : 0, v1 = hh ? nvec : (nvec >> 1);
+    float sq = 0.f;
+    if (r < p.R) {
+      const uint4* src = reinterpret_cast<const uint4*>(p.x + (long long)r * p.ldx);
+      uint4* dst = reinterpret_cast<uint4*>(xs + (size_t)r * p.Kp);
+      for (int v = v0 + lane; v < v1; v += 32) {
+        const uint4 u = src[v];
+        dst[v] = u;
+        const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = __half22float2(h[j]);
+          sq += f.x * f.x + f.y * f.y;
+        }
+      }
+    }
+    sq = warp_sum(sq);
+    if (lane == 0) ssq_s[warp] = sq;
+    __syncthreads();
+    if (p.norm_mode == 2) {
+      if (r < p.R) {
+        const float rstd = rsqrtf((ssq_s[r] + ssq_s[r + 8]) / (float)p.K + p.eps);
+        uint4* dst = reinterpret_cast<uint4*>(xs + (size_t)r * p.Kp);
+        const uint4* wsrc = reinterpret_cast<const uint4*>(p.norm_w);
+        for (int v = v0 + lane; v < v1; v += 32) {
+          uint4 u = dst[v];
+          const uint4 wv = __ldg(wsrc + v);
+          __half2* h = reinterpret_cast<__half2*>(&u);
+          const __half2* wh = reinterpret_cast<const __half2*>(&wv);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 f = __half22float2(h[j]);
+            h[j] = __hmul2(wh[j], __floats2half2_rn(f.x * rstd, f.y * rstd));   // rounding of norm.cu / the reference
+          }
+          dst[v] = u;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  const __half* xr = xs + (size_t)(g < p.R ? g : 0) * p.Kp + 8 * t;
+  int it = 0;
+  for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x, ++it) {
+    const int n0 = blk << 4;
+    const int rowA = n0 + g, rowB = n0 + 8 + g;
+    const __half* wA = p.W + (long long)(rowA < p.N ? rowA : 0) * p.ldw + 8 * t;
+    const __half* wB = p.W + (long long)(rowB < p.N ? rowB : 0) * p.ldw + 8 * t;
+    float accA[4] = {0.f, 0.f, 0.f, 0.f}, accB[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int s0 = warp; s0 < nsteps; s0 += DL_WARPS * DL_UNROLL) {
+      uint4 wa[DL_UNROLL], wb[DL_UNROLL];
+#pragma unroll
+      for (int u = 0; u < DL_UNROLL; ++u) {
+        const int s = s0 + u * DL_WARPS;
+        if (s < nsteps) {
+          wa[u] = ld_stream(wA + (s << 5));
+          wb[u] = ld_stream(wB + (s << 5));
+        } else {
+          wa[u] = make_uint4(0u, 0u, 0u, 0u);
+          wb[u] = make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < DL_UNROLL; ++u) {
+        const int s = s0 + u * DL_WARPS;
+        const uint4 xa = *reinterpret_cast<const uint4*>(xr + ((s < nsteps ? s : 0) << 5));
+        mma16816(accA, xa.x, 0u, xa.y, 0u, wa[u].x, wa[u].y);
+        mma16816(accA, xa.z, 0u, xa.w, 0u, wa[u].z, wa[u].w);
+        mma16816(accB, xa.x, 0u, xa.y, 0u, wb[u].x, wb[u].y);
+        mma16816(accB, xa.z, 0u, xa.w, 0u, wb[u].z, wb[u].w);
+      }
+    }
+    // D[beam g][weight row]: lane holds rows n0 + 2t, 2t+1 (group A) and n0 + 8 + 2t, 2t+1 (group B) of beam g
+    float* pw = part + ((it & 1) * DL_WARPS + warp) * 128 + g * 16 + 2 * t;
+    *reinterpret_cast<float2*>(pw) = make_float2(accA[0], accA[1]);
+    *reinterpret_cast<float2*>(pw + 8) = make_float2(accB[0], accB[1]);
+    __syncthreads();
+    if (tid < 128) {
+      const int r = tid >> 4, c = tid & 15;
+      const float* pr = part + (it & 1) * DL_WARPS * 128 + tid;
+      float v = 0.f;
+#pragma unroll
+      for (int w = 0; w < DL_WARPS; ++w) v += pr[w * 128];
+      if (p.norm_mode == 1) v *= rsqrtf((ssq_s[r] + ssq_s[r + 8]) / (float)p.K + p.eps);
+      const int n = n0 + c;
+      if (p.epi == 2) {
+        const float up = __shfl_down_sync(0xffffffffu, v, 1);
+        if (!(c & 1) && r < p.R && n + 1 < p.N) {
+          float o = dec_silu(v) * up;
+          const int oc = n >> 1;
+          if (p.residual) o += __half2float(p.residual[(long long)r * p.ldr + oc]);
+          p.y[(long long)r * p.ldy + oc] = __float2half_rn(o);
+        }
+      } else if (r < p.R && n < p.N) {
+        if (p.residual) v += __half2float(p.residual[(long long)r * p.ldr + n]);
+        p.y[(long long)r * p.ldy + n] = __float2half_rn(v);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+struct DecRopeParams {
+  __half* qkv;
+  long long ldq;       // row = [q | k | v], each H*D
+  const float* cos_t;
+  const float* sin_t;
+  const int* n_gen;    // device scalar: tokens generated before this step
+  __half* ks;
+  __half* vs;
+  long long s_beam_stride, s_tok_stride;
+  int* src;
+  int src_ld;
+  int prefix_len, max_pos, l_max, R, H, D;
+};
+
+__global__ void decode_rope_append_kernel(const DecRopeParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int j_suf = *p.n_gen;
+  const int pos = p.prefix_len + j_suf;
+  if (j_suf >= p.l_max || pos >= p.max_pos) return;   // the host never launches past the capacity
+  const int half_d = p.D >> 1, groups = half_d >> 3;
+  const int total = p.R * p.H * groups;
+  const long long HD = (long long)p.H * p.D;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int j = (i % groups) * 8;
+    const int rh = i / groups;
+    const int h = rh % p.H, r = rh / p.H;
+    if (h == 0 && j == 0) p.src[r * p.src_ld + j_suf] = r;   // the new token of beam r lives in physical row r
+    const float4* cp = reinterpret_cast<const float4*>(p.cos_t + (long long)pos * half_d + j);
+    const float4* sp = reinterpret_cast<const float4*>(p.sin_t + (long long)pos * half_d + j);
+    const float4 c0 = __ldg(cp), c1 = __ldg(cp + 1), s0 = __ldg(sp), s1 = __ldg(sp + 1);
+    const float c[8] = {c0.x, c0.y, c0.z, c0.w, c1.x, c1.y, c1.z, c1.w};
+    const float sn[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+    __half* row = p.qkv + (long long)r * p.ldq + (long long)h * p.D;
+    const long long cache_off = (long long)r * p.s_beam_stride + (long long)j_suf * p.s_tok_stride + (long long)h * p.D;
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {   // 0: q (in place), 1: k (-> cache)
+      __half* base = row + which * HD;
+      const uint4 ulo = *reinterpret_cast<const uint4*>(base + j);
+      const uint4 uhi = *reinterpret_cast<const uint4*>(base + j + half_d);
+      const __half2* hlo = reinterpret_cast<const __half2*>(&ulo);
+      const __half2* hhi = reinterpret_cast<const __half2*>(&uhi);
+      uint4 olo, ohi;
+      uint32_t* plo = reinterpret_cast<uint32_t*>(&olo);
+      uint32_t* phi = reinterpret_cast<uint32_t*>(&ohi);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {   // same arithmetic as rope_kernel (elementwise.cu)
+        const float2 lo = __half22float2(hlo[q]);
+        const float2 hi = __half22float2(hhi[q]);
+        plo[q] = pack_half2(lo.x * c[2 * q] - hi.x * sn[2 * q], lo.y * c[2 * q + 1] - hi.y * sn[2 * q + 1]);
+        phi[q] = pack_half2(hi.x * c[2 * q] + lo.x * sn[2 * q], hi.y * c[2 * q + 1] + lo.y * sn[2 * q + 1]);
+      }
+      __half* dst = which == 0 ? base : p.ks + cache_off;
+      *reinterpret_cast<uint4*>(dst + j) = olo;
+      *reinterpret_cast<uint4*>(dst + j + half_d) = ohi;
+    }
+    const __half* vsrc = row + 2 * HD;
+    __half* vdst = p.vs + cache_off;
+    *reinterpret_cast<uint4*>(vdst + j) = *reinterpret_cast<const uint4*>(vsrc + j);
+    *reinterpret_cast<uint4*>(vdst + j + half_d) = *reinterpret_cast<const uint4*>(vsrc + j + half_d);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int DA_THREADS = 512;
+constexpr int DA_WARPS = DA_THREADS / 32;
+constexpr int DA_D = 128;        // head dim (Vicuna / Llama: 4096 / 32)
+constexpr int DA_WS_ROW = 132;   // floats per (head, split, beam) in the workspace: o[128], m, l, pad
+
+struct DecAttnParams {
+  const __half* q;
+  long long ldq;
+  const __half* kp;
+  const __half* vp;
+  long long p_stride;
+  const uint8_t* p_mask;
+  const __half* ks;
+  const __half* vs;
+  long long s_beam_stride, s_tok_stride;
+  const int* src;
+  int src_ld;
+  const int* n_gen;
+  float* ws;
+  int R, H, Sp, NS, cap;
+  float scale;
+};
+
+DEVI void half8_to_float(const uint4& u, float (&f)[8]) {
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 v = __half22float2(h[j]);
+    f[2 * j] = v.x;
+    f[2 * j + 1] = v.y;
+  }
+}
+DEVI float sum16(float v) {   // over the 16 lanes of a half-warp
+  v += __shfl_xor_sync(0xffffffffu, v, 8);
+  v += __shfl_xor_sync(0xffffffffu, v, 4);
+  v += __shfl_xor_sync(0xffffffffu, v, 2);
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v;
+}
+
+__global__ void __launch_bounds__(DA_THREADS, 1) decode_attention_kernel(const DecAttnParams p) {
+  extern __shared__ __align__(16) uint8_t da_smem[];
+  float* sc = reinterpret_cast<float*>(da_smem);            // [8][cap] scores, then probabilities
+  float* red = sc + (size_t)DL_RMAX * p.cap;                // [16 warps][R][128]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, hw = lane >> 4, c = lane & 15;
+  const int h = blockIdx.x, sp = blockIdx.y;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int n_suf = *p.n_gen + 1;   // the token appended by this step is a key too
+  const int pk0 = (int)((long long)p.Sp * sp / p.NS), pk1 = (int)((long long)p.Sp * (sp + 1) / p.NS);
+  const int sk0 = (int)((long long)n_suf * sp / p.NS), sk1 = (int)((long long)n_suf * (sp + 1) / p.NS);
+  const int np = pk1 - pk0, ns = sk1 - sk0, ntot = np + ns;
+  const long long hoff = (long long)h * DA_D + 8 * c;
+  constexpr int U = 4;
+  constexpr float NEG_INF = -INFINITY;
+
+  // ---- scores: half-warp per key, lane = 16-byte chunk of the head dim ----
+  {
+    float qf[DL_RMAX][8];
+#pragma unroll
+    for (int r = 0; r < DL_RMAX; ++r) {
+      uint4 u = make_uint4(0u, 0u, 0u, 0u);
+      if (r < p.R) u = *reinterpret_cast<const uint4*>(p.q + (long long)r * p.ldq + hoff);
+      half8_to_float(u, qf[r]);
+    }
+    for (int b0 = 2 * warp; b0 < np; b0 += 2 * DA_WARPS * U) {   // warp-uniform trip count (shuffles inside)
+      const int i0 = b0 + hw;
+      uint4 kv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + 2 * DA_WARPS * u;
+        kv[u] = i < np ? __ldg(reinterpret_cast<const uint4*>(p.kp + (long long)(pk0 + i) * p.p_stride + hoff))
+                       : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + 2 * DA_WARPS * u;
+        float kf[8];
+        half8_to_float(kv[u], kf);
+        const bool masked = p.p_mask != nullptr && i < np && p.p_mask[pk0 + i] == 0;
+#pragma unroll
+        for (int r = 0; r < DL_RMAX; ++r) {
+          float d = 0.f;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) d = fmaf(qf[r][e], kf[e], d);
+          d = sum16(d);
+          if (c == 0 && i < np && r < p.R) sc[r * p.cap + i] = masked ? NEG_INF : d * p.scale;
+        }
+      }
+    }
+    // generated keys: per beam, through the ancestry table
+#pragma unroll
+    for (int r = 0; r < DL_RMAX; ++r) {
+      if (r < p.R) {
+        for (int c0 = sk0 + 2 * warp; c0 < sk1; c0 += 2 * DA_WARPS * U) {
+          const int j0 = c0 + hw;
+          uint4 kv[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int j = j0 + 2 * DA_WARPS * u;
+            kv[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (j < sk1) {
+              const int pr = p.src[r * p.src_ld + j];
+              kv[u] = *reinterpret_cast<const uint4*>(p.ks + (long long)pr * p.s_beam_stride +
+                                                      (long long)j * p.s_tok_stride + hoff);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int j = j0 + 2 * DA_WARPS * u;
+            float kf[8];
+            half8_to_float(kv[u], kf);
+            float d = 0.f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) d = fmaf(qf[r][e], kf[e], d);
+            d = sum16(d);
+            if (c == 0 && j < sk1) sc[r * p.cap + np + (j - sk0)] = d * p.scale;
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- fp32 softmax of this split: warp r -> beam r ----
+  float* wsb = p.ws + ((size_t)(h * p.NS + sp) * DL_RMAX) * DA_WS_ROW;
+  if (warp < p.R) {
+    float* s = sc + warp * p.cap;
+    float m = NEG_INF;
+    for (int i = lane; i < ntot; i += 32) m = fmaxf(m, s[i]);
+    m = warp_max(m);
+    float l = 0.f;
+    for (int i = lane; i < ntot; i += 32) {
+      const float e = (m == NEG_INF) ? 0.f : __expf(s[i] - m);
+      s[i] = e;
+      l += e;
+    }
+    l = warp_sum(l);
+    if (lane == 0) {
+      wsb[warp * DA_WS_ROW + 128] = m;
+      wsb[warp * DA_WS_ROW + 129] = l;
+    }
+  }
+  __syncthreads();
+  // ---- o = P V (unnormalised) ----
+  {
+    float acc[DL_RMAX][8];
+#pragma unroll
+    for (int r = 0; r < DL_RMAX; ++r)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[r][e] = 0.f;
+    for (int b0 = 2 * warp; b0 < np; b0 += 2 * DA_WARPS * U) {   // warp-uniform trip count (shuffles inside)
+      const int i0 = b0 + hw;
+      uint4 vv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + 2 * DA_WARPS * u;
+        vv[u] = i < np ? __ldg(reinterpret_cast<const uint4*>(p.vp + (long long)(pk0 + i) * p.p_stride + hoff))
+                       : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = i0 + 2 * DA_WARPS * u;
+        if (i < np) {
+          float vf[8];
+          half8_to_float(vv[u], vf);
+#pragma unroll
+          for (int r = 0; r < DL_RMAX; ++r) {
+            if (r < p.R) {
+              const float pr = sc[r * p.cap + i];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) acc[r][e] = fmaf(pr, vf[e], acc[r][e]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < DL_RMAX; ++r) {
+      if (r < p.R) {
+        for (int c0 = sk0 + 2 * warp; c0 < sk1; c0 += 2 * DA_WARPS * U) {
+          const int j0 = c0 + hw;
+          uint4 vv[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int j = j0 + 2 * DA_WARPS * u;
+            vv[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (j < sk1) {
+              const int pr = p.src[r * p.src_ld + j];
+              vv[u] = *reinterpret_cast<const uint4*>(p.vs + (long long)pr * p.s_beam_stride +
+                                                      (long long)j * p.s_tok_stride + hoff);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int j = j0 + 2 * DA_WARPS * u;
+            if (j < sk1) {
+              float vf[8];
+              half8_to_float(vv[u], vf);
+              const float pr = sc[r * p.cap + np + (j - sk0)];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) acc[r][e] = fmaf(pr, vf[e], acc[r][e]);
+            }
+          }
+        }
+      }
+    }
+    // the two half-warps of a warp hold different keys: fold them, then one partial per warp
+#pragma unroll
+    for (int r = 0; r < DL_RMAX; ++r) {
+      if (r < p.R) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[r][e] += __shfl_xor_sync(0xffffffffu, acc[r][e], 16);
+        if (hw == 0) {
+          float* dst = red + ((size_t)warp * p.R + r) * DA_D + 8 * c;
+          *reinterpret_cast<float4*>(dst) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+          *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < p.R * DA_D; idx += DA_THREADS) {
+    const int r = idx >> 7, d = idx & 127;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < DA_WARPS; ++w) s += red[((size_t)w * p.R + r) * DA_D + d];
+    wsb[r * DA_WS_ROW + d] = s;
+  }
+}
+
+// out[r, h*128 + d] = sum_s o_s[d] e^(m_s - M) / sum_s l_s e^(m_s - M)
+__global__ void __launch_bounds__(DA_D) decode_attention_combine_kernel(const float* __restrict__ ws, __half* out,
+                                                                        long long ldo, int NS) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int h = blockIdx.x, r = blockIdx.y, d = threadIdx.x;
+  const float* base = ws + ((size_t)h * NS * DL_RMAX + r) * DA_WS_ROW;
+  const size_t split_stride = (size_t)DL_RMAX * DA_WS_ROW;
+  float M = -INFINITY;
+  for (int s = 0; s < NS; ++s) M = fmaxf(M, base[s * split_stride + 128]);
+  float L = 0.f, o = 0.f;
+  if (M != -INFINITY) {
+    for (int s = 0; s < NS; ++s) {
+      const float w = __expf(base[s * split_stride + 128] - M);
+      L = fmaf(base[s * split_stride + 129], w, L);
+      o = fmaf(base[s * split_stride + d], w, o);
+    }
+  }
+  out[(long long)r * ldo + (long long)h * DA_D + d] = __float2half_rn(L > 0.f ? o / L : 0.f);
+}
+
+int env_int_dec(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+int num_sms_dec() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
+constexpr int DL_SMEM_MAX = 220 * 1024;
+constexpr int DA_SMEM_MAX = 200 * 1024;
+
+}  // namespace
+
+extern "C" int stllm_decode_linear_f16(const void* x, long long ldx, const void* W, long long ldw, void* y,
+                                       long long ldy, int R, int N, int K, int norm_mode, const void* norm_weight,
+                                       float norm_eps, const void* residual, long long ldr, int epilogue,
+                                       void* stream) {
+  STLLM_CHECK_ARG(x && W && y && R >= 1 && R <= DL_RMAX && N >= 1 && K >= 32);
+  STLLM_CHECK_ARG(norm_mode >= 0 && norm_mode <= 2 && (norm_mode != 2 || norm_weight != nullptr));
+  STLLM_CHECK_ARG(epilogue == 0 || epilogue == 2);
+  STLLM_CHECK_ARG(epilogue != 2 || N % 2 == 0);
+  STLLM_CHECK_ARG(ldx % 8 == 0 && ldw % 8 == 0 && ldx >= K && ldw >= K);
+  STLLM_CHECK_ARG((((uintptr_t)x | (uintptr_t)W | (uintptr_t)norm_weight) & 15) == 0);
+  if (K % 32 != 0) {
+    stllm_set_last_error("stllm_decode_linear_f16: K=%d is not a multiple of 32", K);
+    return STLLM_ERR_UNSUPPORTED;
+  }
+  DecLinParams p;
+  p.x = (const __half*)x; p.ldx = ldx;
+  p.W = (const __half*)W; p.ldw = ldw;
+  p.y = (__half*)y; p.ldy = ldy;
+  p.residual = (const __half*)residual; p.ldr = ldr;
+  p.norm_w = (const __half*)norm_weight;
+  p.R = R; p.N = N; p.K = K;
+  p.Kp = K + (((K * 2) % 128 == 64) ? 0 : 32);
+  p.norm_mode = norm_mode; p.epi = epilogue; p.eps = norm_eps;
+  static const int prefetch = env_int_dec("STLLM_DECODE_PREFETCH", 1);
+  p.prefetch = prefetch;
+  const size_t smem = (size_t)R * p.Kp * 2 + (size_t)(2 * DL_WARPS * 128 + 16) * sizeof(float);
+  if (smem > (size_t)DL_SMEM_MAX) {
+    stllm_set_last_error("stllm_decode_linear_f16: R=%d x K=%d activations do not fit in shared memory", R, K);
+    return STLLM_ERR_UNSUPPORTED;
+  }
+  static bool configured = false;
+  if (!configured) {
+    STLLM_CHECK_CUDA(cudaFuncSetAttribute(decode_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DL_SMEM_MAX));
+    configured = true;
+  }
+  const int nblk = (N + 15) / 16;
+  const int per_sm = (int)((size_t)(226 * 1024) / (smem + 1024)) >= 2 ? 2 : 1;
+  int grid = num_sms_dec() * per_sm;
+  if (grid > nblk) grid = nblk;
+  STLLM_CHECK_CUDA(stllm_launch(decode_linear_kernel, dim3(grid), dim3(DL_THREADS), smem, (cudaStream_t)stream, p));
+  return STLLM_OK;
+}
+
+extern "C" int stllm_decode_rope_append_f16(void* qkv, long long ldq, const float* cos_t, const float* sin_t,
+                                            int max_pos, int prefix_len, const int* n_gen, void* k_suffix,
+                                            void* v_suffix, long long s_beam_stride, long long s_tok_stride, int l_max,
+                                            int* src, int src_ld, int R, int H, int D, void* stream) {
+  STLLM_CHECK_ARG(qkv && cos_t && sin_t && n_gen && k_suffix && v_suffix && src);
+  STLLM_CHECK_ARG(R >= 1 && R <= DL_RMAX && H >= 1 && D % 16 == 0 && ldq >= 3LL * H * D && ldq % 8 == 0);
+  STLLM_CHECK_ARG(s_beam_stride % 8 == 0 && s_tok_stride % 8 == 0 && s_tok_stride >= (long long)H * D && src_ld >= l_max);
+  STLLM_CHECK_ARG((((uintptr_t)qkv | (uintptr_t)k_suffix | (uintptr_t)v_suffix | (uintptr_t)cos_t | (uintptr_t)sin_t) & 15) == 0);
+  DecRopeParams p;
+  p.qkv = (__half*)qkv; p.ldq = ldq; p.cos_t = cos_t; p.sin_t = sin_t; p.n_gen = n_gen;
+  p.ks = (__half*)k_suffix; p.vs = (__half*)v_suffix;
+  p.s_beam_stride = s_beam_stride; p.s_tok_stride = s_tok_stride;
+  p.src = src; p.src_ld = src_ld;
+  p.prefix_len = prefix_len; p.max_pos = max_pos; p.l_max = l_max; p.R = R; p.H = H; p.D = D;
+  const int total = R * H * (D / 16);
+  STLLM_CHECK_CUDA(stllm_launch(decode_rope_append_kernel, dim3((total + 127) / 128), dim3(128), 0, (cudaStream_t)stream, p));
+  return STLLM_OK;
+}
+
+extern "C" long long stllm_decode_attention_workspace_bytes(int H, int n_split) {
+  if (H <= 0 || n_split <= 0) return 0;
+  return (long long)H * n_split * DL_RMAX * DA_WS_ROW * (long long)sizeof(float);
+}
+
+extern "C" int stllm_decode_attention_f16(const void* q, long long ldq, const void* k_prefix, const void* v_prefix,
+                                          long long p_stride, const void* prefix_mask, int prefix_len,
+                                          const void* k_suffix, const void* v_suffix, long long s_beam_stride,
+                                          long long s_tok_stride, int l_max, const int* src, int src_ld,
+                                          const int* n_gen, void* out, long long ldo, void* workspace,
+                                          long long workspace_bytes, int R, int H, int D, int n_split, float scale,
+                                          void* stream) {
+  STLLM_CHECK_ARG(q && k_prefix && v_prefix && k_suffix && v_suffix && src && n_gen && out && workspace);
+  STLLM_CHECK_ARG(R >= 1 && R <= DL_RMAX && H >= 1 && prefix_len >= 0 && l_max >= 1 && n_split >= 1 && n_split <= 64);
+  STLLM_CHECK_ARG(ldq % 8 == 0 && p_stride % 8 == 0 && s_beam_stride % 8 == 0 && s_tok_stride % 8 == 0 && src_ld >= l_max);
+  STLLM_CHECK_ARG((((uintptr_t)q | (uintptr_t)k_prefix | (uintptr_t)v_prefix | (uintptr_t)k_suffix | (uintptr_t)v_suffix) & 15) == 0);
+  STLLM_CHECK_ARG(workspace_bytes >= stllm_decode_attention_workspace_bytes(H, n_split) && ((uintptr_t)workspace & 15) == 0);
+  if (D != DA_D) {
+    stllm_set_last_error("stllm_decode_attention_f16: head dim %d unsupported (128 only)", D);
+    return STLLM_ERR_UNSUPPORTED;
+  }
+  DecAttnParams p;
+  p.q = (const __half*)q; p.ldq = ldq;
+  p.kp = (const __half*)k_prefix; p.vp = (const __half*)v_prefix; p.p_stride = p_stride;
+  p.p_mask = (const uint8_t*)prefix_mask;
+  p.ks = (const __half*)k_suffix; p.vs = (const __half*)v_suffix;
+  p.s_beam_stride = s_beam_stride; p.s_tok_stride = s_tok_stride;
+  p.src = src; p.src_ld = src_ld; p.n_gen = n_gen; p.ws = (float*)workspace;
+  p.R = R; p.H = H; p.Sp = prefix_len; p.NS = n_split;
+  p.cap = (((prefix_len + n_split - 1) / n_split + (l_max + n_split - 1) / n_split + 2) + 3) & ~3;
+  p.scale = scale;
+  const size_t smem = ((size_t)DL_RMAX * p.cap + (size_t)DA_WARPS * R * DA_D) * sizeof(float);
+  if (smem > (size_t)DA_SMEM_MAX) {
+    stllm_set_last_error("stllm_decode_attention_f16: %d + %d keys over %d splits do not fit in shared memory",
+                         prefix_len, l_max, n_split);
+    return STLLM_ERR_UNSUPPORTED;
+  }
+  static bool configured = false;
+  if (!configured) {
+    STLLM_CHECK_CUDA(cudaFuncSetAttribute(decode_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DA_SMEM_MAX));
+    configured = true;
+  }
+  STLLM_CHECK_CUDA(stllm_launch(decode_attention_kernel, dim3(H, n_split), dim3(DA_THREADS), smem, (cudaStream_t)stream, p));
+  STLLM_CHECK_CUDA(stllm_launch(decode_attention_combine_kernel, dim3(H, R), dim3(DA_D), 0, (cudaStream_t)stream,
+                                (const float*)workspace, (__half*)out, ldo, n_split));
+  return STLLM_OK;
+}

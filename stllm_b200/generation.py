@@ -8,8 +8,17 @@ prefills `num_beams` identical rows).  Returns generated toke
 the reference callers strip a leading 0/1 token only if present, conversation.py:245-248).
 Sampling/beam bookkeeping is host-side torch on tiny [beams, vocab] tensors; every model forward runs in the
 sm_100a kernels.
+
+Decode steps: for batch 1 (every reference call site) the steps run on `decode.DecodeEngine` -- the HBM-bound kernels of
+csrc/decode.cu replayed as one CUDA graph per token, prompt K/V shared by the beams, ancestry table instead of cache
+re-ordering.  Other shapes (batch > 1, head dim != 128) take the general kernels through model.forward with a KVCache.
+STLLM_DECODE_ENGINE=0 forces the general route.
 """
+import os
+
 import torch
+
+from . import decode as _decode
 
 
 def _process_logits(logits, generated, cur_len, min_length, eos_ids, repetition_penalty, temperature):
@@ -67,6 +76,11 @@ def generate(model, inputs_embeds=None, input_ids=None, max_new_tokens=20, stopp
     cache = out.past_key_values
     logits = out.logits[:, -1]
     n_steps = max_len - S
+    engine = None
+    n_rows = max(1, num_beams)
+    if B == 1 and n_steps > 1 and inputs_embeds.is_cuda and os.environ.get("STLLM_DECODE_ENGINE", "1") != "0" \
+            and _decode.supported(model, n_rows):
+        engine = _decode.DecodeEngine(model, cache, S, n_rows, n_steps - 1, prefix_mask=attention_mask)
     if num_beams <= 1:
         generated = torch.zeros(B, 0, dtype=torch.long, device=dev)
         finished = torch.zeros(B, dtype=torch.bool, device=dev)
@@ -84,13 +98,17 @@ def generate(model, inputs_embeds=None, input_ids=None, max_new_tokens=20, stopp
                 finished |= nxt == e
             if bool(finished.all()) or _stopped(stopping_criteria, generated, lg) or step + 1 == n_steps:
                 break
-            out = model.forward(input_ids=nxt[:, None], past_key_values=cache, use_cache=True)
-            logits = out.logits[:, -1]
+            if engine is not None:
+                logits = engine.step(nxt)
+            else:
+                out = model.forward(input_ids=nxt[:, None], past_key_values=cache, use_cache=True)
+                logits = out.logits[:, -1]
         return generated
     # ---------------- beam search (batch 1, as every reference call site uses) ----------------
     assert B == 1, "beam search is implemented for batch size 1 (the reference's harnesses generate one clip at a time)"
     nb = num_beams
-    cache.expand_batch(nb)
+    if engine is None:
+        cache.expand_batch(nb)
     logits = logits.expand(nb, -1)
     beam_scores = torch.zeros(nb, device=dev)
     beam_scores[1:] = -1e9
@@ -130,9 +148,13 @@ def generate(model, inputs_embeds=None, input_ids=None, max_new_tokens=20, stopp
         seqs = torch.cat([seqs[idx], tok[:, None]], dim=1)
         if done or _stopped(stopping_criteria, seqs[:1], lg) or step + 1 == n_steps:
             break
-        cache.reorder(idx)
-        out = model.forward(input_ids=tok[:, None], past_key_values=cache, use_cache=True)
-        logits = out.logits[:, -1]
+        if engine is not None:
+            engine.reorder(idx)
+            logits = engine.step(tok)
+        else:
+            cache.reorder(idx)
+            out = model.forward(input_ids=tok[:, None], past_key_values=cache, use_cache=True)
+            logits = out.logits[:, -1]
     if not done:
         for b in range(nb):
             sc = beam_scores[b].item() / (max(seqs.shape[1], 1) ** length_penalty)

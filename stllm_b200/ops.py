@@ -374,3 +374,87 @@ def rope_tables(head_dim, max_pos, base=10000.0, device="cuda"):
     t = torch.arange(max_pos, dtype=torch.float32)
     freqs = torch.outer(t, inv_freq)
     return freqs.cos().contiguous().to(device), freqs.sin().contiguous().to(device)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# single-token decode step (csrc/decode.cu): HBM-bound byte movers for R <= 8 rows (beams)
+# ---------------------------------------------------------------------------------------------------------------------
+DECODE_MAX_ROWS = 8
+
+
+def decode_linear(x, w, out, norm_mode=NORM_NONE, norm_weight=None, norm_eps=0.0, residual=None, epilogue=EPI_NONE):
+    """out[R, N'] = epi(norm(x)[R, K] @ w[N, K].T) (+ residual);  R <= 8.  norm_mode NORM_RMS: `w` carries the norm
+    weight (packed copy), the result is scaled by rstd;  2: explicit RMSNorm with `norm_weight` (reference rounding).
+    out may alias residual."""
+    global launch_count
+    _need_cuda(x, w, out, norm_weight, residual)
+    assert x.dtype == torch.float16 and w.dtype == torch.float16 and out.dtype == torch.float16
+    assert x.dim() == 2 and out.dim() == 2 and x.stride(1) == 1 and out.stride(1) == 1 and w.stride(1) == 1
+    R, K = x.shape
+    N = w.shape[0]
+    n_out = N // 2 if epilogue == EPI_SWIGLU else N
+    assert w.shape[1] == K and out.shape == (R, n_out) and R <= DECODE_MAX_ROWS
+    ldr = 0
+    if residual is not None:
+        assert residual.dtype == torch.float16 and residual.shape == (R, n_out) and residual.stride(1) == 1
+        ldr = residual.stride(0)
+    if norm_mode == 2:
+        assert norm_weight is not None and norm_weight.dtype == torch.float16 and norm_weight.numel() == K
+    rc = _lib.load().stllm_decode_linear_f16(_ptr(x), x.stride(0), _ptr(w), w.stride(0), _ptr(out), out.stride(0), R,
+                                             N, K, norm_mode, _ptr(norm_weight), float(norm_eps), _ptr(residual), ldr,
+                                             epilogue, _stream())
+    _lib.check(rc, "stllm_decode_linear_f16")
+    launch_count += 1
+    return out
+
+
+def decode_rope_append(qkv, cos_t, sin_t, prefix_len, n_gen, k_suffix, v_suffix, src, nheads, head_dim):
+    """RoPE at position prefix_len + n_gen[0] on the q and k parts of qkv [R, 3*H*D] (q in place); roped k and v are
+    appended to the suffix caches [rows, l_max, H*D] at token n_gen[0]; src[r, n_gen[0]] = r."""
+    global launch_count
+    _need_cuda(qkv, cos_t, sin_t, n_gen, k_suffix, v_suffix, src)
+    assert qkv.dim() == 2 and qkv.stride(1) == 1 and qkv.shape[1] == 3 * nheads * head_dim
+    assert n_gen.dtype == torch.int32 and src.dtype == torch.int32 and src.dim() == 2 and src.stride(1) == 1
+    assert k_suffix.dim() == 3 and k_suffix.stride(2) == 1 and k_suffix.shape == v_suffix.shape
+    assert k_suffix.stride() == v_suffix.stride() and k_suffix.shape[2] == nheads * head_dim
+    assert cos_t.dtype == torch.float32 and cos_t.shape[1] == head_dim // 2 and cos_t.is_contiguous()
+    R = qkv.shape[0]
+    assert k_suffix.shape[0] >= R and src.shape[0] >= R and src.shape[1] >= k_suffix.shape[1]
+    rc = _lib.load().stllm_decode_rope_append_f16(_ptr(qkv), qkv.stride(0), _ptr(cos_t), _ptr(sin_t), cos_t.shape[0],
+                                                  int(prefix_len), _ptr(n_gen), _ptr(k_suffix), _ptr(v_suffix),
+                                                  k_suffix.stride(0), k_suffix.stride(1), k_suffix.shape[1], _ptr(src),
+                                                  src.stride(0), R, nheads, head_dim, _stream())
+    _lib.check(rc, "stllm_decode_rope_append_f16")
+    launch_count += 1
+
+
+def decode_attention_workspace(nheads, n_split, device):
+    n = int(_lib.load().stllm_decode_attention_workspace_bytes(nheads, n_split))
+    return torch.empty(n // 4, dtype=torch.float32, device=device)
+
+
+def decode_attention(q, k_prefix, v_prefix, k_suffix, v_suffix, src, n_gen, out, workspace, nheads, head_dim, scale,
+                     n_split=4, prefix_mask=None):
+    """out[r] = softmax(scale q_r K^T) V over [k_prefix (shared by all beams) || generated tokens 0..n_gen[0] of beam r
+    through the ancestry table src].  q: [R, >= H*D] (first H*D columns), k_prefix/v_prefix: [Sp, H*D] (row stride free),
+    k_suffix/v_suffix: [rows, l_max, H*D], out: [R, H*D].  Launches 2 kernels."""
+    global launch_count
+    _need_cuda(q, k_prefix, v_prefix, k_suffix, v_suffix, src, n_gen, out, workspace, prefix_mask)
+    R = q.shape[0]
+    HD = nheads * head_dim
+    assert q.dim() == 2 and q.stride(1) == 1 and q.shape[1] >= HD and out.shape == (R, HD) and out.stride(1) == 1
+    assert k_prefix.dim() == 2 and k_prefix.stride(1) == 1 and k_prefix.shape[1] == HD
+    assert v_prefix.shape == k_prefix.shape and v_prefix.stride() == k_prefix.stride()
+    assert k_suffix.dim() == 3 and k_suffix.stride(2) == 1 and k_suffix.shape[2] == HD
+    assert v_suffix.shape == k_suffix.shape and v_suffix.stride() == k_suffix.stride()
+    assert n_gen.dtype == torch.int32 and src.dtype == torch.int32 and src.stride(1) == 1
+    if prefix_mask is not None:
+        assert prefix_mask.dtype == torch.uint8 and prefix_mask.is_contiguous() and prefix_mask.numel() == k_prefix.shape[0]
+    rc = _lib.load().stllm_decode_attention_f16(
+        _ptr(q), q.stride(0), _ptr(k_prefix), _ptr(v_prefix), k_prefix.stride(0), _ptr(prefix_mask),
+        k_prefix.shape[0], _ptr(k_suffix), _ptr(v_suffix), k_suffix.stride(0), k_suffix.stride(1), k_suffix.shape[1],
+        _ptr(src), src.stride(0), _ptr(n_gen), _ptr(out), out.stride(0), _ptr(workspace),
+        workspace.numel() * workspace.element_size(), R, nheads, head_dim, n_split, float(scale), _stream())
+    _lib.check(rc, "stllm_decode_attention_f16")
+    launch_count += 2
+    return out
