@@ -28,7 +28,6 @@ namespace {
 constexpr int DL_THREADS = 512;
 constexpr int DL_WARPS = DL_THREADS / 32;
 constexpr int DL_RMAX = 8;
-constexpr int DL_UNROLL = 4;
 
 struct DecLinParams {
   const __half* x;
@@ -68,7 +67,10 @@ DEVI float dec_silu(float x) {
   return x * r;   // same arithmetic as the SwiGLU epilogue of the prefill GEMM (gemm_tcgen05.cu: silu)
 }
 
-__global__ void __launch_bounds__(DL_THREADS, 2) decode_linear_kernel(const DecLinParams p) {
+// DL_UNROLL 32-element steps are in flight per warp: 4 with two CTAs per SM (<= 64 registers), 8 when the staged
+// activations leave room for one CTA only (down_proj with several beams)
+template <int DL_UNROLL, int MIN_CTAS>
+__global__ void __launch_bounds__(DL_THREADS, MIN_CTAS) decode_linear_kernel(const DecLinParams p) {
   extern __shared__ __align__(16) uint8_t dl_smem[];
   __half* xs = reinterpret_cast<__half*>(dl_smem);                                   // [R][Kp]
   float* part = reinterpret_cast<float*>(dl_smem + (size_t)p.R * p.Kp * 2);          // [2][16 warps][8 x 16]
@@ -89,48 +91,69 @@ __global__ void __launch_bounds__(DL_THREADS, 2) decode_linear_kernel(const DecL
     }
   }
   pdl_wait();
-  // ---- stage the activations (and their row statistics): warp w -> row w & 7, half (w >> 3) of the row ----
+  // ---- stage the activations: one flat, coalesced copy by all threads (independent 16-byte loads, one round trip) ----
   {
-    const int r = warp & 7, hh = warp >> 3;
     const int nvec = p.K >> 3;
-    const int v0 = hh ? (nvec >> 1) : 0, v1 = hh ? nvec : (nvec >> 1);
-    float sq = 0.f;
-    if (r < p.R) {
-      const uint4* src = reinterpret_cast<const uint4*>(p.x + (long long)r * p.ldx);
-      uint4* dst = reinterpret_cast<uint4*>(xs + (size_t)r * p.Kp);
-      for (int v = v0 + lane; v < v1; v += 32) {
-        const uint4 u = src[v];
-        dst[v] = u;
-        const __half2* h = reinterpret_cast<const __half2*>(&u);
+    const int total = p.R * nvec;
+    for (int f0 = tid; f0 < total; f0 += DL_THREADS * 4) {
+      uint4 u[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float2 f = __half22float2(h[j]);
-          sq += f.x * f.x + f.y * f.y;
+      for (int j = 0; j < 4; ++j) {
+        const int f = f0 + j * DL_THREADS;
+        if (f < total) {
+          const int r = f / nvec, v = f - r * nvec;
+          u[j] = *(reinterpret_cast<const uint4*>(p.x + (long long)r * p.ldx) + v);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int f = f0 + j * DL_THREADS;
+        if (f < total) {
+          const int r = f / nvec, v = f - r * nvec;
+          *(reinterpret_cast<uint4*>(xs + (size_t)r * p.Kp) + v) = u[j];
         }
       }
     }
-    sq = warp_sum(sq);
-    if (lane == 0) ssq_s[warp] = sq;
     __syncthreads();
-    if (p.norm_mode == 2) {
+    // row statistics from shared memory: warp w -> row w & 7, half (w >> 3) of the row
+    if (p.norm_mode != 0) {
+      const int r = warp & 7, hh = warp >> 3;
+      const int v0 = hh ? (nvec >> 1) : 0, v1 = hh ? nvec : (nvec >> 1);
+      float sq = 0.f;
+      uint4* row = reinterpret_cast<uint4*>(xs + (size_t)r * p.Kp);
       if (r < p.R) {
-        const float rstd = rsqrtf((ssq_s[r] + ssq_s[r + 8]) / (float)p.K + p.eps);
-        uint4* dst = reinterpret_cast<uint4*>(xs + (size_t)r * p.Kp);
-        const uint4* wsrc = reinterpret_cast<const uint4*>(p.norm_w);
         for (int v = v0 + lane; v < v1; v += 32) {
-          uint4 u = dst[v];
-          const uint4 wv = __ldg(wsrc + v);
-          __half2* h = reinterpret_cast<__half2*>(&u);
-          const __half2* wh = reinterpret_cast<const __half2*>(&wv);
+          const uint4 u = row[v];
+          const __half2* h = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const float2 f = __half22float2(h[j]);
-            h[j] = __hmul2(wh[j], __floats2half2_rn(f.x * rstd, f.y * rstd));   // rounding of norm.cu / the reference
+            sq += f.x * f.x + f.y * f.y;
           }
-          dst[v] = u;
         }
       }
+      sq = warp_sum(sq);
+      if (lane == 0) ssq_s[warp] = sq;
       __syncthreads();
+      if (p.norm_mode == 2) {
+        if (r < p.R) {
+          const float rstd = rsqrtf((ssq_s[r] + ssq_s[r + 8]) / (float)p.K + p.eps);
+          const uint4* wsrc = reinterpret_cast<const uint4*>(p.norm_w);
+          for (int v = v0 + lane; v < v1; v += 32) {
+            uint4 u = row[v];
+            const uint4 wv = __ldg(wsrc + v);
+            __half2* h = reinterpret_cast<__half2*>(&u);
+            const __half2* wh = reinterpret_cast<const __half2*>(&wv);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = __half22float2(h[j]);
+              h[j] = __hmul2(wh[j], __floats2half2_rn(f.x * rstd, f.y * rstd));   // rounding of norm.cu / the reference
+            }
+            row[v] = u;
+          }
+        }
+        __syncthreads();
+      }
     }
   }
   const __half* xr = xs + (size_t)(g < p.R ? g : 0) * p.Kp + 8 * t;
@@ -301,7 +324,8 @@ DEVI float sum16(float v) {   // over the 16 lanes of a half-warp
 __global__ void __launch_bounds__(DA_THREADS, 1) decode_attention_kernel(const DecAttnParams p) {
   extern __shared__ __align__(16) uint8_t da_smem[];
   float* sc = reinterpret_cast<float*>(da_smem);            // [8][cap] scores, then probabilities
-  float* red = sc + (size_t)DL_RMAX * p.cap;                // [16 warps][R][128]
+  float* red = sc + (size_t)DL_RMAX * p.cap;                // [16 warps][R][128] prefix partials
+  float* red_s = red + (size_t)DA_WARPS * p.R * DA_D;       // [16 warps][128] suffix partials (warp w -> beam w % R)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, hw = lane >> 4, c = lane & 15;
   const int h = blockIdx.x, sp = blockIdx.y;
   pdl_launch_dependents();
@@ -313,6 +337,11 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attention_kernel(const D
   const long long hoff = (long long)h * DA_D + 8 * c;
   constexpr int U = 4;
   constexpr float NEG_INF = -INFINITY;
+  // generated keys differ per beam: the warps are dealt out to the beams (warp w -> beam w % R, slice w / R of nsub), so
+  // all beams walk their ancestry chains at the same time
+  const int nsub = DA_WARPS / p.R;
+  const int my_r = warp % p.R, my_sub = warp / p.R;
+  const bool suf_warp = my_sub < nsub;
 
   // ---- scores: half-warp per key, lane = 16-byte chunk of the head dim ----
   {
@@ -340,42 +369,42 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attention_kernel(const D
         const bool masked = p.p_mask != nullptr && i < np && p.p_mask[pk0 + i] == 0;
 #pragma unroll
         for (int r = 0; r < DL_RMAX; ++r) {
-          float d = 0.f;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) d = fmaf(qf[r][e], kf[e], d);
-          d = sum16(d);
-          if (c == 0 && i < np && r < p.R) sc[r * p.cap + i] = masked ? NEG_INF : d * p.scale;
-        }
-      }
-    }
-    // generated keys: per beam, through the ancestry table
-#pragma unroll
-    for (int r = 0; r < DL_RMAX; ++r) {
-      if (r < p.R) {
-        for (int c0 = sk0 + 2 * warp; c0 < sk1; c0 += 2 * DA_WARPS * U) {
-          const int j0 = c0 + hw;
-          uint4 kv[U];
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const int j = j0 + 2 * DA_WARPS * u;
-            kv[u] = make_uint4(0u, 0u, 0u, 0u);
-            if (j < sk1) {
-              const int pr = p.src[r * p.src_ld + j];
-              kv[u] = *reinterpret_cast<const uint4*>(p.ks + (long long)pr * p.s_beam_stride +
-                                                      (long long)j * p.s_tok_stride + hoff);
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const int j = j0 + 2 * DA_WARPS * u;
-            float kf[8];
-            half8_to_float(kv[u], kf);
+          if (r < p.R) {
             float d = 0.f;
 #pragma unroll
             for (int e = 0; e < 8; ++e) d = fmaf(qf[r][e], kf[e], d);
             d = sum16(d);
-            if (c == 0 && j < sk1) sc[r * p.cap + np + (j - sk0)] = d * p.scale;
+            if (c == 0 && i < np) sc[r * p.cap + i] = masked ? NEG_INF : d * p.scale;
           }
+        }
+      }
+    }
+    if (suf_warp) {
+      float qs[8];
+      half8_to_float(*reinterpret_cast<const uint4*>(p.q + (long long)my_r * p.ldq + hoff), qs);
+      for (int c0 = sk0 + 2 * my_sub; c0 < sk1; c0 += 2 * nsub * U) {
+        const int j0 = c0 + hw;
+        uint4 kv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int j = j0 + 2 * nsub * u;
+          kv[u] = make_uint4(0u, 0u, 0u, 0u);
+          if (j < sk1) {
+            const int pr = p.src[my_r * p.src_ld + j];
+            kv[u] = *reinterpret_cast<const uint4*>(p.ks + (long long)pr * p.s_beam_stride +
+                                                    (long long)j * p.s_tok_stride + hoff);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int j = j0 + 2 * nsub * u;
+          float kf[8];
+          half8_to_float(kv[u], kf);
+          float d = 0.f;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) d = fmaf(qs[e], kf[e], d);
+          d = sum16(d);
+          if (c == 0 && j < sk1) sc[my_r * p.cap + np + (j - sk0)] = d * p.scale;
         }
       }
     }
@@ -408,7 +437,7 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attention_kernel(const D
     for (int r = 0; r < DL_RMAX; ++r)
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[r][e] = 0.f;
-    for (int b0 = 2 * warp; b0 < np; b0 += 2 * DA_WARPS * U) {   // warp-uniform trip count (shuffles inside)
+    for (int b0 = 2 * warp; b0 < np; b0 += 2 * DA_WARPS * U) {
       const int i0 = b0 + hw;
       uint4 vv[U];
 #pragma unroll
@@ -434,36 +463,6 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attention_kernel(const D
         }
       }
     }
-#pragma unroll
-    for (int r = 0; r < DL_RMAX; ++r) {
-      if (r < p.R) {
-        for (int c0 = sk0 + 2 * warp; c0 < sk1; c0 += 2 * DA_WARPS * U) {
-          const int j0 = c0 + hw;
-          uint4 vv[U];
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const int j = j0 + 2 * DA_WARPS * u;
-            vv[u] = make_uint4(0u, 0u, 0u, 0u);
-            if (j < sk1) {
-              const int pr = p.src[r * p.src_ld + j];
-              vv[u] = *reinterpret_cast<const uint4*>(p.vs + (long long)pr * p.s_beam_stride +
-                                                      (long long)j * p.s_tok_stride + hoff);
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const int j = j0 + 2 * DA_WARPS * u;
-            if (j < sk1) {
-              float vf[8];
-              half8_to_float(vv[u], vf);
-              const float pr = sc[r * p.cap + np + (j - sk0)];
-#pragma unroll
-              for (int e = 0; e < 8; ++e) acc[r][e] = fmaf(pr, vf[e], acc[r][e]);
-            }
-          }
-        }
-      }
-    }
     // the two half-warps of a warp hold different keys: fold them, then one partial per warp
 #pragma unroll
     for (int r = 0; r < DL_RMAX; ++r) {
@@ -477,6 +476,44 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attention_kernel(const D
         }
       }
     }
+    // generated keys of this warp's beam
+    float as[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) as[e] = 0.f;
+    if (suf_warp) {
+      for (int c0 = sk0 + 2 * my_sub; c0 < sk1; c0 += 2 * nsub * U) {
+        const int j0 = c0 + hw;
+        uint4 vv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int j = j0 + 2 * nsub * u;
+          vv[u] = make_uint4(0u, 0u, 0u, 0u);
+          if (j < sk1) {
+            const int pr = p.src[my_r * p.src_ld + j];
+            vv[u] = *reinterpret_cast<const uint4*>(p.vs + (long long)pr * p.s_beam_stride +
+                                                    (long long)j * p.s_tok_stride + hoff);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int j = j0 + 2 * nsub * u;
+          if (j < sk1) {
+            float vf[8];
+            half8_to_float(vv[u], vf);
+            const float pr = sc[my_r * p.cap + np + (j - sk0)];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) as[e] = fmaf(pr, vf[e], as[e]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) as[e] += __shfl_xor_sync(0xffffffffu, as[e], 16);
+    if (hw == 0) {
+      float* dst = red_s + (size_t)warp * DA_D + 8 * c;
+      *reinterpret_cast<float4*>(dst) = make_float4(as[0], as[1], as[2], as[3]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(as[4], as[5], as[6], as[7]);
+    }
   }
   __syncthreads();
   for (int idx = tid; idx < p.R * DA_D; idx += DA_THREADS) {
@@ -484,6 +521,7 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attention_kernel(const D
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < DA_WARPS; ++w) s += red[((size_t)w * p.R + r) * DA_D + d];
+    for (int w = r; w < nsub * p.R; w += p.R) s += red_s[(size_t)w * DA_D + d];
     wsb[r * DA_WS_ROW + d] = s;
   }
 }
@@ -562,14 +600,18 @@ extern "C" int stllm_decode_linear_f16(const void* x, long long ldx, const void*
   }
   static bool configured = false;
   if (!configured) {
-    STLLM_CHECK_CUDA(cudaFuncSetAttribute(decode_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DL_SMEM_MAX));
+    STLLM_CHECK_CUDA(cudaFuncSetAttribute(decode_linear_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DL_SMEM_MAX / 2));
+    STLLM_CHECK_CUDA(cudaFuncSetAttribute(decode_linear_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DL_SMEM_MAX));
     configured = true;
   }
   const int nblk = (N + 15) / 16;
-  const int per_sm = (int)((size_t)(226 * 1024) / (smem + 1024)) >= 2 ? 2 : 1;
-  int grid = num_sms_dec() * per_sm;
+  const bool two = smem <= (size_t)(DL_SMEM_MAX / 2);
+  int grid = num_sms_dec() * (two ? 2 : 1);
   if (grid > nblk) grid = nblk;
-  STLLM_CHECK_CUDA(stllm_launch(decode_linear_kernel, dim3(grid), dim3(DL_THREADS), smem, (cudaStream_t)stream, p));
+  if (two)
+    STLLM_CHECK_CUDA(stllm_launch(decode_linear_kernel<4, 2>, dim3(grid), dim3(DL_THREADS), smem, (cudaStream_t)stream, p));
+  else
+    STLLM_CHECK_CUDA(stllm_launch(decode_linear_kernel<8, 1>, dim3(grid), dim3(DL_THREADS), smem, (cudaStream_t)stream, p));
   return STLLM_OK;
 }
 
@@ -604,7 +646,8 @@ extern "C" int stllm_decode_attention_f16(const void* q, long long ldq, const vo
                                           const int* n_gen, void* out, long long ldo, void* workspace,
                                           long long workspace_bytes, int R, int H, int D, int n_split, float scale,
                                           void* stream) {
-  STLLM_CHECK_ARG(q && k_prefix && v_prefix && k_suffix && v_suffix && src && n_gen && out && workspace);
+  STLLM_CHECK_ARG(q && k_suffix && v_suffix && src && n_gen && out && workspace);
+  STLLM_CHECK_ARG(prefix_len == 0 || (k_prefix && v_prefix));
   STLLM_CHECK_ARG(R >= 1 && R <= DL_RMAX && H >= 1 && prefix_len >= 0 && l_max >= 1 && n_split >= 1 && n_split <= 64);
   STLLM_CHECK_ARG(ldq % 8 == 0 && p_stride % 8 == 0 && s_beam_stride % 8 == 0 && s_tok_stride % 8 == 0 && src_ld >= l_max);
   STLLM_CHECK_ARG((((uintptr_t)q | (uintptr_t)k_prefix | (uintptr_t)v_prefix | (uintptr_t)k_suffix | (uintptr_t)v_suffix) & 15) == 0);
@@ -623,7 +666,7 @@ extern "C" int stllm_decode_attention_f16(const void* q, long long ldq, const vo
   p.R = R; p.H = H; p.Sp = prefix_len; p.NS = n_split;
   p.cap = (((prefix_len + n_split - 1) / n_split + (l_max + n_split - 1) / n_split + 2) + 3) & ~3;
   p.scale = scale;
-  const size_t smem = ((size_t)DL_RMAX * p.cap + (size_t)DA_WARPS * R * DA_D) * sizeof(float);
+  const size_t smem = ((size_t)DL_RMAX * p.cap + (size_t)DA_WARPS * (R + 1) * DA_D) * sizeof(float);
   if (smem > (size_t)DA_SMEM_MAX) {
     stllm_set_last_error("stllm_decode_attention_f16: %d + %d keys over %d splits do not fit in shared memory",
                          prefix_len, l_max, n_split);
