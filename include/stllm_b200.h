@@ -213,6 +213,20 @@ int stllm_decode_attention_f16(const void* q, long long ldq, const void* k_prefi
                                const int* src, int src_ld, const int* n_gen, void* out, long long ldo, void* workspace,
                                long long workspace_bytes, int R, int H, int D, int n_split, float scale, void* stream);
 
+/* stllm_decode_rope_append_f16 + stllm_decode_attention_f16 in ONE launch per layer: every CTA (head, key split) ropes
+ * the query rows of its head itself; the CTA of the last split ropes k of the new token, stores k / v into the suffix
+ * caches (and src[r, *n_gen] = r) and scores that key from shared memory; the last CTA of a head to finish merges the
+ * splits (atomic ticket, reset for the next launch).  qkv is NOT modified.  The workspace holds the split partials and
+ * the tickets: stllm_decode_attention_fused_workspace_bytes(H, n_split) bytes, ZEROED once by the caller. */
+long long stllm_decode_attention_fused_workspace_bytes(int H, int n_split);
+int stllm_decode_attention_fused_f16(void* qkv, long long ldq, const float* cos_t, const float* sin_t, int max_pos,
+                                     const void* k_prefix, const void* v_prefix, long long p_stride,
+                                     const void* prefix_mask, int prefix_len, void* k_suffix, void* v_suffix,
+                                     long long s_beam_stride, long long s_tok_stride, int l_max, int* src, int src_ld,
+                                     const int* n_gen, void* out, long long ldo, void* workspace,
+                                     long long workspace_bytes, int R, int H, int D, int n_split, float scale,
+                                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -128,6 +128,40 @@ def attn_case(R, H, Sp, n_gen, l_max, n_split, mask=False):
                   out, ref, atol=3e-3, rtol=3e-3)
 
 
+def attn_fused_case(R, H, Sp, n_gen, l_max, n_split, mask=False, repeats=2):
+    """rope + append + attention + merge in one launch, against the unfused pieces' references; launched `repeats` times on
+    the same workspace (the ticket counters must reset themselves)"""
+    HD = H * 128
+    q, kp, vp, ks, vs, src, pm = attn_setup(R, H, Sp, n_gen, l_max, mask, seed=n_gen + 1)
+    qkv = q   # [R, 3*HD] un-roped q | k | v of the new token
+    cos_t, sin_t = ops.rope_tables(128, 2048)
+    ws = ops.decode_attention_fused_workspace(H, n_split, dev)
+    scale = 1.0 / math.sqrt(128)
+    ng = torch.tensor([n_gen], device=dev, dtype=torch.int32)
+    # reference: prefill RoPE kernel at the same position, append, then the attention reference
+    roped = qkv.clone()
+    ops.rope_(roped, torch.full((R,), Sp + n_gen, device=dev, dtype=torch.int32), cos_t, sin_t, 2 * H, 128)
+    ks_ref, vs_ref, src_ref = ks.clone(), vs.clone(), src.clone()
+    ks_ref[:, n_gen] = roped[:, HD:2 * HD]
+    vs_ref[:, n_gen] = qkv[:, 2 * HD:]
+    src_ref[:, n_gen] = torch.arange(R, device=dev, dtype=torch.int32)
+    ref = attn_ref(roped, kp, vp, ks_ref, vs_ref, src_ref, pm, R, H, n_gen + 1, scale)
+    ok = True
+    qkv_before = qkv.clone()
+    for it in range(repeats):
+        out = torch.full((R, HD), float("nan"), device=dev, dtype=torch.float16)
+        ops.decode_attention_fused(qkv, cos_t, sin_t, kp, vp, ks, vs, src, ng, out, ws, H, 128, scale, n_split=n_split,
+                                   prefix_mask=pm)
+        torch.cuda.synchronize()
+        ok &= report(f"decode_attention_fused R={R} H={H} Sp={Sp} n_gen={n_gen} l_max={l_max} splits={n_split} "
+                     f"mask={int(mask)} run {it}", out, ref, atol=3e-3, rtol=3e-3)
+    ok &= report("  fused: k appended (bit-exact with rope_kernel)", ks.reshape(R, -1), ks_ref.reshape(R, -1), 0, 0)
+    ok &= report("  fused: v appended", vs.reshape(R, -1), vs_ref.reshape(R, -1), 0, 0)
+    ok &= report("  fused: ancestry", src.float(), src_ref.float(), 0, 0)
+    ok &= report("  fused: qkv untouched", qkv, qkv_before, 0, 0)
+    return ok
+
+
 def rope_append_case(R, H, prefix_len, n_gen, l_max):
     D = 128
     HD = H * D
@@ -287,6 +321,33 @@ def time_decode(layers, beams, S=576, steps=48, general=True):
     return res
 
 
+def time_generate(layers, beams, S=576, new_tokens=64):
+    """the public call: llm.generate(inputs_embeds=[1,S,4096], ...) end to end (prefill + graph capture + decode steps +
+    host-side beam bookkeeping), decode engine vs the general-kernel route"""
+    from stllm_b200.pipeline import build_model
+    model = build_model(llama_layers=layers, vit_depth=1, qformer_layers=1, device=torch.device("cuda", 0), seed=0)
+    g = torch.Generator(device=dev).manual_seed(5)
+    emb = (torch.randn(1, S, 4096, device=dev, generator=g) * 0.05).half()
+    res = dict(layers=layers, beams=beams, prefix=S, new_tokens=new_tokens)
+    for route in ("engine", "general"):
+        os.environ["STLLM_DECODE_ENGINE"] = "1" if route == "engine" else "0"
+        n = new_tokens if route == "engine" else min(new_tokens, 24)
+        model.generate(inputs_embeds=emb, max_new_tokens=4, num_beams=beams, eos_token_id=-1)   # warm-up
+        torch.cuda.synchronize()
+        t0 = time.time()
+        out = model.generate(inputs_embeds=emb, max_new_tokens=n, num_beams=beams, eos_token_id=-1)
+        torch.cuda.synchronize()
+        dt = time.time() - t0
+        res[route + "_s"] = dt
+        res[route + "_tokens"] = int(out.shape[1])
+        res[route + "_tokens_per_s_incl_prefill"] = out.shape[1] / dt
+    os.environ.pop("STLLM_DECODE_ENGINE", None)
+    print("TIME generate " + json.dumps(res), flush=True)
+    del model
+    torch.cuda.empty_cache()
+    return res
+
+
 def main():
     print(torch.cuda.get_device_name(0), flush=True)
     torch.manual_seed(0)
@@ -329,6 +390,18 @@ def main():
     attn_case(8, 32, 1500, 299, 300, 4)
     attn_case(2, 4, 0, 5, 8, 2)                   # no prefix at all
     attn_case(5, 32, 576, 20, 64, 1)
+    # ---- fused rope + append + attention + merge ----
+    attn_fused_case(1, 2, 12, 0, 8, 1)
+    attn_fused_case(1, 2, 12, 3, 8, 4)
+    attn_fused_case(3, 2, 5, 6, 8, 4)
+    attn_fused_case(5, 32, 576, 0, 64, 5)
+    attn_fused_case(5, 32, 576, 37, 64, 5, repeats=3)
+    attn_fused_case(5, 32, 577, 63, 64, 3, mask=True)      # > 128 prompt keys per split: second batch of loads
+    attn_fused_case(8, 32, 1500, 299, 300, 12)
+    attn_fused_case(8, 32, 1500, 299, 300, 4)
+    attn_fused_case(2, 4, 0, 5, 8, 2)
+    attn_fused_case(1, 32, 576, 150, 256, 5)               # greedy: all 16 warps on one beam's generated keys
+    attn_fused_case(5, 32, 576, 20, 64, 1)
     # ---- engine vs the general kernels (model.forward + KVCache) ----
     engine_vs_general(2, 256, 512, 2, 128, 12, 1, 5, use_graph=False)
     engine_vs_general(2, 256, 512, 2, 128, 12, 3, 6, use_graph=True, mask=True)
@@ -354,6 +427,8 @@ def timings():
         if "--layers" in sys.argv:
             layers = int(sys.argv[sys.argv.index("--layers") + 1])
         dec = [time_decode(layers, 1), time_decode(layers, 5)]
+        if "--generate" in sys.argv:
+            dec += [time_generate(layers, 1), time_generate(layers, 5)]
         os.makedirs("gpurun_out", exist_ok=True)
         tag = os.environ.get("DECODE_TIMING_TAG", "")
         with open(f"gpurun_out/decode_timing{tag}.json", "w") as f:

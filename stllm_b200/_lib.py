@@ -51,6 +51,10 @@ SIGNATURES = {
     "stllm_decode_rope_append_f16": [c_void_p, c_ll, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                      c_ll, c_ll, c_int, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "stllm_decode_attention_workspace_bytes": [c_int, c_int],
+    "stllm_decode_attention_fused_workspace_bytes": [c_int, c_int],
+    "stllm_decode_attention_fused_f16": [c_void_p, c_ll, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_ll, c_void_p,
+                                         c_int, c_void_p, c_void_p, c_ll, c_ll, c_int, c_void_p, c_int, c_void_p,
+                                         c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_float, c_void_p],
     "stllm_decode_attention_f16": [c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_void_p, c_int, c_void_p, c_void_p, c_ll,
                                    c_ll, c_int, c_void_p, c_int, c_void_p, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int,
                                    c_int, c_int, c_float, c_void_p],
@@ -80,6 +84,7 @@ def load():
         fn.restype = c_int
     lib.stllm_gemm_workspace_bytes.restype = c_ll
     lib.stllm_decode_attention_workspace_bytes.restype = c_ll
+    lib.stllm_decode_attention_fused_workspace_bytes.restype = c_ll
     lib.stllm_last_error.argtypes = []
     lib.stllm_last_error.restype = ctypes.c_char_p
     _lib = lib

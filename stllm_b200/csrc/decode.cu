@@ -547,6 +547,350 @@ __global__ void __launch_bounds__(DA_D) decode_attention_combine_kernel(const fl
   out[(long long)r * ldo + (long long)h * DA_D + d] = __float2half_rn(L > 0.f ? o / L : 0.f);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Fused variant: RoPE of q / k, the cache append, the attention of one (head, key split) and the merge of the splits in
+// ONE launch (3 launches -> 1 per layer).  Every CTA ropes the R query rows of its head itself (R x 128 values); the
+// CTA of the LAST split owns the new token: it ropes k, stores k / v into the suffix caches and scores the new key from
+// shared memory, so no CTA reads a cache slot written by this launch.  The last CTA of a head to finish (atomic
+// ticket) merges the splits.  All global loads of a CTA are issued up front (prefix K and V, the ancestry entries, then
+// the generated K and V): two dependent round trips instead of eight.
+struct DecAttnFusedParams {
+  __half* qkv;
+  long long ldq;
+  const float* cos_t;
+  const float* sin_t;
+  const __half* kp;
+  const __half* vp;
+  long long p_stride;
+  const uint8_t* p_mask;
+  __half* ks;
+  __half* vs;
+  long long s_beam_stride, s_tok_stride;
+  int* src;
+  int src_ld;
+  const int* n_gen;
+  __half* out;
+  long long ldo;
+  float* ws;
+  int* tickets;   // [H], zero before the first launch; reset by the merging CTA
+  int R, H, Sp, NS, cap, l_max, max_pos;
+  float scale;
+};
+
+__global__ void __launch_bounds__(DA_THREADS, 1) decode_attention_fused_kernel(const DecAttnFusedParams p) {
+  extern __shared__ __align__(16) uint8_t da_smem[];
+  float* sc = reinterpret_cast<float*>(da_smem);            // [8][cap]
+  float* red = sc + (size_t)DL_RMAX * p.cap;                // [16 warps][R][128]
+  float* red_s = red + (size_t)DA_WARPS * p.R * DA_D;       // [16 warps][128]
+  float* qs = red_s + (size_t)DA_WARPS * DA_D;              // [8][128] roped q (fp16-rounded values)
+  float* kn = qs + DL_RMAX * DA_D;                          // [8][128] roped k of the new token (last split only)
+  float* vn = kn + DL_RMAX * DA_D;                          // [8][128] v of the new token
+  __shared__ int s_last;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, hw = lane >> 4, c = lane & 15;
+  const int h = blockIdx.x, sp = blockIdx.y;
+  const bool last_split = sp == p.NS - 1;
+  pdl_launch_dependents();
+  const int pk0 = (int)((long long)p.Sp * sp / p.NS), pk1 = (int)((long long)p.Sp * (sp + 1) / p.NS);
+  const int np = pk1 - pk0;
+  const long long hoff = (long long)h * DA_D + 8 * c;
+  constexpr int U = 4;
+  constexpr float NEG_INF = -INFINITY;
+  const int nsub = DA_WARPS / p.R;
+  const int my_r = warp % p.R, my_sub = warp / p.R;
+  const bool suf_warp = my_sub < nsub;
+  // ---- (a) the prompt's K and V of the first batch: static data, requested before the predecessor has finished ----
+  uint4 kv0[U], vv0[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int i = 2 * warp + hw + 2 * DA_WARPS * u;
+    kv0[u] = make_uint4(0u, 0u, 0u, 0u);
+    vv0[u] = make_uint4(0u, 0u, 0u, 0u);
+    if (i < np) {
+      kv0[u] = __ldg(reinterpret_cast<const uint4*>(p.kp + (long long)(pk0 + i) * p.p_stride + hoff));
+      vv0[u] = __ldg(reinterpret_cast<const uint4*>(p.vp + (long long)(pk0 + i) * p.p_stride + hoff));
+    }
+  }
+  pdl_wait();
+  const int n_gen = *p.n_gen;
+  const int n_suf = n_gen + 1;
+  const int sk0 = (int)((long long)n_suf * sp / p.NS);
+  const int sk1 = (int)((long long)n_suf * (sp + 1) / p.NS);
+  const int sk1c = last_split ? sk1 - 1 : sk1;   // keys read from the cache; the new token (j = n_gen) comes from smem
+  const int ns = sk1 - sk0, ntot = np + ns;
+  const int pos = p.Sp + n_gen;
+  if (n_gen >= p.l_max || pos >= p.max_pos) return;   // the host never launches past the capacity
+  // ---- (b) ancestry entries of the first batch of generated keys ----
+  int pr0[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int j = sk0 + 2 * my_sub + hw + 2 * nsub * u;
+    pr0[u] = (suf_warp && j < sk1c) ? p.src[my_r * p.src_ld + j] : 0;
+  }
+  // ---- (c) RoPE of q (and of k for the new token) into shared memory ----
+  for (int idx = tid; idx < p.R * 64; idx += DA_THREADS) {
+    const int r = idx >> 6, i = idx & 63;
+    const float cs = __ldg(p.cos_t + (long long)pos * 64 + i), sn = __ldg(p.sin_t + (long long)pos * 64 + i);
+    const __half* row = p.qkv + (long long)r * p.ldq + (long long)h * DA_D;
+    const float lo = __half2float(row[i]), hi = __half2float(row[i + 64]);
+    qs[r * DA_D + i] = __half2float(__float2half_rn(lo * cs - hi * sn));        // rounding of rope_kernel
+    qs[r * DA_D + i + 64] = __half2float(__float2half_rn(hi * cs + lo * sn));
+    if (last_split) {
+      const long long HD = (long long)p.H * DA_D;
+      const float klo = __half2float(row[HD + i]), khi = __half2float(row[HD + i + 64]);
+      const __half rlo = __float2half_rn(klo * cs - khi * sn), rhi = __float2half_rn(khi * cs + klo * sn);
+      const __half vlo = row[2 * HD + i], vhi = row[2 * HD + i + 64];
+      kn[r * DA_D + i] = __half2float(rlo);
+      kn[r * DA_D + i + 64] = __half2float(rhi);
+      vn[r * DA_D + i] = __half2float(vlo);
+      vn[r * DA_D + i + 64] = __half2float(vhi);
+      const long long off = (long long)r * p.s_beam_stride + (long long)n_gen * p.s_tok_stride + (long long)h * DA_D;
+      p.ks[off + i] = rlo;
+      p.ks[off + i + 64] = rhi;
+      p.vs[off + i] = vlo;
+      p.vs[off + i + 64] = vhi;
+      if (h == 0 && i == 0) p.src[r * p.src_ld + n_gen] = r;
+    }
+  }
+  // ---- (d) generated K and V of the first batch ----
+  uint4 ks0[U], vs0[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int j = sk0 + 2 * my_sub + hw + 2 * nsub * u;
+    ks0[u] = make_uint4(0u, 0u, 0u, 0u);
+    vs0[u] = make_uint4(0u, 0u, 0u, 0u);
+    if (suf_warp && j < sk1c) {
+      const long long off = (long long)pr0[u] * p.s_beam_stride + (long long)j * p.s_tok_stride + hoff;
+      ks0[u] = *reinterpret_cast<const uint4*>(p.ks + off);
+      vs0[u] = *reinterpret_cast<const uint4*>(p.vs + off);
+    }
+  }
+  __syncthreads();
+  // ---- scores ----
+  {
+    // prompt keys: first batch from registers, further batches (np > 128) loaded here
+    for (int b0 = 0; b0 < np; b0 += 2 * DA_WARPS * U) {   // block-uniform trip count
+      uint4 kv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = b0 + 2 * warp + hw + 2 * DA_WARPS * u;
+        if (b0 == 0) kv[u] = kv0[u];
+        else kv[u] = i < np ? __ldg(reinterpret_cast<const uint4*>(p.kp + (long long)(pk0 + i) * p.p_stride + hoff))
+                            : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = b0 + 2 * warp + hw + 2 * DA_WARPS * u;
+        float kf[8];
+        half8_to_float(kv[u], kf);
+        const bool masked = p.p_mask != nullptr && i < np && p.p_mask[pk0 + i] == 0;
+        for (int r = 0; r < p.R; ++r) {
+          const float4 q0 = *reinterpret_cast<const float4*>(qs + r * DA_D + 8 * c);
+          const float4 q1 = *reinterpret_cast<const float4*>(qs + r * DA_D + 8 * c + 4);
+          float d = q0.x * kf[0];
+          d = fmaf(q0.y, kf[1], d); d = fmaf(q0.z, kf[2], d); d = fmaf(q0.w, kf[3], d);
+          d = fmaf(q1.x, kf[4], d); d = fmaf(q1.y, kf[5], d); d = fmaf(q1.z, kf[6], d); d = fmaf(q1.w, kf[7], d);
+          d = sum16(d);
+          if (c == 0 && i < np) sc[r * p.cap + i] = masked ? NEG_INF : d * p.scale;
+        }
+      }
+    }
+    // generated keys of this warp's beam (warp-uniform loops)
+    if (suf_warp) {
+      float qr[8];
+      {
+        const float4 q0 = *reinterpret_cast<const float4*>(qs + my_r * DA_D + 8 * c);
+        const float4 q1 = *reinterpret_cast<const float4*>(qs + my_r * DA_D + 8 * c + 4);
+        qr[0] = q0.x; qr[1] = q0.y; qr[2] = q0.z; qr[3] = q0.w; qr[4] = q1.x; qr[5] = q1.y; qr[6] = q1.z; qr[7] = q1.w;
+      }
+      for (int c0 = sk0 + 2 * my_sub; c0 < sk1c; c0 += 2 * nsub * U) {
+        const bool first = c0 == sk0 + 2 * my_sub;
+        uint4 kv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int j = c0 + hw + 2 * nsub * u;
+          if (first) kv[u] = ks0[u];
+          else {
+            kv[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (j < sk1c) {
+              const int pr = p.src[my_r * p.src_ld + j];
+              kv[u] = *reinterpret_cast<const uint4*>(p.ks + (long long)pr * p.s_beam_stride +
+                                                      (long long)j * p.s_tok_stride + hoff);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int j = c0 + hw + 2 * nsub * u;
+          float kf[8];
+          half8_to_float(kv[u], kf);
+          float d = 0.f;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) d = fmaf(qr[e], kf[e], d);
+          d = sum16(d);
+          if (c == 0 && j < sk1c) sc[my_r * p.cap + np + (j - sk0)] = d * p.scale;
+        }
+      }
+    }
+    // the new token's key (last split): warp r -> beam r, from shared memory
+    if (last_split && warp < p.R) {
+      float d = 0.f;
+      for (int i = lane; i < DA_D; i += 32) d = fmaf(qs[warp * DA_D + i], kn[warp * DA_D + i], d);
+      d = warp_sum(d);
+      if (lane == 0) sc[warp * p.cap + np + (n_gen - sk0)] = d * p.scale;
+    }
+  }
+  __syncthreads();
+  // ---- fp32 softmax of this split: warp r -> beam r ----
+  float* wsb = p.ws + ((size_t)(h * p.NS + sp) * DL_RMAX) * DA_WS_ROW;
+  if (warp < p.R) {
+    float* s = sc + warp * p.cap;
+    float m = NEG_INF;
+    for (int i = lane; i < ntot; i += 32) m = fmaxf(m, s[i]);
+    m = warp_max(m);
+    float l = 0.f;
+    for (int i = lane; i < ntot; i += 32) {
+      const float e = (m == NEG_INF) ? 0.f : __expf(s[i] - m);
+      s[i] = e;
+      l += e;
+    }
+    l = warp_sum(l);
+    if (lane == 0) {
+      wsb[warp * DA_WS_ROW + 128] = m;
+      wsb[warp * DA_WS_ROW + 129] = l;
+    }
+  }
+  __syncthreads();
+  // ---- o = P V (unnormalised) ----
+  {
+    float acc[DL_RMAX][8];
+#pragma unroll
+    for (int r = 0; r < DL_RMAX; ++r)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[r][e] = 0.f;
+    for (int b0 = 0; b0 < np; b0 += 2 * DA_WARPS * U) {
+      uint4 vv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = b0 + 2 * warp + hw + 2 * DA_WARPS * u;
+        if (b0 == 0) vv[u] = vv0[u];
+        else vv[u] = i < np ? __ldg(reinterpret_cast<const uint4*>(p.vp + (long long)(pk0 + i) * p.p_stride + hoff))
+                            : make_uint4(0u, 0u, 0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int i = b0 + 2 * warp + hw + 2 * DA_WARPS * u;
+        if (i < np) {
+          float vf[8];
+          half8_to_float(vv[u], vf);
+#pragma unroll
+          for (int r = 0; r < DL_RMAX; ++r) {
+            if (r < p.R) {
+              const float pr = sc[r * p.cap + i];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) acc[r][e] = fmaf(pr, vf[e], acc[r][e]);
+            }
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < DL_RMAX; ++r) {
+      if (r < p.R) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[r][e] += __shfl_xor_sync(0xffffffffu, acc[r][e], 16);
+        if (hw == 0) {
+          float* dst = red + ((size_t)warp * p.R + r) * DA_D + 8 * c;
+          *reinterpret_cast<float4*>(dst) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+          *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[r][4], acc[r][5], acc[r][6], acc[r][7]);
+        }
+      }
+    }
+    float as[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) as[e] = 0.f;
+    if (suf_warp) {
+      for (int c0 = sk0 + 2 * my_sub; c0 < sk1c; c0 += 2 * nsub * U) {
+        const bool first = c0 == sk0 + 2 * my_sub;
+        uint4 vv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int j = c0 + hw + 2 * nsub * u;
+          if (first) vv[u] = vs0[u];
+          else {
+            vv[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (j < sk1c) {
+              const int pr = p.src[my_r * p.src_ld + j];
+              vv[u] = *reinterpret_cast<const uint4*>(p.vs + (long long)pr * p.s_beam_stride +
+                                                      (long long)j * p.s_tok_stride + hoff);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int j = c0 + hw + 2 * nsub * u;
+          if (j < sk1c) {
+            float vf[8];
+            half8_to_float(vv[u], vf);
+            const float pr = sc[my_r * p.cap + np + (j - sk0)];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) as[e] = fmaf(pr, vf[e], as[e]);
+          }
+        }
+      }
+      // the new token's value: added once per beam by the first of the beam's warps (half-warp 0 only: folded below)
+      if (last_split && my_sub == 0 && hw == 0) {
+        const float pr = sc[my_r * p.cap + np + (n_gen - sk0)];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) as[e] = fmaf(pr, vn[my_r * DA_D + 8 * c + e], as[e]);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) as[e] += __shfl_xor_sync(0xffffffffu, as[e], 16);
+    if (hw == 0) {
+      float* dst = red_s + (size_t)warp * DA_D + 8 * c;
+      *reinterpret_cast<float4*>(dst) = make_float4(as[0], as[1], as[2], as[3]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(as[4], as[5], as[6], as[7]);
+    }
+  }
+  __syncthreads();
+  for (int idx = tid; idx < p.R * DA_D; idx += DA_THREADS) {
+    const int r = idx >> 7, d = idx & 127;
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < DA_WARPS; ++w) s += red[((size_t)w * p.R + r) * DA_D + d];
+    for (int w = r; w < nsub * p.R; w += p.R) s += red_s[(size_t)w * DA_D + d];
+    wsb[r * DA_WS_ROW + d] = s;
+  }
+  // ---- merge of the splits by the last CTA of this head ----
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    const int prev = atomicAdd(p.tickets + h, 1);
+    s_last = prev == p.NS - 1;
+    if (s_last) p.tickets[h] = 0;   // every CTA of this head has arrived: ready for the next launch
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const float* base = p.ws + (size_t)h * p.NS * DL_RMAX * DA_WS_ROW;
+  const size_t split_stride = (size_t)DL_RMAX * DA_WS_ROW;
+  for (int idx = tid; idx < p.R * DA_D; idx += DA_THREADS) {
+    const int r = idx >> 7, d = idx & 127;
+    const float* br = base + (size_t)r * DA_WS_ROW;
+    float M = NEG_INF;
+    for (int s = 0; s < p.NS; ++s) M = fmaxf(M, __ldcg(br + s * split_stride + 128));
+    float L = 0.f, o = 0.f;
+    if (M != NEG_INF) {
+      for (int s = 0; s < p.NS; ++s) {
+        const float w = __expf(__ldcg(br + s * split_stride + 128) - M);
+        L = fmaf(__ldcg(br + s * split_stride + 129), w, L);
+        o = fmaf(__ldcg(br + s * split_stride + d), w, o);
+      }
+    }
+    p.out[(long long)r * p.ldo + (long long)h * DA_D + d] = __float2half_rn(L > 0.f ? o / L : 0.f);
+  }
+}
+
 int env_int_dec(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
@@ -680,5 +1024,56 @@ extern "C" int stllm_decode_attention_f16(const void* q, long long ldq, const vo
   STLLM_CHECK_CUDA(stllm_launch(decode_attention_kernel, dim3(H, n_split), dim3(DA_THREADS), smem, (cudaStream_t)stream, p));
   STLLM_CHECK_CUDA(stllm_launch(decode_attention_combine_kernel, dim3(H, R), dim3(DA_D), 0, (cudaStream_t)stream,
                                 (const float*)workspace, (__half*)out, ldo, n_split));
+  return STLLM_OK;
+}
+
+extern "C" long long stllm_decode_attention_fused_workspace_bytes(int H, int n_split) {
+  if (H <= 0 || n_split <= 0) return 0;
+  return stllm_decode_attention_workspace_bytes(H, n_split) + (((long long)H * (long long)sizeof(int) + 15) & ~15LL);
+}
+
+extern "C" int stllm_decode_attention_fused_f16(void* qkv, long long ldq, const float* cos_t, const float* sin_t,
+                                                int max_pos, const void* k_prefix, const void* v_prefix,
+                                                long long p_stride, const void* prefix_mask, int prefix_len,
+                                                void* k_suffix, void* v_suffix, long long s_beam_stride,
+                                                long long s_tok_stride, int l_max, int* src, int src_ld,
+                                                const int* n_gen, void* out, long long ldo, void* workspace,
+                                                long long workspace_bytes, int R, int H, int D, int n_split,
+                                                float scale, void* stream) {
+  STLLM_CHECK_ARG(qkv && cos_t && sin_t && k_suffix && v_suffix && src && n_gen && out && workspace);
+  STLLM_CHECK_ARG(prefix_len == 0 || (k_prefix && v_prefix));
+  STLLM_CHECK_ARG(R >= 1 && R <= DL_RMAX && H >= 1 && prefix_len >= 0 && l_max >= 1 && n_split >= 1 && n_split <= 64);
+  STLLM_CHECK_ARG(ldq % 8 == 0 && ldq >= 3LL * H * D && p_stride % 8 == 0 && s_beam_stride % 8 == 0 &&
+                  s_tok_stride % 8 == 0 && src_ld >= l_max);
+  STLLM_CHECK_ARG((((uintptr_t)qkv | (uintptr_t)k_prefix | (uintptr_t)v_prefix | (uintptr_t)k_suffix | (uintptr_t)v_suffix) & 15) == 0);
+  STLLM_CHECK_ARG(workspace_bytes >= stllm_decode_attention_fused_workspace_bytes(H, n_split) && ((uintptr_t)workspace & 15) == 0);
+  if (D != DA_D) {
+    stllm_set_last_error("stllm_decode_attention_fused_f16: head dim %d unsupported (128 only)", D);
+    return STLLM_ERR_UNSUPPORTED;
+  }
+  DecAttnFusedParams p;
+  p.qkv = (__half*)qkv; p.ldq = ldq; p.cos_t = cos_t; p.sin_t = sin_t;
+  p.kp = (const __half*)k_prefix; p.vp = (const __half*)v_prefix; p.p_stride = p_stride;
+  p.p_mask = (const uint8_t*)prefix_mask;
+  p.ks = (__half*)k_suffix; p.vs = (__half*)v_suffix;
+  p.s_beam_stride = s_beam_stride; p.s_tok_stride = s_tok_stride;
+  p.src = src; p.src_ld = src_ld; p.n_gen = n_gen; p.out = (__half*)out; p.ldo = ldo;
+  p.ws = (float*)workspace;
+  p.tickets = (int*)((char*)workspace + stllm_decode_attention_workspace_bytes(H, n_split));
+  p.R = R; p.H = H; p.Sp = prefix_len; p.NS = n_split; p.l_max = l_max; p.max_pos = max_pos;
+  p.cap = (((prefix_len + n_split - 1) / n_split + (l_max + n_split - 1) / n_split + 2) + 3) & ~3;
+  p.scale = scale;
+  const size_t smem = ((size_t)DL_RMAX * p.cap + (size_t)DA_WARPS * (R + 1) * DA_D + 3 * DL_RMAX * DA_D) * sizeof(float);
+  if (smem > (size_t)DA_SMEM_MAX) {
+    stllm_set_last_error("stllm_decode_attention_fused_f16: %d + %d keys over %d splits do not fit in shared memory",
+                         prefix_len, l_max, n_split);
+    return STLLM_ERR_UNSUPPORTED;
+  }
+  static bool configured = false;
+  if (!configured) {
+    STLLM_CHECK_CUDA(cudaFuncSetAttribute(decode_attention_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DA_SMEM_MAX));
+    configured = true;
+  }
+  STLLM_CHECK_CUDA(stllm_launch(decode_attention_fused_kernel, dim3(H, n_split), dim3(DA_THREADS), smem, (cudaStream_t)stream, p));
   return STLLM_OK;
 }

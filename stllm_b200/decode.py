@@ -5,8 +5,8 @@ max_new_tokens 100-300, num_beams 1 or 5): every step re-runs LlamaForCausalLM.f
 cache that holds `num_beams` copies of the prompt and is index_selected as a whole after every beam re-ordering
 (modeling_llama_mem.py:205-217,715-752).  Here a step is
 
-    embedding gather -> 32 x [ (RMSNorm) q|k|v -> RoPE + cache append -> attention over (shared prompt KV || per-beam
-    suffix) -> o_proj + residual -> (RMSNorm) gate|up SwiGLU -> down + residual ] -> (RMSNorm) lm_head
+    embedding gather -> 32 x [ (RMSNorm) q|k|v -> {RoPE + cache append + attention over (shared prompt KV || per-beam
+    suffix) + split merge: one launch} -> o_proj + residual -> (RMSNorm) gate|up SwiGLU -> down + residual ] -> (RMSNorm) lm_head
 
 on the HBM-bound kernels of csrc/decode.cu (weights streamed once per token for all beams), captured ONCE into a CUDA graph
 and replayed per token; the position / suffix length lives in device memory.  The prompt's K/V (written by the prefill
@@ -71,10 +71,15 @@ class DecodeEngine:
         self.prefix_mask = None
         if prefix_mask is not None and not bool(prefix_mask.all()):
             self.prefix_mask = prefix_mask.reshape(-1)[:self.Sp].to(torch.uint8).contiguous()
+        # key splits: <= 128 prompt keys per CTA, so that all of a CTA's prompt K/V is requested in one batch of loads
         if n_split is None:
-            n_split = int(os.environ.get("STLLM_DECODE_SPLITS", "4"))
-        self.n_split = max(1, n_split)
-        self.ws = ops.decode_attention_workspace(self.H, self.n_split, dev)
+            n_split = int(os.environ.get("STLLM_DECODE_SPLITS", "0")) or (self.Sp + 127) // 128
+        self.n_split = min(max(1, n_split), 16)
+        self.fused_attn = os.environ.get("STLLM_DECODE_FUSED_ATTN", "1") != "0"
+        if self.fused_attn:
+            self.ws = ops.decode_attention_fused_workspace(self.H, self.n_split, dev)
+        else:
+            self.ws = ops.decode_attention_workspace(self.H, self.n_split, dev)
         self.steps_done = 0
         self.graph = None
         if use_graph is None:
@@ -94,11 +99,16 @@ class DecodeEngine:
                 ops.decode_linear(x, L["w_qkv"], self.qkv, norm_mode=ops.NORM_RMS, norm_eps=self.eps)
             else:
                 ops.decode_linear(x, L["w_qkv"], self.qkv, norm_mode=2, norm_weight=L["ln1"], norm_eps=self.eps)
-            ops.decode_rope_append(self.qkv, self.cos_t, self.sin_t, self.Sp, self.n_gen, self.ks[li], self.vs[li],
-                                   self.src, self.H, self.d)
-            ops.decode_attention(self.qkv, self.kp[li], self.vp[li], self.ks[li], self.vs[li], self.src, self.n_gen,
-                                 self.a, self.ws, self.H, self.d, scale, n_split=self.n_split,
-                                 prefix_mask=self.prefix_mask)
+            if self.fused_attn:
+                ops.decode_attention_fused(self.qkv, self.cos_t, self.sin_t, self.kp[li], self.vp[li], self.ks[li],
+                                           self.vs[li], self.src, self.n_gen, self.a, self.ws, self.H, self.d, scale,
+                                           n_split=self.n_split, prefix_mask=self.prefix_mask)
+            else:
+                ops.decode_rope_append(self.qkv, self.cos_t, self.sin_t, self.Sp, self.n_gen, self.ks[li],
+                                       self.vs[li], self.src, self.H, self.d)
+                ops.decode_attention(self.qkv, self.kp[li], self.vp[li], self.ks[li], self.vs[li], self.src,
+                                     self.n_gen, self.a, self.ws, self.H, self.d, scale, n_split=self.n_split,
+                                     prefix_mask=self.prefix_mask)
             ops.decode_linear(self.a, L["w_o"], x, residual=x)
             if fuse:
                 ops.decode_linear(x, L["w_gu"], self.g, norm_mode=ops.NORM_RMS, norm_eps=self.eps,

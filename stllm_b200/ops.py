@@ -458,3 +458,37 @@ def decode_attention(q, k_prefix, v_prefix, k_suffix, v_suffix, src, n_gen, out,
     _lib.check(rc, "stllm_decode_attention_f16")
     launch_count += 2
     return out
+
+
+def decode_attention_fused_workspace(nheads, n_split, device):
+    """zeroed workspace (split partials + per-head tickets) of decode_attention_fused"""
+    n = int(_lib.load().stllm_decode_attention_fused_workspace_bytes(nheads, n_split))
+    return torch.zeros(n // 4, dtype=torch.float32, device=device)
+
+
+def decode_attention_fused(qkv, cos_t, sin_t, k_prefix, v_prefix, k_suffix, v_suffix, src, n_gen, out, workspace, nheads,
+                           head_dim, scale, n_split=4, prefix_mask=None):
+    """decode_rope_append + decode_attention in one launch: qkv [R, 3*H*D] un-roped (left unchanged); the new token's
+    roped k and v are appended to the suffix caches at token n_gen[0]; out [R, H*D]."""
+    global launch_count
+    _need_cuda(qkv, cos_t, sin_t, k_prefix, v_prefix, k_suffix, v_suffix, src, n_gen, out, workspace, prefix_mask)
+    R = qkv.shape[0]
+    HD = nheads * head_dim
+    assert qkv.dim() == 2 and qkv.stride(1) == 1 and qkv.shape[1] == 3 * HD and out.shape == (R, HD) and out.stride(1) == 1
+    assert k_prefix.dim() == 2 and k_prefix.stride(1) == 1 and k_prefix.shape[1] == HD
+    assert v_prefix.shape == k_prefix.shape and v_prefix.stride() == k_prefix.stride()
+    assert k_suffix.dim() == 3 and k_suffix.stride(2) == 1 and k_suffix.shape[2] == HD and k_suffix.shape[0] >= R
+    assert v_suffix.shape == k_suffix.shape and v_suffix.stride() == k_suffix.stride()
+    assert n_gen.dtype == torch.int32 and src.dtype == torch.int32 and src.stride(1) == 1 and src.shape[0] >= R
+    assert cos_t.dtype == torch.float32 and cos_t.shape[1] == head_dim // 2 and cos_t.is_contiguous()
+    if prefix_mask is not None:
+        assert prefix_mask.dtype == torch.uint8 and prefix_mask.is_contiguous() and prefix_mask.numel() == k_prefix.shape[0]
+    rc = _lib.load().stllm_decode_attention_fused_f16(
+        _ptr(qkv), qkv.stride(0), _ptr(cos_t), _ptr(sin_t), cos_t.shape[0], _ptr(k_prefix), _ptr(v_prefix),
+        k_prefix.stride(0), _ptr(prefix_mask), k_prefix.shape[0], _ptr(k_suffix), _ptr(v_suffix), k_suffix.stride(0),
+        k_suffix.stride(1), k_suffix.shape[1], _ptr(src), src.stride(0), _ptr(n_gen), _ptr(out), out.stride(0),
+        _ptr(workspace), workspace.numel() * workspace.element_size(), R, nheads, head_dim, n_split, float(scale),
+        _stream())
+    _lib.check(rc, "stllm_decode_attention_fused_f16")
+    launch_count += 1
+    return out
