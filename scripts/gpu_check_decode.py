@@ -321,6 +321,55 @@ def time_decode(layers, beams, S=576, steps=48, general=True):
     return res
 
 
+AB_VARIANTS = (("default", {}), ("unfused_attention", {"STLLM_DECODE_FUSED_ATTN": "0"}),
+               ("no_weight_prefetch", {"STLLM_DECODE_PREFETCH": "0"}), ("no_xdirect", {"STLLM_DECODE_XDIRECT": "0"}),
+               ("splits_4", {"STLLM_DECODE_SPLITS": "4"}), ("splits_8", {"STLLM_DECODE_SPLITS": "8"}))
+
+
+def time_decode_ab(layers, beams, S=576, steps=32, rounds=3):
+    """A/B of the engine's switches inside ONE process on ONE model: every variant captures its own graph; timing rounds
+    alternate between the variants (boxes and clocks differ from run to run, so only same-process numbers compare)"""
+    from stllm_b200.decode import DecodeEngine
+    from stllm_b200.pipeline import build_model
+    model = build_model(llama_layers=layers, vit_depth=1, qformer_layers=1, device=torch.device("cuda", 0), seed=0)
+    g = torch.Generator(device=dev).manual_seed(5)
+    emb = (torch.randn(1, S, 4096, device=dev, generator=g) * 0.05).half()
+    lmax = 8 + steps * rounds + 8
+    out = model(samples=None, inputs_embeds=emb, use_cache=True, cache_max_len=S + lmax)
+    tok = torch.randint(3, 32000, (beams,), device=dev, generator=g)
+    idx = torch.arange(beams, device=dev).flip(0)
+    engines = []
+    for name, env in AB_VARIANTS:
+        os.environ.update(env)
+        engines.append((name, DecodeEngine(model, out.past_key_values, S, beams, lmax)))
+        for k in env:
+            os.environ.pop(k)
+    res = {name: [] for name, _ in engines}
+    for name, eng in engines:
+        for _ in range(8):
+            eng.step(tok)
+    for _ in range(rounds):
+        for name, eng in engines:
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                if beams > 1:
+                    eng.reorder(idx)
+                eng.step(tok)
+            e1.record()
+            torch.cuda.synchronize()
+            res[name].append(round(e0.elapsed_time(e1) / steps, 4))
+    cfg = model.config
+    wbytes = layers * (4 * 4096 * 4096 + 3 * 4096 * cfg.intermediate_size) * 2 + cfg.vocab_size * 4096 * 2
+    summary = dict(layers=layers, beams=beams, prefix=S, weight_gb=wbytes / 1e9, ms_per_token=res,
+                   best_gbs={k: round(wbytes / 1e9 / (min(v) * 1e-3)) for k, v in res.items()})
+    print("TIME decode_ab " + json.dumps(summary), flush=True)
+    del engines, model
+    torch.cuda.empty_cache()
+    return summary
+
+
 def time_generate(layers, beams, S=576, new_tokens=64):
     """the public call: llm.generate(inputs_embeds=[1,S,4096], ...) end to end (prefill + graph capture + decode steps +
     host-side beam bookkeeping), decode engine vs the general-kernel route"""
@@ -427,6 +476,8 @@ def timings():
         if "--layers" in sys.argv:
             layers = int(sys.argv[sys.argv.index("--layers") + 1])
         dec = [time_decode(layers, 1), time_decode(layers, 5)]
+        if "--ab" in sys.argv:
+            dec += [time_decode_ab(layers, 1), time_decode_ab(layers, 5)]
         if "--generate" in sys.argv:
             dec += [time_generate(layers, 1), time_generate(layers, 5)]
         os.makedirs("gpurun_out", exist_ok=True)

@@ -1,14 +1,10 @@
 #!/bin/bash
-# Decode-engine checks on one B200: kernel + engine checks, timings, A/Bs (fused attention launch, weight prefetch), the
+# Decode-engine checks on one B200: kernel + engine checks, timings with same-process A/Bs of the engine's switches, the
 # generate tests, and an ncu launch list of an eager decode step.
 mkdir -p gpurun_out
-timeout 900 python scripts/gpu_check_decode.py --generate > gpurun_out/decode_check.log 2>&1
+timeout 1200 python scripts/gpu_check_decode.py --generate --ab > gpurun_out/decode_check.log 2>&1
 echo "decode check rc=$?"
 grep -E "FAIL|failures|TIME|Error|error" gpurun_out/decode_check.log | head -80
-DECODE_TIMING_TAG=_unfused STLLM_DECODE_FUSED_ATTN=0 timeout 600 python scripts/gpu_check_decode.py --time-only > gpurun_out/decode_time_unfused.log 2>&1
-echo "unfused rc=$?"; grep "TIME decode " gpurun_out/decode_time_unfused.log | tail -4
-DECODE_TIMING_TAG=_noprefetch STLLM_DECODE_PREFETCH=0 timeout 600 python scripts/gpu_check_decode.py --time-only > gpurun_out/decode_time_noprefetch.log 2>&1
-echo "noprefetch rc=$?"; grep "TIME decode " gpurun_out/decode_time_noprefetch.log | tail -4
 timeout 600 python -m pytest tests/test_generate_gpu.py tests/test_decode_gpu.py -x -q > gpurun_out/pytest_decode.log 2>&1
 echo "pytest rc=$?"; tail -5 gpurun_out/pytest_decode.log
 for B in 1 5; do

@@ -59,6 +59,13 @@ DEVI uint4 ld_stream(const __half* p) {
   asm volatile("ld.global.cs.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
 }
+DEVI uint4 ld_stream_nol1(const __half* p) {
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p));
+  return v;
+}
 DEVI void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 DEVI float dec_silu(float x) {
   float e, r;
@@ -69,11 +76,14 @@ DEVI float dec_silu(float x) {
 
 // DL_UNROLL 32-element steps are in flight per warp: 4 with two CTAs per SM (<= 64 registers), 8 when the staged
 // activations leave room for one CTA only (down_proj with several beams)
-template <int DL_UNROLL, int MIN_CTAS>
+// X_DIRECT: the activations are NOT staged in shared memory but read through L1 (read-only path) by every lane, 16 bytes
+// per step -- for wide inputs with several beams (down_proj: 5 x 11008 halves = 110 KB would leave room for one CTA per SM
+// only).  No normalisation in this mode.  The weights bypass L1 (no_allocate) so the activations stay resident there.
+template <int DL_UNROLL, int MIN_CTAS, bool X_DIRECT>
 __global__ void __launch_bounds__(DL_THREADS, MIN_CTAS) decode_linear_kernel(const DecLinParams p) {
   extern __shared__ __align__(16) uint8_t dl_smem[];
   __half* xs = reinterpret_cast<__half*>(dl_smem);                                   // [R][Kp]
-  float* part = reinterpret_cast<float*>(dl_smem + (size_t)p.R * p.Kp * 2);          // [2][16 warps][8 x 16]
+  float* part = reinterpret_cast<float*>(dl_smem + (X_DIRECT ? (size_t)0 : (size_t)p.R * p.Kp * 2));   // [2][16 warps][8 x 16]
   float* ssq_s = part + 2 * DL_WARPS * 128;                                          // [16]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
   const int nblk = (p.N + 15) >> 4;
@@ -92,7 +102,7 @@ __global__ void __launch_bounds__(DL_THREADS, MIN_CTAS) decode_linear_kernel(con
   }
   pdl_wait();
   // ---- stage the activations: one flat, coalesced copy by all threads (independent 16-byte loads, one round trip) ----
-  {
+  if (!X_DIRECT) {
     const int nvec = p.K >> 3;
     const int total = p.R * nvec;
     for (int f0 = tid; f0 < total; f0 += DL_THREADS * 4) {
@@ -156,7 +166,8 @@ __global__ void __launch_bounds__(DL_THREADS, MIN_CTAS) decode_linear_kernel(con
       }
     }
   }
-  const __half* xr = xs + (size_t)(g < p.R ? g : 0) * p.Kp + 8 * t;
+  const __half* xr = X_DIRECT ? p.x + (long long)(g < p.R ? g : 0) * p.ldx + 8 * t
+                              : xs + (size_t)(g < p.R ? g : 0) * p.Kp + 8 * t;
   int it = 0;
   for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x, ++it) {
     const int n0 = blk << 4;
@@ -170,8 +181,8 @@ __global__ void __launch_bounds__(DL_THREADS, MIN_CTAS) decode_linear_kernel(con
       for (int u = 0; u < DL_UNROLL; ++u) {
         const int s = s0 + u * DL_WARPS;
         if (s < nsteps) {
-          wa[u] = ld_stream(wA + (s << 5));
-          wb[u] = ld_stream(wB + (s << 5));
+          wa[u] = X_DIRECT ? ld_stream_nol1(wA + (s << 5)) : ld_stream(wA + (s << 5));
+          wb[u] = X_DIRECT ? ld_stream_nol1(wB + (s << 5)) : ld_stream(wB + (s << 5));
         } else {
           wa[u] = make_uint4(0u, 0u, 0u, 0u);
           wb[u] = make_uint4(0u, 0u, 0u, 0u);
@@ -180,7 +191,8 @@ __global__ void __launch_bounds__(DL_THREADS, MIN_CTAS) decode_linear_kernel(con
 #pragma unroll
       for (int u = 0; u < DL_UNROLL; ++u) {
         const int s = s0 + u * DL_WARPS;
-        const uint4 xa = *reinterpret_cast<const uint4*>(xr + ((s < nsteps ? s : 0) << 5));
+        const uint4 xa = X_DIRECT ? __ldg(reinterpret_cast<const uint4*>(xr + ((s < nsteps ? s : 0) << 5)))
+                                  : *reinterpret_cast<const uint4*>(xr + ((s < nsteps ? s : 0) << 5));
         mma16816(accA, xa.x, 0u, xa.y, 0u, wa[u].x, wa[u].y);
         mma16816(accA, xa.z, 0u, xa.w, 0u, wa[u].z, wa[u].w);
         mma16816(accB, xa.x, 0u, xa.y, 0u, wb[u].x, wb[u].y);
@@ -632,12 +644,14 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attention_fused_kernel(c
     const float cs = __ldg(p.cos_t + (long long)pos * 64 + i), sn = __ldg(p.sin_t + (long long)pos * 64 + i);
     const __half* row = p.qkv + (long long)r * p.ldq + (long long)h * DA_D;
     const float lo = __half2float(row[i]), hi = __half2float(row[i + 64]);
-    qs[r * DA_D + i] = __half2float(__float2half_rn(lo * cs - hi * sn));        // rounding of rope_kernel
-    qs[r * DA_D + i + 64] = __half2float(__float2half_rn(hi * cs + lo * sn));
+    // explicit contraction = what nvcc emits for rope_kernel (elementwise.cu): fma(lo, c, -rn(hi s)), fma(hi, c, rn(lo s))
+    qs[r * DA_D + i] = __half2float(__float2half_rn(__fmaf_rn(lo, cs, -__fmul_rn(hi, sn))));
+    qs[r * DA_D + i + 64] = __half2float(__float2half_rn(__fmaf_rn(hi, cs, __fmul_rn(lo, sn))));
     if (last_split) {
       const long long HD = (long long)p.H * DA_D;
       const float klo = __half2float(row[HD + i]), khi = __half2float(row[HD + i + 64]);
-      const __half rlo = __float2half_rn(klo * cs - khi * sn), rhi = __float2half_rn(khi * cs + klo * sn);
+      const __half rlo = __float2half_rn(__fmaf_rn(klo, cs, -__fmul_rn(khi, sn)));
+      const __half rhi = __float2half_rn(__fmaf_rn(khi, cs, __fmul_rn(klo, sn)));
       const __half vlo = row[2 * HD + i], vhi = row[2 * HD + i + 64];
       kn[r * DA_D + i] = __half2float(rlo);
       kn[r * DA_D + i + 64] = __half2float(rhi);
@@ -935,27 +949,32 @@ extern "C" int stllm_decode_linear_f16(const void* x, long long ldx, const void*
   p.R = R; p.N = N; p.K = K;
   p.Kp = K + (((K * 2) % 128 == 64) ? 0 : 32);
   p.norm_mode = norm_mode; p.epi = epilogue; p.eps = norm_eps;
-  static const int prefetch = env_int_dec("STLLM_DECODE_PREFETCH", 1);
+  const int prefetch = env_int_dec("STLLM_DECODE_PREFETCH", 1);   // read per call: A/B inside one process
   p.prefetch = prefetch;
-  const size_t smem = (size_t)R * p.Kp * 2 + (size_t)(2 * DL_WARPS * 128 + 16) * sizeof(float);
+  const size_t part_bytes = (size_t)(2 * DL_WARPS * 128 + 16) * sizeof(float);
+  size_t smem = (size_t)R * p.Kp * 2 + part_bytes;
   if (smem > (size_t)DL_SMEM_MAX) {
     stllm_set_last_error("stllm_decode_linear_f16: R=%d x K=%d activations do not fit in shared memory", R, K);
     return STLLM_ERR_UNSUPPORTED;
   }
   static bool configured = false;
   if (!configured) {
-    STLLM_CHECK_CUDA(cudaFuncSetAttribute(decode_linear_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DL_SMEM_MAX / 2));
-    STLLM_CHECK_CUDA(cudaFuncSetAttribute(decode_linear_kernel<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, DL_SMEM_MAX));
+    STLLM_CHECK_CUDA(cudaFuncSetAttribute(decode_linear_kernel<4, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DL_SMEM_MAX / 2));
+    STLLM_CHECK_CUDA(cudaFuncSetAttribute(decode_linear_kernel<8, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DL_SMEM_MAX));
     configured = true;
   }
+  const int direct_ok = env_int_dec("STLLM_DECODE_XDIRECT", 1);
   const int nblk = (N + 15) / 16;
   const bool two = smem <= (size_t)(DL_SMEM_MAX / 2);
-  int grid = num_sms_dec() * (two ? 2 : 1);
+  const bool direct = !two && norm_mode == 0 && direct_ok;
+  int grid = num_sms_dec() * ((two || direct) ? 2 : 1);
   if (grid > nblk) grid = nblk;
   if (two)
-    STLLM_CHECK_CUDA(stllm_launch(decode_linear_kernel<4, 2>, dim3(grid), dim3(DL_THREADS), smem, (cudaStream_t)stream, p));
+    STLLM_CHECK_CUDA(stllm_launch(decode_linear_kernel<4, 2, false>, dim3(grid), dim3(DL_THREADS), smem, (cudaStream_t)stream, p));
+  else if (direct)
+    STLLM_CHECK_CUDA(stllm_launch(decode_linear_kernel<4, 2, true>, dim3(grid), dim3(DL_THREADS), part_bytes, (cudaStream_t)stream, p));
   else
-    STLLM_CHECK_CUDA(stllm_launch(decode_linear_kernel<8, 1>, dim3(grid), dim3(DL_THREADS), smem, (cudaStream_t)stream, p));
+    STLLM_CHECK_CUDA(stllm_launch(decode_linear_kernel<8, 1, false>, dim3(grid), dim3(DL_THREADS), smem, (cudaStream_t)stream, p));
   return STLLM_OK;
 }
 
