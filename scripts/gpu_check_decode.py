@@ -322,8 +322,9 @@ def time_decode(layers, beams, S=576, steps=48, general=True):
 
 
 AB_VARIANTS = (("default", {}), ("unfused_attention", {"STLLM_DECODE_FUSED_ATTN": "0"}),
-               ("no_weight_prefetch", {"STLLM_DECODE_PREFETCH": "0"}), ("no_xdirect", {"STLLM_DECODE_XDIRECT": "0"}),
-               ("splits_4", {"STLLM_DECODE_SPLITS": "4"}), ("splits_8", {"STLLM_DECODE_SPLITS": "8"}))
+               ("no_weight_prefetch", {"STLLM_DECODE_PREFETCH": "0"}), ("prefetch_plus_l2", {"STLLM_DECODE_PREFETCH": "2"}),
+               ("no_xdirect", {"STLLM_DECODE_XDIRECT": "0"}), ("splits_2", {"STLLM_DECODE_SPLITS": "2"}),
+               ("splits_5", {"STLLM_DECODE_SPLITS": "5"}))
 
 
 def time_decode_ab(layers, beams, S=576, steps=32, rounds=3):

@@ -89,15 +89,40 @@ __global__ void __launch_bounds__(DL_THREADS, MIN_CTAS) decode_linear_kernel(con
   const int nblk = (p.N + 15) >> 4;
   const int nsteps = p.K >> 5;
   pdl_launch_dependents();
-  // The weights do not depend on the previous kernel: start pulling this CTA's first 16 rows into L2 while the
-  // predecessor drains and the activations are staged.
+  // The weights do not depend on the previous kernel: the first batch of this CTA's weight loads (DL_UNROLL steps of
+  // 2 x 16 bytes per lane: 64 KB per CTA) is requested BEFORE griddepcontrol.wait and stays in registers while the
+  // predecessor drains and the activations are staged -- HBM keeps streaming across the kernel boundary.  p.prefetch == 2
+  // additionally pulls the rest of the first 16 rows into L2.
+  uint4 wa[DL_UNROLL], wb[DL_UNROLL];
+  bool preloaded = false;
+  auto load_batch = [&](int blk, int s0) {
+    const int n0 = blk << 4;
+    const int rowA = n0 + g, rowB = n0 + 8 + g;
+    const __half* wA = p.W + (long long)(rowA < p.N ? rowA : 0) * p.ldw + 8 * t;
+    const __half* wB = p.W + (long long)(rowB < p.N ? rowB : 0) * p.ldw + 8 * t;
+#pragma unroll
+    for (int u = 0; u < DL_UNROLL; ++u) {
+      const int s = s0 + u * DL_WARPS;
+      if (s < nsteps) {
+        wa[u] = X_DIRECT ? ld_stream_nol1(wA + (s << 5)) : ld_stream(wA + (s << 5));
+        wb[u] = X_DIRECT ? ld_stream_nol1(wB + (s << 5)) : ld_stream(wB + (s << 5));
+      } else {
+        wa[u] = make_uint4(0u, 0u, 0u, 0u);
+        wb[u] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+  };
   if (p.prefetch && (int)blockIdx.x < nblk) {
-    const int sectors_per_row = p.K >> 4;   // 32-byte sectors
-    const int total = 16 * sectors_per_row;
-    const int n0 = (int)blockIdx.x << 4;
-    for (int i = tid; i < total; i += DL_THREADS) {
-      const int r = i / sectors_per_row, s = i - r * sectors_per_row;
-      if (n0 + r < p.N) prefetch_l2(p.W + (long long)(n0 + r) * p.ldw + (s << 4));
+    load_batch(blockIdx.x, warp);
+    preloaded = true;
+    if (p.prefetch == 2) {
+      const int sectors_per_row = p.K >> 4;   // 32-byte sectors
+      const int total = 16 * sectors_per_row;
+      const int n0 = (int)blockIdx.x << 4;
+      for (int i = tid; i < total; i += DL_THREADS) {
+        const int r = i / sectors_per_row, s = i - r * sectors_per_row;
+        if (n0 + r < p.N) prefetch_l2(p.W + (long long)(n0 + r) * p.ldw + (s << 4));
+      }
     }
   }
   pdl_wait();
@@ -171,23 +196,10 @@ __global__ void __launch_bounds__(DL_THREADS, MIN_CTAS) decode_linear_kernel(con
   int it = 0;
   for (int blk = blockIdx.x; blk < nblk; blk += gridDim.x, ++it) {
     const int n0 = blk << 4;
-    const int rowA = n0 + g, rowB = n0 + 8 + g;
-    const __half* wA = p.W + (long long)(rowA < p.N ? rowA : 0) * p.ldw + 8 * t;
-    const __half* wB = p.W + (long long)(rowB < p.N ? rowB : 0) * p.ldw + 8 * t;
     float accA[4] = {0.f, 0.f, 0.f, 0.f}, accB[4] = {0.f, 0.f, 0.f, 0.f};
     for (int s0 = warp; s0 < nsteps; s0 += DL_WARPS * DL_UNROLL) {
-      uint4 wa[DL_UNROLL], wb[DL_UNROLL];
-#pragma unroll
-      for (int u = 0; u < DL_UNROLL; ++u) {
-        const int s = s0 + u * DL_WARPS;
-        if (s < nsteps) {
-          wa[u] = X_DIRECT ? ld_stream_nol1(wA + (s << 5)) : ld_stream(wA + (s << 5));
-          wb[u] = X_DIRECT ? ld_stream_nol1(wB + (s << 5)) : ld_stream(wB + (s << 5));
-        } else {
-          wa[u] = make_uint4(0u, 0u, 0u, 0u);
-          wb[u] = make_uint4(0u, 0u, 0u, 0u);
-        }
-      }
+      if (!preloaded) load_batch(blk, s0);
+      preloaded = false;
 #pragma unroll
       for (int u = 0; u < DL_UNROLL; ++u) {
         const int s = s0 + u * DL_WARPS;
@@ -198,6 +210,11 @@ __global__ void __launch_bounds__(DL_THREADS, MIN_CTAS) decode_linear_kernel(con
         mma16816(accB, xa.x, 0u, xa.y, 0u, wb[u].x, wb[u].y);
         mma16816(accB, xa.z, 0u, xa.w, 0u, wb[u].z, wb[u].w);
       }
+    }
+    // the next block's first batch is requested before this block's reduction (barrier + epilogue) starts
+    if (p.prefetch && blk + (int)gridDim.x < nblk) {
+      load_batch(blk + gridDim.x, warp);
+      preloaded = true;
     }
     // D[beam g][weight row]: lane holds rows n0 + 2t, 2t+1 (group A) and n0 + 8 + 2t, 2t+1 (group B) of beam g
     float* pw = part + ((it & 1) * DL_WARPS + warp) * 128 + g * 16 + 2 * t;
