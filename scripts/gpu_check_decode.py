@@ -128,7 +128,7 @@ def attn_case(R, H, Sp, n_gen, l_max, n_split, mask=False):
                   out, ref, atol=3e-3, rtol=3e-3)
 
 
-def attn_fused_case(R, H, Sp, n_gen, l_max, n_split, mask=False, repeats=2):
+def attn_fused_case(R, H, Sp, n_gen, l_max, n_split, mask=False, repeats=2, prefetch=False):
     """rope + append + attention + merge in one launch, against the unfused pieces' references; launched `repeats` times on
     the same workspace (the ticket counters must reset themselves)"""
     HD = H * 128
@@ -150,8 +150,9 @@ def attn_fused_case(R, H, Sp, n_gen, l_max, n_split, mask=False, repeats=2):
     qkv_before = qkv.clone()
     for it in range(repeats):
         out = torch.full((R, HD), float("nan"), device=dev, dtype=torch.float16)
+        pf = torch.randn(1031, 1024, device=dev).half() if prefetch else None   # ~2 MB, not a multiple of the grid
         ops.decode_attention_fused(qkv, cos_t, sin_t, kp, vp, ks, vs, src, ng, out, ws, H, 128, scale, n_split=n_split,
-                                   prefix_mask=pm)
+                                   prefix_mask=pm, prefetch=pf)
         torch.cuda.synchronize()
         ok &= report(f"decode_attention_fused R={R} H={H} Sp={Sp} n_gen={n_gen} l_max={l_max} splits={n_split} "
                      f"mask={int(mask)} run {it}", out, ref, atol=3e-3, rtol=3e-3)
@@ -323,8 +324,8 @@ def time_decode(layers, beams, S=576, steps=48, general=True):
 
 AB_VARIANTS = (("default", {}), ("unfused_attention", {"STLLM_DECODE_FUSED_ATTN": "0"}),
                ("no_weight_prefetch", {"STLLM_DECODE_PREFETCH": "0"}), ("prefetch_plus_l2", {"STLLM_DECODE_PREFETCH": "2"}),
-               ("no_xdirect", {"STLLM_DECODE_XDIRECT": "0"}), ("splits_2", {"STLLM_DECODE_SPLITS": "2"}),
-               ("splits_5", {"STLLM_DECODE_SPLITS": "5"}))
+               ("no_xdirect", {"STLLM_DECODE_XDIRECT": "0"}), ("no_prefetch_next", {"STLLM_DECODE_PREFETCH_NEXT": "0"}),
+               ("splits_3", {"STLLM_DECODE_SPLITS": "3"}))
 
 
 def time_decode_ab(layers, beams, S=576, steps=32, rounds=3):
@@ -446,6 +447,7 @@ def main():
     attn_fused_case(3, 2, 5, 6, 8, 4)
     attn_fused_case(5, 32, 576, 0, 64, 5)
     attn_fused_case(5, 32, 576, 37, 64, 5, repeats=3)
+    attn_fused_case(5, 32, 576, 38, 64, 4, prefetch=True)
     attn_fused_case(5, 32, 577, 63, 64, 3, mask=True)      # > 128 prompt keys per split: second batch of loads
     attn_fused_case(8, 32, 1500, 299, 300, 12)
     attn_fused_case(8, 32, 1500, 299, 300, 4)

@@ -54,7 +54,8 @@ SIGNATURES = {
     "stllm_decode_attention_fused_workspace_bytes": [c_int, c_int],
     "stllm_decode_attention_fused_f16": [c_void_p, c_ll, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_ll, c_void_p,
                                          c_int, c_void_p, c_void_p, c_ll, c_ll, c_int, c_void_p, c_int, c_void_p,
-                                         c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_float, c_void_p],
+                                         c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_float, c_void_p, c_ll,
+                                         c_void_p],
     "stllm_decode_attention_f16": [c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_void_p, c_int, c_void_p, c_void_p, c_ll,
                                    c_ll, c_int, c_void_p, c_int, c_void_p, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int,
                                    c_int, c_int, c_float, c_void_p],

@@ -602,6 +602,8 @@ struct DecAttnFusedParams {
   long long ldo;
   float* ws;
   int* tickets;   // [H], zero before the first launch; reset by the merging CTA
+  const uint8_t* pf_ptr;   // optional: memory the NEXT kernel streams (o_proj weights) -> pulled into L2 while this
+  long long pf_bytes;      // kernel's latency chain leaves HBM idle
   int R, H, Sp, NS, cap, l_max, max_pos;
   float scale;
 };
@@ -638,6 +640,12 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attention_fused_kernel(c
       kv0[u] = __ldg(reinterpret_cast<const uint4*>(p.kp + (long long)(pk0 + i) * p.p_stride + hoff));
       vv0[u] = __ldg(reinterpret_cast<const uint4*>(p.vp + (long long)(pk0 + i) * p.p_stride + hoff));
     }
+  }
+  if (p.pf_ptr != nullptr) {
+    const long long sectors = p.pf_bytes >> 5;
+    const long long nthreads = (long long)gridDim.x * gridDim.y * DA_THREADS;
+    const long long me = ((long long)blockIdx.y * gridDim.x + blockIdx.x) * DA_THREADS + tid;
+    for (long long i = me; i < sectors; i += nthreads) prefetch_l2(p.pf_ptr + (i << 5));
   }
   pdl_wait();
   const int n_gen = *p.n_gen;
@@ -714,7 +722,9 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attention_fused_kernel(c
         float kf[8];
         half8_to_float(kv[u], kf);
         const bool masked = p.p_mask != nullptr && i < np && p.p_mask[pk0 + i] == 0;
-        for (int r = 0; r < p.R; ++r) {
+#pragma unroll
+        for (int r = 0; r < DL_RMAX; ++r) {
+          if (r >= p.R) break;
           const float4 q0 = *reinterpret_cast<const float4*>(qs + r * DA_D + 8 * c);
           const float4 q1 = *reinterpret_cast<const float4*>(qs + r * DA_D + 8 * c + 4);
           float d = q0.x * kf[0];
@@ -988,9 +998,10 @@ extern "C" int stllm_decode_linear_f16(const void* x, long long ldx, const void*
   if (grid > nblk) grid = nblk;
   if (two)
     STLLM_CHECK_CUDA(stllm_launch(decode_linear_kernel<4, 2, false>, dim3(grid), dim3(DL_THREADS), smem, (cudaStream_t)stream, p));
-  else if (direct)
+  else if (direct) {
+    p.prefetch = 0;   // the register preload spills in this variant
     STLLM_CHECK_CUDA(stllm_launch(decode_linear_kernel<4, 2, true>, dim3(grid), dim3(DL_THREADS), part_bytes, (cudaStream_t)stream, p));
-  else
+  } else
     STLLM_CHECK_CUDA(stllm_launch(decode_linear_kernel<8, 1, false>, dim3(grid), dim3(DL_THREADS), smem, (cudaStream_t)stream, p));
   return STLLM_OK;
 }
@@ -1075,8 +1086,10 @@ extern "C" int stllm_decode_attention_fused_f16(void* qkv, long long ldq, const 
                                                 long long s_tok_stride, int l_max, int* src, int src_ld,
                                                 const int* n_gen, void* out, long long ldo, void* workspace,
                                                 long long workspace_bytes, int R, int H, int D, int n_split,
-                                                float scale, void* stream) {
+                                                float scale, const void* prefetch_ptr, long long prefetch_bytes,
+                                                void* stream) {
   STLLM_CHECK_ARG(qkv && cos_t && sin_t && k_suffix && v_suffix && src && n_gen && out && workspace);
+  STLLM_CHECK_ARG(prefetch_bytes >= 0 && (((uintptr_t)prefetch_ptr) & 31) == 0);
   STLLM_CHECK_ARG(prefix_len == 0 || (k_prefix && v_prefix));
   STLLM_CHECK_ARG(R >= 1 && R <= DL_RMAX && H >= 1 && prefix_len >= 0 && l_max >= 1 && n_split >= 1 && n_split <= 64);
   STLLM_CHECK_ARG(ldq % 8 == 0 && ldq >= 3LL * H * D && p_stride % 8 == 0 && s_beam_stride % 8 == 0 &&
@@ -1099,6 +1112,8 @@ extern "C" int stllm_decode_attention_fused_f16(void* qkv, long long ldq, const 
   p.R = R; p.H = H; p.Sp = prefix_len; p.NS = n_split; p.l_max = l_max; p.max_pos = max_pos;
   p.cap = (((prefix_len + n_split - 1) / n_split + (l_max + n_split - 1) / n_split + 2) + 3) & ~3;
   p.scale = scale;
+  p.pf_ptr = prefetch_bytes > 0 ? (const uint8_t*)prefetch_ptr : nullptr;
+  p.pf_bytes = prefetch_bytes;
   const size_t smem = ((size_t)DL_RMAX * p.cap + (size_t)DA_WARPS * (R + 1) * DA_D + 3 * DL_RMAX * DA_D) * sizeof(float);
   if (smem > (size_t)DA_SMEM_MAX) {
     stllm_set_last_error("stllm_decode_attention_fused_f16: %d + %d keys over %d splits do not fit in shared memory",

@@ -81,6 +81,8 @@ class DecodeEngine:
                 n_split = min((self.Sp + 127) // 128, max(1, sms // self.H))
         self.n_split = min(max(1, n_split), 16)
         self.fused_attn = os.environ.get("STLLM_DECODE_FUSED_ATTN", "1") != "0"
+        # the attention launch moves few bytes: it also pulls the o_proj weights (33.5 MB << 126 MB L2) into L2
+        self.prefetch_next = os.environ.get("STLLM_DECODE_PREFETCH_NEXT", "1") != "0"
         if self.fused_attn:
             self.ws = ops.decode_attention_fused_workspace(self.H, self.n_split, dev)
         else:
@@ -107,7 +109,8 @@ class DecodeEngine:
             if self.fused_attn:
                 ops.decode_attention_fused(self.qkv, self.cos_t, self.sin_t, self.kp[li], self.vp[li], self.ks[li],
                                            self.vs[li], self.src, self.n_gen, self.a, self.ws, self.H, self.d, scale,
-                                           n_split=self.n_split, prefix_mask=self.prefix_mask)
+                                           n_split=self.n_split, prefix_mask=self.prefix_mask,
+                                           prefetch=L["w_o"] if self.prefetch_next else None)
             else:
                 ops.decode_rope_append(self.qkv, self.cos_t, self.sin_t, self.Sp, self.n_gen, self.ks[li],
                                        self.vs[li], self.src, self.H, self.d)
