@@ -208,6 +208,43 @@ class CpuReference:
 
 
 # ---------------------------------------------------------------------------------------------- main
+def decode_leg(model, peaks, dev, steps=48, S=T_FRAMES * Q_TOK + PROMPT_LEN):
+    """Secondary measurement (not the headline metric): the cached single-token steps that follow the prefill in every
+    harness of the reference (generate, num_beams 1 and 5), on the decode engine (csrc/decode.cu, one CUDA graph per
+    token).  The step is HBM-bound: achieved = weight bytes streamed per token / time, against the measured HBM peak."""
+    import torch
+    from stllm_b200.decode import DecodeEngine
+    cfg = model.config
+    C, F, V, nL = cfg.hidden_size, cfg.intermediate_size, cfg.vocab_size, cfg.num_hidden_layers
+    wbytes = (nL * (4 * C * C + 3 * C * F) + V * C) * 2
+    g = torch.Generator(device=dev).manual_seed(5)
+    emb = (torch.randn(1, S, C, device=dev, generator=g) * 0.05).half()
+    out = {"unit": "tokens/s", "prefix_len": S, "weight_bytes_per_token": wbytes, "peak_gbs": peaks["hbm"],
+           "bound": "hbm"}
+    for beams in (1, 5):
+        o = model(samples=None, inputs_embeds=emb, use_cache=True, cache_max_len=S + steps + 16)
+        eng = DecodeEngine(model, o.past_key_values, S, beams, steps + 16)
+        tok = torch.randint(3, V, (beams,), device=dev, generator=g)
+        idx = torch.arange(beams, device=dev).flip(0)
+        for _ in range(4):
+            eng.step(tok)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            if beams > 1:
+                eng.reorder(idx)
+            eng.step(tok)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out["beams_%d" % beams] = {"ms_per_token": ms, "tokens_per_s": 1e3 / ms, "achieved_gbs": wbytes / 1e9 / (ms * 1e-3),
+                                   "frac": wbytes / 1e9 / (ms * 1e-3) / peaks["hbm"],
+                                   "launches_per_token": eng.launches_per_step}
+        del eng, o
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -220,6 +257,8 @@ def main():
     ap.add_argument("--vit-depth", type=int, default=39)
     ap.add_argument("--qformer-layers", type=int, default=12)
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--decode", action="store_true",
+                    help="also time the decode steps that follow the prefill (SURVEY 8f rank 1) and add a 'decode' object")
     ap.add_argument("--streams", type=int, default=1,
                     help="experiment: independent steps replayed round-robin on this many CUDA streams (value only)")
     args = ap.parse_args()
@@ -449,6 +488,8 @@ def main():
         fps, sample, _ = cpu.run()
         line["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cpu.threads, "kind": "port",
                                 "sample": sample}
+    if args.decode and world == 1:
+        line["decode"] = decode_leg(model, peaks, dev)
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -324,7 +324,7 @@ def time_decode(layers, beams, S=576, steps=48, general=True):
 
 AB_VARIANTS = (("default", {}), ("unfused_attention", {"STLLM_DECODE_FUSED_ATTN": "0"}),
                ("no_weight_prefetch", {"STLLM_DECODE_PREFETCH": "0"}), ("prefetch_plus_l2", {"STLLM_DECODE_PREFETCH": "2"}),
-               ("no_xdirect", {"STLLM_DECODE_XDIRECT": "0"}), ("no_prefetch_next", {"STLLM_DECODE_PREFETCH_NEXT": "0"}),
+               ("xdirect", {"STLLM_DECODE_XDIRECT": "1"}), ("no_prefetch_next", {"STLLM_DECODE_PREFETCH_NEXT": "0"}),
                ("splits_3", {"STLLM_DECODE_SPLITS": "3"}))
 
 

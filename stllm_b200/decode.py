@@ -63,8 +63,8 @@ class DecodeEngine:
         self.logits = torch.zeros(R, cfg.vocab_size, **f16)
         self.n_gen = torch.zeros(1, dtype=torch.int32, device=dev)
         self.src = torch.zeros(R, self.Lmax, dtype=torch.int32, device=dev)
-        self.ks = torch.zeros(nL, R, self.Lmax, C, **f16)
-        self.vs = torch.zeros(nL, R, self.Lmax, C, **f16)
+        self.ks = torch.empty(nL, R, self.Lmax, C, **f16)   # every slot is written before it is read
+        self.vs = torch.empty(nL, R, self.Lmax, C, **f16)
         # the prompt's K/V stay where the prefill wrote them: [Sp, H*d] rows of batch element 0
         self.kp = [cache.k[li][0, :self.Sp].reshape(self.Sp, C) for li in range(nL)]
         self.vp = [cache.v[li][0, :self.Sp].reshape(self.Sp, C) for li in range(nL)]

@@ -122,8 +122,11 @@ def generate(model, inputs_embeds=None, input_ids=None, max_new_tokens=20, stopp
         logp = lg.log_softmax(dim=-1) + beam_scores[:, None]
         V = logp.shape[1]
         top_s, top_i = logp.view(-1).topk(2 * nb)
+        # one device->host transfer (one synchronisation) for the 2*nb candidates; indices are exact in float64
+        cand = torch.stack([top_s.double(), top_i.double()]).cpu()
+        cand_s, cand_i = cand[0].tolist(), [int(v) for v in cand[1].tolist()]
         nb_idx, nb_tok, nb_score = [], [], []
-        for rank, (s, i) in enumerate(zip(top_s.tolist(), top_i.tolist())):
+        for rank, (s, i) in enumerate(zip(cand_s, cand_i)):
             b, t = i // V, i % V
             if t in eos_ids:
                 if rank >= nb:
@@ -139,12 +142,12 @@ def generate(model, inputs_embeds=None, input_ids=None, max_new_tokens=20, stopp
             if len(nb_idx) == nb:
                 break
         if len(hyps) >= nb:
-            best_possible = top_s.max().item() / (cur_len ** length_penalty)
+            best_possible = max(cand_s) / (cur_len ** length_penalty)
             if worst >= best_possible:
                 done = True
-        idx = torch.tensor(nb_idx, device=dev)
-        tok = torch.tensor(nb_tok, device=dev)
-        beam_scores = torch.tensor(nb_score, device=dev)
+        # one host->device transfer for (source beam, token, score) of the surviving beams
+        pk = torch.tensor([nb_idx, nb_tok, nb_score], dtype=torch.float64).to(dev, non_blocking=True)
+        idx, tok, beam_scores = pk[0].long(), pk[1].long(), pk[2].float()
         seqs = torch.cat([seqs[idx], tok[:, None]], dim=1)
         if done or _stopped(stopping_criteria, seqs[:1], lg) or step + 1 == n_steps:
             break
