@@ -221,7 +221,8 @@ def decode_leg(model, peaks, dev, steps=48, S=T_FRAMES * Q_TOK + PROMPT_LEN):
     emb = (torch.randn(1, S, C, device=dev, generator=g) * 0.05).half()
     out = {"unit": "tokens/s", "prefix_len": S, "weight_bytes_per_token": wbytes, "peak_gbs": peaks["hbm"],
            "bound": "hbm"}
-    for beams in (1, 5):
+    order = [int(v) for v in os.environ.get("STLLM_BENCH_DECODE_BEAMS", "1,5").split(",")]
+    for beams in order:
         o = model(samples=None, inputs_embeds=emb, use_cache=True, cache_max_len=S + steps + 16)
         eng = DecodeEngine(model, o.past_key_values, S, beams, steps + 16)
         tok = torch.randint(3, V, (beams,), device=dev, generator=g)

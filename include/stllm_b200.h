@@ -218,8 +218,9 @@ int stllm_decode_attention_f16(const void* q, long long ldq, const void* k_prefi
  * caches (and src[r, *n_gen] = r) and scores that key from shared memory; the last CTA of a head to finish merges the
  * splits (atomic ticket, reset for the next launch).  qkv is NOT modified.  The workspace holds the split partials and
  * the tickets: stllm_decode_attention_fused_workspace_bytes(H, n_split) bytes, ZEROED once by the caller.
- * prefetch_ptr / prefetch_bytes (optional, 32-byte aligned): static memory the NEXT kernel will stream (the o_proj
- * weights); it is pulled into L2 with prefetch.global.L2 while this kernel's short latency chain leaves HBM idle. */
+ * prefetch_ptr / prefetch_bytes, prefetch_ptr2 / prefetch_bytes2 (optional, 16-byte aligned): static memory the NEXT
+ * kernels will stream (the o_proj weights, the head of the gate|up weights); pulled into L2 with
+ * cp.async.bulk.prefetch.L2 while this kernel's short latency chain leaves HBM idle. */
 long long stllm_decode_attention_fused_workspace_bytes(int H, int n_split);
 int stllm_decode_attention_fused_f16(void* qkv, long long ldq, const float* cos_t, const float* sin_t, int max_pos,
                                      const void* k_prefix, const void* v_prefix, long long p_stride,
@@ -227,7 +228,8 @@ int stllm_decode_attention_fused_f16(void* qkv, long long ldq, const float* cos_
                                      long long s_beam_stride, long long s_tok_stride, int l_max, int* src, int src_ld,
                                      const int* n_gen, void* out, long long ldo, void* workspace,
                                      long long workspace_bytes, int R, int H, int D, int n_split, float scale,
-                                     const void* prefetch_ptr, long long prefetch_bytes, void* stream);
+                                     const void* prefetch_ptr, long long prefetch_bytes, const void* prefetch_ptr2,
+                                     long long prefetch_bytes2, void* stream);
 
 #ifdef __cplusplus
 }

@@ -323,9 +323,9 @@ def time_decode(layers, beams, S=576, steps=48, general=True):
 
 
 AB_VARIANTS = (("default", {}), ("unfused_attention", {"STLLM_DECODE_FUSED_ATTN": "0"}),
-               ("no_weight_prefetch", {"STLLM_DECODE_PREFETCH": "0"}), ("prefetch_plus_l2", {"STLLM_DECODE_PREFETCH": "2"}),
-               ("xdirect", {"STLLM_DECODE_XDIRECT": "1"}), ("no_prefetch_next", {"STLLM_DECODE_PREFETCH_NEXT": "0"}),
-               ("splits_3", {"STLLM_DECODE_SPLITS": "3"}))
+               ("no_weight_prefetch", {"STLLM_DECODE_PREFETCH": "0"}), ("no_prefetch_next", {"STLLM_DECODE_PREFETCH_NEXT": "0"}),
+               ("prefetch_gu_0mb", {"STLLM_DECODE_PREFETCH_GU_MB": "0"}), ("prefetch_gu_24mb", {"STLLM_DECODE_PREFETCH_GU_MB": "24"}),
+               ("prefetch_gu_80mb", {"STLLM_DECODE_PREFETCH_GU_MB": "80"}))
 
 
 def time_decode_ab(layers, beams, S=576, steps=32, rounds=3):
@@ -367,6 +367,45 @@ def time_decode_ab(layers, beams, S=576, steps=32, rounds=3):
     summary = dict(layers=layers, beams=beams, prefix=S, weight_gb=wbytes / 1e9, ms_per_token=res,
                    best_gbs={k: round(wbytes / 1e9 / (min(v) * 1e-3)) for k, v in res.items()})
     print("TIME decode_ab " + json.dumps(summary), flush=True)
+    del engines, model
+    torch.cuda.empty_cache()
+    return summary
+
+
+def time_decode_skip(layers, beams, S=576, steps=32, rounds=2):
+    """in-graph cost of each kernel kind: the step timed with one kind left out (debug_skip), same process, alternating"""
+    from stllm_b200.decode import DecodeEngine
+    from stllm_b200.pipeline import build_model
+    model = build_model(llama_layers=layers, vit_depth=1, qformer_layers=1, device=torch.device("cuda", 0), seed=0)
+    g = torch.Generator(device=dev).manual_seed(5)
+    emb = (torch.randn(1, S, 4096, device=dev, generator=g) * 0.05).half()
+    lmax = 8 + steps * rounds + 8
+    out = model(samples=None, inputs_embeds=emb, use_cache=True, cache_max_len=S + lmax)
+    tok = torch.randint(3, 32000, (beams,), device=dev, generator=g)
+    idx = torch.arange(beams, device=dev).flip(0)
+    kinds = ("", "qkv", "attn", "o", "gu", "down")
+    engines = [(k or "full", DecodeEngine(model, out.past_key_values, S, beams, lmax, debug_skip=(k,) if k else ()))
+               for k in kinds]
+    res = {name: [] for name, _ in engines}
+    for name, eng in engines:
+        for _ in range(8):
+            eng.step(tok)
+    for _ in range(rounds):
+        for name, eng in engines:
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                if beams > 1:
+                    eng.reorder(idx)
+                eng.step(tok)
+            e1.record()
+            torch.cuda.synchronize()
+            res[name].append(e0.elapsed_time(e1) / steps)
+    full = min(res["full"])
+    per_launch = {k: round((full - min(v)) / layers * 1e3, 2) for k, v in res.items() if k != "full"}
+    summary = dict(layers=layers, beams=beams, full_ms=round(full, 4), in_graph_us_per_launch=per_launch)
+    print("TIME decode_skip " + json.dumps(summary), flush=True)
     del engines, model
     torch.cuda.empty_cache()
     return summary

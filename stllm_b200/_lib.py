@@ -55,7 +55,7 @@ SIGNATURES = {
     "stllm_decode_attention_fused_f16": [c_void_p, c_ll, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_ll, c_void_p,
                                          c_int, c_void_p, c_void_p, c_ll, c_ll, c_int, c_void_p, c_int, c_void_p,
                                          c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_int, c_float, c_void_p, c_ll,
-                                         c_void_p],
+                                         c_void_p, c_ll, c_void_p],
     "stllm_decode_attention_f16": [c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_void_p, c_int, c_void_p, c_void_p, c_ll,
                                    c_ll, c_int, c_void_p, c_int, c_void_p, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int,
                                    c_int, c_int, c_float, c_void_p],

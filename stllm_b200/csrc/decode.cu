@@ -66,6 +66,10 @@ DEVI uint4 ld_stream_nol1(const __half* p) {
                : "l"(p));
   return v;
 }
+// one instruction pulls `bytes` (multiple of 16) into L2
+DEVI void prefetch_l2_bulk(const void* p, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 DEVI void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 DEVI float dec_silu(float x) {
   float e, r;
@@ -602,8 +606,8 @@ struct DecAttnFusedParams {
   long long ldo;
   float* ws;
   int* tickets;   // [H], zero before the first launch; reset by the merging CTA
-  const uint8_t* pf_ptr;   // optional: memory the NEXT kernel streams (o_proj weights) -> pulled into L2 while this
-  long long pf_bytes;      // kernel's latency chain leaves HBM idle
+  const uint8_t* pf_ptr[2];   // optional: memory the NEXT kernels stream (o_proj weights, the head of gate|up) -> pulled
+  long long pf_bytes[2];      // into L2 while this kernel's latency chain leaves HBM idle
   int R, H, Sp, NS, cap, l_max, max_pos;
   float scale;
 };
@@ -641,11 +645,21 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attention_fused_kernel(c
       vv0[u] = __ldg(reinterpret_cast<const uint4*>(p.vp + (long long)(pk0 + i) * p.p_stride + hoff));
     }
   }
-  if (p.pf_ptr != nullptr) {
-    const long long sectors = p.pf_bytes >> 5;
-    const long long nthreads = (long long)gridDim.x * gridDim.y * DA_THREADS;
-    const long long me = ((long long)blockIdx.y * gridDim.x + blockIdx.x) * DA_THREADS + tid;
-    for (long long i = me; i < sectors; i += nthreads) prefetch_l2(p.pf_ptr + (i << 5));
+  // bulk L2 prefetch (8 KB per instruction, one lane per warp, consecutive warps of the grid take consecutive chunks)
+  if (lane == 0) {
+    constexpr long long CH = 8192;
+    const long long nwarps = (long long)gridDim.x * gridDim.y * DA_WARPS;
+    const long long me = ((long long)blockIdx.y * gridDim.x + blockIdx.x) + (long long)warp * gridDim.x * gridDim.y;
+#pragma unroll
+    for (int reg = 0; reg < 2; ++reg) {
+      if (p.pf_ptr[reg] != nullptr) {
+        const long long nch = (p.pf_bytes[reg] + CH - 1) / CH;
+        for (long long i = me; i < nch; i += nwarps) {
+          const long long left = p.pf_bytes[reg] - i * CH;
+          prefetch_l2_bulk(p.pf_ptr[reg] + i * CH, (uint32_t)((left < CH ? left : CH) & ~15LL));
+        }
+      }
+    }
   }
   pdl_wait();
   const int n_gen = *p.n_gen;
@@ -1109,9 +1123,10 @@ extern "C" int stllm_decode_attention_fused_f16(void* qkv, long long ldq, const 
                                                 const int* n_gen, void* out, long long ldo, void* workspace,
                                                 long long workspace_bytes, int R, int H, int D, int n_split,
                                                 float scale, const void* prefetch_ptr, long long prefetch_bytes,
-                                                void* stream) {
+                                                const void* prefetch_ptr2, long long prefetch_bytes2, void* stream) {
   STLLM_CHECK_ARG(qkv && cos_t && sin_t && k_suffix && v_suffix && src && n_gen && out && workspace);
-  STLLM_CHECK_ARG(prefetch_bytes >= 0 && (((uintptr_t)prefetch_ptr) & 31) == 0);
+  STLLM_CHECK_ARG(prefetch_bytes >= 0 && (((uintptr_t)prefetch_ptr) & 15) == 0);
+  STLLM_CHECK_ARG(prefetch_bytes2 >= 0 && (((uintptr_t)prefetch_ptr2) & 15) == 0);
   STLLM_CHECK_ARG(prefix_len == 0 || (k_prefix && v_prefix));
   STLLM_CHECK_ARG(R >= 1 && R <= DL_RMAX && H >= 1 && prefix_len >= 0 && l_max >= 1 && n_split >= 1 && n_split <= 64);
   STLLM_CHECK_ARG(ldq % 8 == 0 && ldq >= 3LL * H * D && p_stride % 8 == 0 && s_beam_stride % 8 == 0 &&
@@ -1134,8 +1149,10 @@ extern "C" int stllm_decode_attention_fused_f16(void* qkv, long long ldq, const 
   p.R = R; p.H = H; p.Sp = prefix_len; p.NS = n_split; p.l_max = l_max; p.max_pos = max_pos;
   p.cap = (((prefix_len + n_split - 1) / n_split + (l_max + n_split - 1) / n_split + 2) + 3) & ~3;
   p.scale = scale;
-  p.pf_ptr = prefetch_bytes > 0 ? (const uint8_t*)prefetch_ptr : nullptr;
-  p.pf_bytes = prefetch_bytes;
+  p.pf_ptr[0] = prefetch_bytes > 0 ? (const uint8_t*)prefetch_ptr : nullptr;
+  p.pf_bytes[0] = prefetch_bytes;
+  p.pf_ptr[1] = prefetch_bytes2 > 0 ? (const uint8_t*)prefetch_ptr2 : nullptr;
+  p.pf_bytes[1] = prefetch_bytes2;
   const size_t smem = ((size_t)DL_RMAX * p.cap + (size_t)DA_WARPS * (R + 1) * DA_D + 3 * DL_RMAX * DA_D) * sizeof(float);
   if (smem > (size_t)DA_SMEM_MAX) {
     stllm_set_last_error("stllm_decode_attention_fused_f16: %d + %d keys over %d splits do not fit in shared memory",

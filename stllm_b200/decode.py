@@ -30,7 +30,8 @@ def supported(llm, n_rows):
 
 
 class DecodeEngine:
-    def __init__(self, llm, cache, prefix_len, n_rows, max_steps, prefix_mask=None, use_graph=None, n_split=None):
+    def __init__(self, llm, cache, prefix_len, n_rows, max_steps, prefix_mask=None, use_graph=None, n_split=None,
+                 debug_skip=()):
         """llm: STLLMForCausalLM; cache: the KVCache the prefill filled (batch 1); n_rows: beams (1 = greedy/sampling);
         max_steps: decode steps that may follow."""
         assert supported(llm, n_rows)
@@ -83,12 +84,16 @@ class DecodeEngine:
         self.fused_attn = os.environ.get("STLLM_DECODE_FUSED_ATTN", "1") != "0"
         # the attention launch moves few bytes: it also pulls the o_proj weights (33.5 MB << 126 MB L2) into L2
         self.prefetch_next = os.environ.get("STLLM_DECODE_PREFETCH_NEXT", "1") != "0"
+        # ... and the head of the gate|up weights (rows are consumed in this order by the first wave of the GEMV)
+        gu_mb = float(os.environ.get("STLLM_DECODE_PREFETCH_GU_MB", "48")) if self.prefetch_next else 0.0
+        self.prefetch_gu_rows = min(2 * F, int(gu_mb * 1e6 / (2 * C))) // 16 * 16
         if self.fused_attn:
             self.ws = ops.decode_attention_fused_workspace(self.H, self.n_split, dev)
         else:
             self.ws = ops.decode_attention_workspace(self.H, self.n_split, dev)
         self.steps_done = 0
         self.graph = None
+        self.debug_skip = frozenset(debug_skip)   # timing studies only: kernel kinds left out of the step
         if use_graph is None:
             use_graph = os.environ.get("STLLM_DECODE_GRAPH", "1") != "0"
         self.launches_per_step = None
@@ -102,29 +107,39 @@ class DecodeEngine:
         x = ops.gather_rows(self.embed_w, self.tok, out=self.x)
         scale = 1.0 / (self.d ** 0.5)
         for li, L in enumerate(P["layers"]):
-            if fuse and li > 0:
+            skip = self.debug_skip
+            if "qkv" in skip:
+                pass
+            elif fuse and li > 0:
                 ops.decode_linear(x, L["w_qkv"], self.qkv, norm_mode=ops.NORM_RMS, norm_eps=self.eps)
             else:
                 ops.decode_linear(x, L["w_qkv"], self.qkv, norm_mode=2, norm_weight=L["ln1"], norm_eps=self.eps)
-            if self.fused_attn:
+            if "attn" in skip:
+                pass
+            elif self.fused_attn:
                 ops.decode_attention_fused(self.qkv, self.cos_t, self.sin_t, self.kp[li], self.vp[li], self.ks[li],
                                            self.vs[li], self.src, self.n_gen, self.a, self.ws, self.H, self.d, scale,
                                            n_split=self.n_split, prefix_mask=self.prefix_mask,
-                                           prefetch=L["w_o"] if self.prefetch_next else None)
+                                           prefetch=L["w_o"] if self.prefetch_next else None,
+                                           prefetch2=L["w_gu"][:self.prefetch_gu_rows] if self.prefetch_gu_rows else None)
             else:
                 ops.decode_rope_append(self.qkv, self.cos_t, self.sin_t, self.Sp, self.n_gen, self.ks[li],
                                        self.vs[li], self.src, self.H, self.d)
                 ops.decode_attention(self.qkv, self.kp[li], self.vp[li], self.ks[li], self.vs[li], self.src,
                                      self.n_gen, self.a, self.ws, self.H, self.d, scale, n_split=self.n_split,
                                      prefix_mask=self.prefix_mask)
-            ops.decode_linear(self.a, L["w_o"], x, residual=x)
-            if fuse:
+            if "o" not in skip:
+                ops.decode_linear(self.a, L["w_o"], x, residual=x)
+            if "gu" in skip:
+                pass
+            elif fuse:
                 ops.decode_linear(x, L["w_gu"], self.g, norm_mode=ops.NORM_RMS, norm_eps=self.eps,
                                   epilogue=ops.EPI_SWIGLU)
             else:
                 ops.decode_linear(x, L["w_gu"], self.g, norm_mode=2, norm_weight=L["ln2"], norm_eps=self.eps,
                                   epilogue=ops.EPI_SWIGLU)
-            ops.decode_linear(self.g, L["w_down"], x, residual=x)
+            if "down" not in skip:
+                ops.decode_linear(self.g, L["w_down"], x, residual=x)
         ops.decode_linear(x, self.lm_w, self.logits, norm_mode=2, norm_weight=P["norm"], norm_eps=self.eps)
         self.n_gen.add_(1)
 

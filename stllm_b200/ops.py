@@ -467,10 +467,10 @@ def decode_attention_fused_workspace(nheads, n_split, device):
 
 
 def decode_attention_fused(qkv, cos_t, sin_t, k_prefix, v_prefix, k_suffix, v_suffix, src, n_gen, out, workspace, nheads,
-                           head_dim, scale, n_split=4, prefix_mask=None, prefetch=None):
+                           head_dim, scale, n_split=4, prefix_mask=None, prefetch=None, prefetch2=None):
     """decode_rope_append + decode_attention in one launch: qkv [R, 3*H*D] un-roped (left unchanged); the new token's
-    roped k and v are appended to the suffix caches at token n_gen[0]; out [R, H*D].  prefetch: optional contiguous tensor
-    (the weights the next kernel streams) pulled into L2 meanwhile."""
+    roped k and v are appended to the suffix caches at token n_gen[0]; out [R, H*D].  prefetch / prefetch2: optional
+    contiguous tensors (weights the next kernels stream) pulled into L2 meanwhile."""
     global launch_count
     _need_cuda(qkv, cos_t, sin_t, k_prefix, v_prefix, k_suffix, v_suffix, src, n_gen, out, workspace, prefix_mask)
     R = qkv.shape[0]
@@ -489,7 +489,8 @@ def decode_attention_fused(qkv, cos_t, sin_t, k_prefix, v_prefix, k_suffix, v_su
         k_prefix.stride(0), _ptr(prefix_mask), k_prefix.shape[0], _ptr(k_suffix), _ptr(v_suffix), k_suffix.stride(0),
         k_suffix.stride(1), k_suffix.shape[1], _ptr(src), src.stride(0), _ptr(n_gen), _ptr(out), out.stride(0),
         _ptr(workspace), workspace.numel() * workspace.element_size(), R, nheads, head_dim, n_split, float(scale),
-        _ptr(prefetch), prefetch.numel() * prefetch.element_size() if prefetch is not None else 0, _stream())
+        _ptr(prefetch), prefetch.numel() * prefetch.element_size() if prefetch is not None else 0,
+        _ptr(prefetch2), prefetch2.numel() * prefetch2.element_size() if prefetch2 is not None else 0, _stream())
     _lib.check(rc, "stllm_decode_attention_fused_f16")
     launch_count += 1
     return out
