@@ -323,9 +323,8 @@ def time_decode(layers, beams, S=576, steps=48, general=True):
 
 
 AB_VARIANTS = (("default", {}), ("unfused_attention", {"STLLM_DECODE_FUSED_ATTN": "0"}),
-               ("no_weight_prefetch", {"STLLM_DECODE_PREFETCH": "0"}), ("no_prefetch_next", {"STLLM_DECODE_PREFETCH_NEXT": "0"}),
-               ("prefetch_gu_0mb", {"STLLM_DECODE_PREFETCH_GU_MB": "0"}), ("prefetch_gu_24mb", {"STLLM_DECODE_PREFETCH_GU_MB": "24"}),
-               ("prefetch_gu_80mb", {"STLLM_DECODE_PREFETCH_GU_MB": "80"}))
+               ("no_weight_prefetch", {"STLLM_DECODE_PREFETCH": "0"}), ("prefetch_next_l2", {"STLLM_DECODE_PREFETCH_NEXT": "1"}),
+               ("xdirect", {"STLLM_DECODE_XDIRECT": "1"}), ("splits_3", {"STLLM_DECODE_SPLITS": "3"}))
 
 
 def time_decode_ab(layers, beams, S=576, steps=32, rounds=3):

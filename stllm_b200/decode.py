@@ -82,8 +82,9 @@ class DecodeEngine:
                 n_split = min((self.Sp + 127) // 128, max(1, sms // self.H))
         self.n_split = min(max(1, n_split), 16)
         self.fused_attn = os.environ.get("STLLM_DECODE_FUSED_ATTN", "1") != "0"
-        # the attention launch moves few bytes: it also pulls the o_proj weights (33.5 MB << 126 MB L2) into L2
-        self.prefetch_next = os.environ.get("STLLM_DECODE_PREFETCH_NEXT", "1") != "0"
+        # experiment, OFF: let the attention launch (few bytes, ~12 us) pull the o_proj weights (33.5 MB << 126 MB L2) and the
+        # head of gate|up into L2.  Same-process A/B: 2.671 (on) vs 2.664 ms/token (off) at 1 beam, 3.33 vs 3.28 at 5.
+        self.prefetch_next = os.environ.get("STLLM_DECODE_PREFETCH_NEXT", "0") != "0"
         # ... and the head of the gate|up weights (rows are consumed in this order by the first wave of the GEMV)
         gu_mb = float(os.environ.get("STLLM_DECODE_PREFETCH_GU_MB", "48")) if self.prefetch_next else 0.0
         self.prefetch_gu_rows = min(2 * F, int(gu_mb * 1e6 / (2 * C))) // 16 * 16
