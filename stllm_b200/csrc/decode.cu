@@ -620,8 +620,10 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attention_fused_kernel(c
   float* qs = red_s + (size_t)DA_WARPS * DA_D;              // [8][128] roped q (fp16-rounded values)
   float* kn = qs + DL_RMAX * DA_D;                          // [8][128] roped k of the new token (last split only)
   float* vn = kn + DL_RMAX * DA_D;                          // [8][128] v of the new token
+  __half* qh = reinterpret_cast<__half*>(vn + DL_RMAX * DA_D);   // [8][128] roped q in fp16 (rows >= R zero): MMA A operand
   __shared__ int s_last;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, hw = lane >> 4, c = lane & 15;
+  const int g = lane >> 2, t = lane & 3;   // mma.sync fragment coordinates
   const int h = blockIdx.x, sp = blockIdx.y;
   const bool last_split = sp == p.NS - 1;
   pdl_launch_dependents();
@@ -634,16 +636,26 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attention_fused_kernel(c
   const int my_r = warp % p.R, my_sub = warp / p.R;
   const bool suf_warp = my_sub < nsub;
   // ---- (a) the prompt's K and V of the first batch: static data, requested before the predecessor has finished ----
-  uint4 kv0[U], vv0[U];
+  // K in the mma.sync B-fragment layout (lane (g, t): key g of an 8-key group, dims 32 s + 8 t .. + 7 of step s), NG groups
+  // per warp = 256 keys per CTA; V in the half-warp-per-key layout of the P V loop, UV keys per half-warp = 160 per CTA
+  constexpr int NG = 2, UV = 5;
+  uint4 kq[NG][4], vv0[UV];
 #pragma unroll
-  for (int u = 0; u < U; ++u) {
-    const int i = 2 * warp + hw + 2 * DA_WARPS * u;
-    kv0[u] = make_uint4(0u, 0u, 0u, 0u);
-    vv0[u] = make_uint4(0u, 0u, 0u, 0u);
-    if (i < np) {
-      kv0[u] = __ldg(reinterpret_cast<const uint4*>(p.kp + (long long)(pk0 + i) * p.p_stride + hoff));
-      vv0[u] = __ldg(reinterpret_cast<const uint4*>(p.vp + (long long)(pk0 + i) * p.p_stride + hoff));
+  for (int gi = 0; gi < NG; ++gi) {
+    const int i = 8 * (warp + DA_WARPS * gi) + g;
+#pragma unroll
+    for (int st = 0; st < 4; ++st) {
+      kq[gi][st] = make_uint4(0u, 0u, 0u, 0u);
+      if (i < np)
+        kq[gi][st] = __ldg(reinterpret_cast<const uint4*>(p.kp + (long long)(pk0 + i) * p.p_stride + (long long)h * DA_D +
+                                                          32 * st + 8 * t));
     }
+  }
+#pragma unroll
+  for (int u = 0; u < UV; ++u) {
+    const int i = 2 * warp + hw + 2 * DA_WARPS * u;
+    vv0[u] = make_uint4(0u, 0u, 0u, 0u);
+    if (i < np) vv0[u] = __ldg(reinterpret_cast<const uint4*>(p.vp + (long long)(pk0 + i) * p.p_stride + hoff));
   }
   // bulk L2 prefetch (8 KB per instruction, one lane per warp, consecutive warps of the grid take consecutive chunks)
   if (lane == 0) {
@@ -678,14 +690,23 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attention_fused_kernel(c
     pr0[u] = (suf_warp && j < sk1c) ? p.src[my_r * p.src_ld + j] : 0;
   }
   // ---- (c) RoPE of q (and of k for the new token) into shared memory ----
-  for (int idx = tid; idx < p.R * 64; idx += DA_THREADS) {
+  for (int idx = tid; idx < DL_RMAX * 64; idx += DA_THREADS) {
     const int r = idx >> 6, i = idx & 63;
+    if (r >= p.R) {
+      qh[r * DA_D + i] = __float2half_rn(0.f);
+      qh[r * DA_D + i + 64] = __float2half_rn(0.f);
+      continue;
+    }
     const float cs = __ldg(p.cos_t + (long long)pos * 64 + i), sn = __ldg(p.sin_t + (long long)pos * 64 + i);
     const __half* row = p.qkv + (long long)r * p.ldq + (long long)h * DA_D;
     const float lo = __half2float(row[i]), hi = __half2float(row[i + 64]);
     // explicit contraction = what nvcc emits for rope_kernel (elementwise.cu): fma(lo, c, -rn(hi s)), fma(hi, c, rn(lo s))
-    qs[r * DA_D + i] = __half2float(__float2half_rn(__fmaf_rn(lo, cs, -__fmul_rn(hi, sn))));
-    qs[r * DA_D + i + 64] = __half2float(__float2half_rn(__fmaf_rn(hi, cs, __fmul_rn(lo, sn))));
+    const __half qlo = __float2half_rn(__fmaf_rn(lo, cs, -__fmul_rn(hi, sn)));
+    const __half qhi = __float2half_rn(__fmaf_rn(hi, cs, __fmul_rn(lo, sn)));
+    qh[r * DA_D + i] = qlo;
+    qh[r * DA_D + i + 64] = qhi;
+    qs[r * DA_D + i] = __half2float(qlo);
+    qs[r * DA_D + i + 64] = __half2float(qhi);
     if (last_split) {
       const long long HD = (long long)p.H * DA_D;
       const float klo = __half2float(row[HD + i]), khi = __half2float(row[HD + i + 64]);
@@ -720,32 +741,45 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attention_fused_kernel(c
   __syncthreads();
   // ---- scores ----
   {
-    // prompt keys: first batch from registers, further batches (np > 128) loaded here
-    for (int b0 = 0; b0 < np; b0 += 2 * DA_WARPS * U) {   // block-uniform trip count
-      uint4 kv[U];
+    // prompt keys on mma.sync m16n8k16: A = roped q (row = beam, rows >= R zero), B = 8 keys; D[beam g][key 2t, 2t+1].
+    // One 16-byte load of a key feeds two MMAs (the k permutation inside a 32-dim step is the same for q and k).
+    // First NG groups per warp from registers, further groups (np > 256) loaded here.
+    {
+      uint4 qa[4];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int i = b0 + 2 * warp + hw + 2 * DA_WARPS * u;
-        if (b0 == 0) kv[u] = kv0[u];
-        else kv[u] = i < np ? __ldg(reinterpret_cast<const uint4*>(p.kp + (long long)(pk0 + i) * p.p_stride + hoff))
-                            : make_uint4(0u, 0u, 0u, 0u);
-      }
+      for (int st = 0; st < 4; ++st) qa[st] = *reinterpret_cast<const uint4*>(qh + g * DA_D + 32 * st + 8 * t);
+      for (int g0 = 0; 8 * g0 < np; g0 += DA_WARPS * NG) {   // block-uniform trip count (warp-collective MMAs inside)
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int i = b0 + 2 * warp + hw + 2 * DA_WARPS * u;
-        float kf[8];
-        half8_to_float(kv[u], kf);
-        const bool masked = p.p_mask != nullptr && i < np && p.p_mask[pk0 + i] == 0;
+        for (int gi = 0; gi < NG; ++gi) {
+          const int grp = g0 + warp + DA_WARPS * gi;
+          const int i = 8 * grp + g;
+          uint4 kk[4];
 #pragma unroll
-        for (int r = 0; r < DL_RMAX; ++r) {
-          if (r >= p.R) break;
-          const float4 q0 = *reinterpret_cast<const float4*>(qs + r * DA_D + 8 * c);
-          const float4 q1 = *reinterpret_cast<const float4*>(qs + r * DA_D + 8 * c + 4);
-          float d = q0.x * kf[0];
-          d = fmaf(q0.y, kf[1], d); d = fmaf(q0.z, kf[2], d); d = fmaf(q0.w, kf[3], d);
-          d = fmaf(q1.x, kf[4], d); d = fmaf(q1.y, kf[5], d); d = fmaf(q1.z, kf[6], d); d = fmaf(q1.w, kf[7], d);
-          d = sum16(d);
-          if (c == 0 && i < np) sc[r * p.cap + i] = masked ? NEG_INF : d * p.scale;
+          for (int st = 0; st < 4; ++st) {
+            if (g0 == 0) kk[st] = kq[gi][st];
+            else {
+              kk[st] = make_uint4(0u, 0u, 0u, 0u);
+              if (i < np)
+                kk[st] = __ldg(reinterpret_cast<const uint4*>(p.kp + (long long)(pk0 + i) * p.p_stride +
+                                                              (long long)h * DA_D + 32 * st + 8 * t));
+            }
+          }
+          float cc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int st = 0; st < 4; ++st) {
+            mma16816(cc, qa[st].x, 0u, qa[st].y, 0u, kk[st].x, kk[st].y);
+            mma16816(cc, qa[st].z, 0u, qa[st].w, 0u, kk[st].z, kk[st].w);
+          }
+          if (g < p.R) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int key = 8 * grp + 2 * t + e;
+              if (key < np) {
+                const bool masked = p.p_mask != nullptr && p.p_mask[pk0 + key] == 0;
+                sc[g * p.cap + key] = masked ? NEG_INF : cc[e] * p.scale;
+              }
+            }
+          }
         }
       }
     }
@@ -822,17 +856,17 @@ __global__ void __launch_bounds__(DA_THREADS, 1) decode_attention_fused_kernel(c
     for (int r = 0; r < DL_RMAX; ++r)
 #pragma unroll
       for (int e = 0; e < 8; ++e) acc[r][e] = 0.f;
-    for (int b0 = 0; b0 < np; b0 += 2 * DA_WARPS * U) {
-      uint4 vv[U];
+    for (int b0 = 0; b0 < np; b0 += 2 * DA_WARPS * UV) {
+      uint4 vv[UV];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
+      for (int u = 0; u < UV; ++u) {
         const int i = b0 + 2 * warp + hw + 2 * DA_WARPS * u;
         if (b0 == 0) vv[u] = vv0[u];
         else vv[u] = i < np ? __ldg(reinterpret_cast<const uint4*>(p.vp + (long long)(pk0 + i) * p.p_stride + hoff))
                             : make_uint4(0u, 0u, 0u, 0u);
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
+      for (int u = 0; u < UV; ++u) {
         const int i = b0 + 2 * warp + hw + 2 * DA_WARPS * u;
         if (i < np) {
           float vf[8];
@@ -1153,7 +1187,8 @@ extern "C" int stllm_decode_attention_fused_f16(void* qkv, long long ldq, const 
   p.pf_bytes[0] = prefetch_bytes;
   p.pf_ptr[1] = prefetch_bytes2 > 0 ? (const uint8_t*)prefetch_ptr2 : nullptr;
   p.pf_bytes[1] = prefetch_bytes2;
-  const size_t smem = ((size_t)DL_RMAX * p.cap + (size_t)DA_WARPS * (R + 1) * DA_D + 3 * DL_RMAX * DA_D) * sizeof(float);
+  const size_t smem = ((size_t)DL_RMAX * p.cap + (size_t)DA_WARPS * (R + 1) * DA_D + 3 * DL_RMAX * DA_D) * sizeof(float) +
+                      (size_t)DL_RMAX * DA_D * sizeof(__half);
   if (smem > (size_t)DA_SMEM_MAX) {
     stllm_set_last_error("stllm_decode_attention_fused_f16: %d + %d keys over %d splits do not fit in shared memory",
                          prefix_len, l_max, n_split);
