@@ -22,7 +22,7 @@ from . import decode as _decode
 
 
 def _process_logits(logits, generated, cur_len, min_length, eos_ids, repetition_penalty, temperature):
-    logits = logits.float()
+    logits = logits.to(torch.float32, copy=True)   # never write into the caller's (possibly expanded) logits
     if repetition_penalty != 1.0 and generated.shape[1] > 0:
         score = torch.gather(logits, 1, generated)
         score = torch.where(score < 0, score * repetition_penalty, score / repetition_penalty)
