@@ -44,6 +44,48 @@ def test_bad_arguments_return_error_codes_not_crashes():
     assert rc == -1
 
 
+def test_decode_entry_points_validate_before_touching_the_device():
+    # argument validation of the decode-step C ABI happens before any CUDA call: exercised here without a GPU, with fake
+    # (never dereferenced) 16-byte-aligned addresses
+    import ctypes
+    from stllm_b200 import _lib, ops
+    lib = _lib.load()
+    P = ctypes.c_void_p(0x1000)
+    names = ["x", "ldx", "W", "ldw", "y", "ldy", "R", "N", "K", "norm_mode", "norm_w", "eps", "res", "ldr", "epi", "st"]
+    ok_args = [P, 4096, P, 4096, P, 4096, 5, 4096, 4096, 0, None, 1e-6, None, 0, 0, None]
+
+    def lin(**kw):
+        a = list(ok_args)
+        for k, v in kw.items():
+            a[names.index(k)] = v
+        return lib.stllm_decode_linear_f16(*a)
+    assert lin(x=None) == -1 and b"bad argument" in lib.stllm_last_error()
+    assert lin(R=9) == -1 and lin(R=0) == -1                       # at most 8 rows (beams) per step
+    assert lin(norm_mode=2) == -1                                   # explicit RMSNorm needs the norm weight
+    assert lin(epi=1) == -1 and lin(epi=2, N=4095) == -1            # only NONE / SWIGLU; SwiGLU pairs rows
+    assert lin(ldx=4090) == -1 and lin(x=ctypes.c_void_p(0x1008)) == -1
+    assert lin(K=4104, ldx=4104, ldw=4104) == -3 and b"multiple of 32" in lib.stllm_last_error()   # unsupported, not bad
+    assert lin(R=8, K=16384, ldx=16384, ldw=16384) == -3            # 8 x 16384 activations exceed shared memory
+    with pytest.raises(_lib.StllmNativeError):
+        ops.decode_linear(torch.zeros(1, 64, dtype=torch.float16), torch.zeros(16, 64, dtype=torch.float16),
+                          torch.zeros(1, 16, dtype=torch.float16))  # CPU tensors: no fallback
+    assert lib.stllm_decode_attention_workspace_bytes(32, 4) == 32 * 4 * 8 * 132 * 4
+    assert lib.stllm_decode_attention_fused_workspace_bytes(32, 4) == 32 * 4 * 8 * 132 * 4 + 128
+    I = ctypes.c_void_p(0x2000)
+    # q, ldq, kp, vp, p_stride, mask, Sp, ks, vs, beam stride, token stride, l_max, src, src_ld, n_gen, out, ldo, ws,
+    # ws bytes, R, H, D, splits, scale, stream
+    att = [P, 12288, P, P, 4096, None, 576, P, P, 4096 * 64, 4096, 64, I, 64, I, P, 4096, P, 1 << 30, 5, 32, 128, 4,
+           0.088, None]
+    for pos, val, want in ((21, 64, -3),      # head dim 64: unsupported
+                           (19, 9, -1),       # 9 beams
+                           (18, 1024, -1),    # workspace too small
+                           (13, 32, -1),      # ancestry table narrower than the suffix cache
+                           (0, None, -1)):    # no q
+        bad = list(att)
+        bad[pos] = val
+        assert lib.stllm_decode_attention_f16(*bad) == want, (pos, val)
+
+
 def test_mask_and_residual_index_bit_exact_with_reference():
     from stllm_b200.st_llm import RandomMaskingGenerator, STLLMModel
     g = np.load(os.path.join(GOLDEN, "mask_kat.npz"))
