@@ -1018,6 +1018,18 @@ int num_sms_dec() {
   return n;
 }
 
+// Hypothesis for the bimodal 5-beam timings (profiles/r01_decode_summary.md section 3), UNTESTED: consecutive kernels of a
+// step ask for different shared-memory sizes (25 ... 127 KB), so the driver may pick different L1 / shared carve-outs and
+// has to drain the SM between them.  STLLM_DECODE_CARVEOUT=1 pins every decode kernel to the maximum shared carve-out
+// (none of them relies on L1 hits).  Off by default until it has been A/B-ed on the device.
+template <typename K>
+cudaError_t dec_configure(K kernel, int max_dyn_smem) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, max_dyn_smem);
+  if (e == cudaSuccess && env_int_dec("STLLM_DECODE_CARVEOUT", 0) != 0)
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+  return e;
+}
+
 constexpr int DL_SMEM_MAX = 220 * 1024;
 constexpr int DA_SMEM_MAX = 200 * 1024;
 
@@ -1056,8 +1068,9 @@ extern "C" int stllm_decode_linear_f16(const void* x, long long ldx, const void*
   }
   static bool configured = false;
   if (!configured) {
-    STLLM_CHECK_CUDA(cudaFuncSetAttribute(decode_linear_kernel<4, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DL_SMEM_MAX / 2));
-    STLLM_CHECK_CUDA(cudaFuncSetAttribute(decode_linear_kernel<8, 1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, DL_SMEM_MAX));
+    STLLM_CHECK_CUDA(dec_configure(decode_linear_kernel<4, 2, false>, DL_SMEM_MAX / 2));
+    STLLM_CHECK_CUDA(dec_configure(decode_linear_kernel<8, 1, false>, DL_SMEM_MAX));
+    STLLM_CHECK_CUDA(dec_configure(decode_linear_kernel<4, 2, true>, 48 * 1024));
     configured = true;
   }
   const int direct_ok = env_int_dec("STLLM_DECODE_XDIRECT", 0);   // A/B: 3.49 (on) vs 3.37 ms/token (off) at 5 beams
@@ -1135,7 +1148,7 @@ extern "C" int stllm_decode_attention_f16(const void* q, long long ldq, const vo
   }
   static bool configured = false;
   if (!configured) {
-    STLLM_CHECK_CUDA(cudaFuncSetAttribute(decode_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DA_SMEM_MAX));
+    STLLM_CHECK_CUDA(dec_configure(decode_attention_kernel, DA_SMEM_MAX));
     configured = true;
   }
   STLLM_CHECK_CUDA(stllm_launch(decode_attention_kernel, dim3(H, n_split), dim3(DA_THREADS), smem, (cudaStream_t)stream, p));
@@ -1196,7 +1209,7 @@ extern "C" int stllm_decode_attention_fused_f16(void* qkv, long long ldq, const 
   }
   static bool configured = false;
   if (!configured) {
-    STLLM_CHECK_CUDA(cudaFuncSetAttribute(decode_attention_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DA_SMEM_MAX));
+    STLLM_CHECK_CUDA(dec_configure(decode_attention_fused_kernel, DA_SMEM_MAX));
     configured = true;
   }
   STLLM_CHECK_CUDA(stllm_launch(decode_attention_fused_kernel, dim3(H, n_split), dim3(DA_THREADS), smem, (cudaStream_t)stream, p));
