@@ -3,6 +3,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <mutex>
+#include <unordered_set>
+
 #include "common.cuh"
 
 static thread_local char g_last_error[1024] = "";
@@ -31,4 +34,18 @@ bool stllm_pdl_enabled() {
     v = (e != nullptr && atoi(e) == 0) ? 0 : 1;
   }
   return v != 0;
+}
+
+// STLLM_CARVEOUT=1: see common.cuh
+bool stllm_carveout_pin_once(const void* fn) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("STLLM_CARVEOUT");
+    enabled = (e != nullptr && atoi(e) != 0) ? 1 : 0;
+  }
+  if (!enabled) return false;
+  static std::mutex mu;
+  static std::unordered_set<const void*> seen;
+  std::lock_guard<std::mutex> lock(mu);
+  return seen.insert(fn).second;
 }

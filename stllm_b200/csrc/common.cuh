@@ -271,6 +271,11 @@ DEVI void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependen
 DEVI void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 bool stllm_pdl_enabled();
+// STLLM_CARVEOUT=1 (experiment, default off, not yet A/B-ed on the device): every kernel launched through stllm_launch is
+// pinned once to the maximum shared-memory carve-out, so that consecutive kernels of a step (GEMM ~200 KB, attention
+// 2 x 96 KB, element-wise kernels 0 KB of shared memory) do not make the driver switch the L1 / shared split of the SMs
+// between launches.  Returns true the first time it sees `fn` (and only when the experiment is enabled).
+bool stllm_carveout_pin_once(const void* fn);
 
 template <typename... KArgs, typename... Args>
 cudaError_t stllm_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
@@ -285,5 +290,7 @@ cudaError_t stllm_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = stllm_pdl_enabled() ? 1 : 0;
+  if (stllm_carveout_pin_once(reinterpret_cast<const void*>(kernel)))
+    (void)cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }

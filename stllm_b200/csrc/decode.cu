@@ -14,13 +14,17 @@
 //       contiguous bytes of a weight row and feeds two MMAs (the k permutation inside a step is the same for both
 //       operands).  The RMSNorm in front of the Linear is part of the prologue: either explicit (w (.) fp16(x rstd), the
 //       reference's rounding) or folded (the packed weights already carry the norm weight; the result is scaled by rstd).
-//   decode_rope_append_kernel RoPE on q (in place) and k, k/v of the new token appended to the per-beam suffix cache
-//                                                                                      modeling_llama_mem.py:81-127,205-217
-//   decode_attention_kernel   softmax(scale q K^T) V for one query token per beam over [shared prompt KV || per-beam
-//       generated KV]; the prompt's K/V is ONE copy read once for all beams (HF 4.28 prefills and re-reads num_beams
-//       copies); generated K/V is addressed through an ancestry table src[beam][j] so a beam re-ordering permutes a few
-//       ints instead of copying the cache (HF _reorder_cache index_selects all of it).  Split over keys (grid = heads x
-//       splits), merged by decode_attention_combine_kernel.                              modeling_llama_mem.py:205-244
+//       The first batch of a CTA's weight loads is issued BEFORE griddepcontrol.wait (and the next block's before the
+//       reduction barrier): HBM keeps streaming across kernel boundaries.
+//   decode_attention_fused_kernel   one launch per layer: RoPE of q / k, append of the new token's k / v to the per-beam
+//       suffix cache, softmax(scale q K^T) V for one query token per beam over [shared prompt KV || per-beam generated KV],
+//       merge of the key splits by the last CTA of a head (atomic ticket).  The prompt's K/V is ONE copy read once for all
+//       beams (HF 4.28 prefills and re-reads num_beams copies); generated K/V is addressed through an ancestry table
+//       src[beam][j], so a beam re-ordering permutes a few ints instead of copying the cache (HF _reorder_cache
+//       index_selects all of it).  Prompt-key scores run on mma.sync with the beams as the 16-row operand.
+//                                                                                      modeling_llama_mem.py:81-127,205-244
+//   decode_rope_append_kernel / decode_attention_kernel / decode_attention_combine_kernel   the same work as three
+//       launches (first version, kept as the A/B reference: STLLM_DECODE_FUSED_ATTN=0).
 #include "common.cuh"
 
 namespace {
