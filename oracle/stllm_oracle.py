@@ -365,9 +365,10 @@ def draw_mask_rate():
 
 
 def encode_img(w, image, cfg, text_ids=None, text_mask=None, collect=None):
-    """STLLMModel.encode_img, st_llm.py:321-377 (has_qformer=True, vit_model='eva_clip_g').
+    """STLLMModel.encode_img, st_llm.py:321-377.
     w: dict of sub-state-dicts {"vit","ln_vision","qformer","query_tokens","llama_proj"};
-    image [B,T,3,H,W] or [T,3,H,W].  Returns inputs_llama [B,T,Q,4096] or [T,Q,4096]."""
+    image [B,T,3,H,W] or [T,3,H,W].  Returns inputs_llama [B,T,Q,4096] or [T,Q,4096]
+    (cfg["has_qformer"] = False, :369-373: [B,T,P/4,4096] from the patch tokens themselves)."""
     infer = image.dim() == 4
     T = image.shape[1]
     if cfg.get("vit_model", "eva_clip_g") == "eva_btadapter_g":
@@ -381,6 +382,14 @@ def encode_img(w, image, cfg, text_ids=None, text_mask=None, collect=None):
     x = ln_vision(w["ln_vision"], x)                                             # :331
     if collect is not None:
         collect["ln_vision"] = x
+    if not cfg.get("has_qformer", True):
+        x = x[:, 1:, :]                                                           # :370 drop the cls token
+        bs, pn, hs = x.shape
+        x = x.reshape(bs, int(pn / 4), int(hs * 4))                               # :371-372 4 neighbouring tokens -> 1
+        out = F.linear(x, w["llama_proj"]["weight"], w["llama_proj"]["bias"])     # :373 (llama_proj: 4 C -> D, :301)
+        if not infer:
+            out = out.view(-1, T, out.shape[1], out.shape[-1])                    # :374-375
+        return out
     if text_ids is not None and text_ids.shape[0] != x.shape[0]:
         text_ids = text_ids.repeat_interleave(T, dim=0)                          # :340-343 (text repeated per frame)
         text_mask = text_mask.repeat_interleave(T, dim=0)

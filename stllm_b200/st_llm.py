@@ -82,8 +82,6 @@ class STLLMModel(nn.Module):
         super().__init__()
         assert vit_model in ["eva_clip_g", "eva_btadapter_g"], \
             "vit model must be eva_clip_g for current version of MiniGPT-4"          # blip2.py:65
-        if not has_qformer:
-            raise NotImplementedError("has_qformer=False is not used by any shipped config (SURVEY a15')")
         self.tokenizer = tokenizer
         self.pre_encoding = pre_encoding
         self.video_input = video_input
@@ -110,23 +108,27 @@ class STLLMModel(nn.Module):
             self.visual_encoder = create_eva_btadapter(vit_precision, clip=self.visual_encoder)
         self.ln_vision = LayerNorm(self.visual_encoder.num_features)
         self.has_qformer = has_qformer
-        qcfg = qformer_config or BertConfig()
-        qcfg.encoder_width = self.visual_encoder.num_features
-        qcfg.query_length = num_query_token
-        self.Qformer = BertLMHeadModel(qcfg)
-        self.query_tokens = nn.Parameter(torch.zeros(1, num_query_token, qcfg.hidden_size))
-        self.query_tokens.data.normal_(mean=0.0, std=qcfg.initializer_range)
-        if not qformer_text_input:                                   # st_llm.py:277-283
-            self.Qformer.bert.embeddings.word_embeddings = None
-            self.Qformer.bert.embeddings.position_embeddings = None
-            for layer in self.Qformer.bert.encoder.layer:
-                layer.output = None
-                layer.intermediate = None
-        elif tokenizer is not None:
-            self.Qformer.resize_token_embeddings(len(tokenizer))    # st_llm.py:285
-        self.Qformer.cls = None
         self.llama_tokenizer = llama_tokenizer
-        self.llama_proj = nn.Linear(qcfg.hidden_size, D)
+        if has_qformer:
+            qcfg = qformer_config or BertConfig()
+            qcfg.encoder_width = self.visual_encoder.num_features
+            qcfg.query_length = num_query_token
+            self.Qformer = BertLMHeadModel(qcfg)
+            self.query_tokens = nn.Parameter(torch.zeros(1, num_query_token, qcfg.hidden_size))
+            self.query_tokens.data.normal_(mean=0.0, std=qcfg.initializer_range)
+            if not qformer_text_input:                                   # st_llm.py:277-283
+                self.Qformer.bert.embeddings.word_embeddings = None
+                self.Qformer.bert.embeddings.position_embeddings = None
+                for layer in self.Qformer.bert.encoder.layer:
+                    layer.output = None
+                    layer.intermediate = None
+            elif tokenizer is not None:
+                self.Qformer.resize_token_embeddings(len(tokenizer))    # st_llm.py:285
+            self.Qformer.cls = None
+            img_f_dim = qcfg.hidden_size                                 # st_llm.py:298
+        else:
+            img_f_dim = self.visual_encoder.num_features * 4             # st_llm.py:300-301: no Q-Former, no query tokens
+        self.llama_proj = nn.Linear(img_f_dim, D)
         self.max_txt_len = max_txt_len
         self.end_sym = end_sym
         self.embed_tokens = None  # set by STLLMLlamaModel.initialize_vision_modules (st_llm.py:54)
@@ -161,6 +163,15 @@ class STLLMModel(nn.Module):
             image = image.reshape((-1,) + tuple(image.shape[2:]))   # 'B T C H W -> (B T) C H W'
         image_embeds = self.visual_encoder(image)
         image_embeds = self.ln_vision(image_embeds)
+        if not self.has_qformer:                                     # st_llm.py:369-373 (SURVEY a15')
+            image_embeds = image_embeds[:, 1:, :]                    # drop the cls token
+            bs, pn, hs = image_embeds.shape
+            image_embeds = image_embeds.reshape(bs, int(pn / 4), int(hs * 4)).contiguous()   # 4 neighbouring tokens -> 1
+            inputs_llama = _linear(self.llama_proj, image_embeds)    # GEMM 4*C -> D
+            if not infer:
+                inputs_llama = inputs_llama.view(-1, T, inputs_llama.shape[1], inputs_llama.shape[-1])
+            atts_llama = torch.ones(inputs_llama.size()[:-1], dtype=torch.long, device=device)
+            return inputs_llama, atts_llama, use_image
         query_tokens = self.query_tokens.expand(image_embeds.shape[0], -1, -1)
         if self.qformer_text_input:
             assert text

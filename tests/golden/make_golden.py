@@ -237,9 +237,42 @@ def golden_flow(ref):
         json.dump(keys, f, indent=0, sort_keys=True)
 
 
+@torch.no_grad()
+def golden_noqformer(ref):
+    """encode_img with has_qformer=False (st_llm.py:300-301,369-373: drop cls, fold 4 neighbouring patch tokens into one,
+    llama_proj 4*C -> D) through the reference's own unbound STLLMModel.encode_img on a hand-assembled object, for a
+    5-D clip batch and a 4-D frame stack."""
+    import contextlib
+    import torch.nn as nn
+    st = ref.st_llm
+    torch.manual_seed(0)
+    M = st.STLLMModel.__new__(st.STLLMModel)
+    nn.Module.__init__(M)
+    M.vit_model, M.has_qformer, M.qformer_text_input = "eva_clip_g", False, False
+    M.visual_encoder = ref_shim.build_vit(ref, img_size=56, embed_dim=176, depth=2, num_heads=2)
+    M.ln_vision = ref.blip2.LayerNorm(176)
+    M.llama_proj = nn.Linear(176 * 4, 64)                       # img_f_dim = num_features * 4 (st_llm.py:301)
+    M.maybe_autocast = lambda dtype=None: contextlib.nullcontext()
+    for n, p in M.named_parameters():
+        if n.endswith("bias") or n.endswith("q_bias") or n.endswith("v_bias"):
+            p.data.normal_(0, 0.05)
+        if ("norm" in n or n.startswith("ln_vision")) and n.endswith("weight"):
+            p.data.add_(torch.randn_like(p) * 0.1)
+    sd = _round_fp16_(M)
+    M = M.eval()
+    g = torch.Generator().manual_seed(1234)
+    clips = torch.randn(2, 3, 3, 56, 56, generator=g)
+    out5, atts5, use5 = st.STLLMModel.encode_img(M, clips)
+    out4, atts4, use4 = st.STLLMModel.encode_img(M, clips[0])
+    _save("noqformer_small.npz", clips=clips.numpy(), out5=out5.numpy(), out4=out4.numpy(), atts5_shape=np.array(atts5.shape),
+          atts4_shape=np.array(atts4.shape), use_image=np.array([int(use5), int(use4)]), depth=2, heads=2,
+          **_sd_arrays("w.", sd))
+
+
 if __name__ == "__main__":
     ref = ref_shim.load_reference()
-    which = sys.argv[1:] or ["vit", "qformer", "qformer_text", "llama", "mask", "flow", "btadapter", "preprocess"]
+    which = sys.argv[1:] or ["vit", "qformer", "qformer_text", "llama", "mask", "flow", "btadapter", "preprocess",
+                             "noqformer"]
     if "vit" in which:
         golden_vit(ref)
     if "qformer" in which:
@@ -256,3 +289,5 @@ if __name__ == "__main__":
         golden_btadapter(ref)
     if "preprocess" in which:
         golden_preprocess()
+    if "noqformer" in which:
+        golden_noqformer(ref)

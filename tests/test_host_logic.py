@@ -86,6 +86,44 @@ def test_decode_entry_points_validate_before_touching_the_device():
         assert lib.stllm_decode_attention_f16(*bad) == want, (pos, val)
 
 
+def test_encode_img_without_qformer_host_logic(monkeypatch):
+    # SURVEY a15' (st_llm.py:300-301,369-373): the product's has_qformer=False branch -- construction (no Q-Former, llama_proj
+    # takes 4 C features) and the token folding of encode_img, checked on the CPU against the reference's own output with the
+    # encoder / LayerNorm / GEMM calls replaced by the oracle's fp32 functions (the kernels themselves are covered elsewhere)
+    import torch.nn as nn
+    from oracle import stllm_oracle as O
+    from stllm_b200 import st_llm as S
+    from tests.util import assert_close, load_golden
+    sm = S.STLLMModel(has_qformer=False, vit_depth=1, llama_hidden=64)
+    assert not hasattr(sm, "Qformer") and not hasattr(sm, "query_tokens")
+    assert sm.llama_proj.in_features == 4 * sm.visual_encoder.num_features == 5632 and sm.llama_proj.out_features == 64
+    assert not any(k.startswith(("Qformer", "query_tokens")) for k in sm.state_dict())
+    sd, g = load_golden("noqformer_small.npz")
+    vit_sd = {k[len("visual_encoder."):]: v for k, v in sd.items() if k.startswith("visual_encoder.")}
+    ln_sd = {k[len("ln_vision."):]: v for k, v in sd.items() if k.startswith("ln_vision.")}
+
+    class Enc(nn.Module):
+        num_features = 176
+
+        def forward(self, img):
+            return O.vit_forward(vit_sd, img, int(g["depth"]), int(g["heads"]))
+
+    class LN(nn.Module):
+        def forward(self, x):
+            return O.ln_vision(ln_sd, x)
+    sm.visual_encoder, sm.ln_vision = Enc(), LN()
+    sm.llama_proj = nn.Linear(176 * 4, 64)
+    sm.llama_proj.load_state_dict({"weight": sd["llama_proj.weight"], "bias": sd["llama_proj.bias"]})
+    monkeypatch.setattr(S, "_linear", lambda mod, x, epilogue=0: torch.nn.functional.linear(x, mod.weight, mod.bias))
+    clips = torch.from_numpy(g["clips"])
+    out5, atts5, use5 = sm.encode_img(clips)
+    out4, atts4, use4 = sm.encode_img(clips[0])
+    assert tuple(atts5.shape) == tuple(g["atts5_shape"]) and tuple(atts4.shape) == tuple(g["atts4_shape"])
+    assert [int(use5), int(use4)] == g["use_image"].tolist() and atts5.dtype == torch.long
+    assert_close(out5, g["out5"], atol=2e-5, rtol=1e-4, what="product encode_img has_qformer=False (5-D)")
+    assert_close(out4, g["out4"], atol=2e-5, rtol=1e-4, what="product encode_img has_qformer=False (4-D)")
+
+
 def test_mask_and_residual_index_bit_exact_with_reference():
     from stllm_b200.st_llm import RandomMaskingGenerator, STLLMModel
     g = np.load(os.path.join(GOLDEN, "mask_kat.npz"))

@@ -72,3 +72,19 @@ def test_btadapter_matches_reference():
     assert_close(out, g["out"], 3e-5, 1e-5, "bt-adapter out [B,T]")
     out1 = O.bt_adapter_forward(sd, frames[0], int(g["depth"]), int(g["heads"]), bt_depth=int(g["bt_depth"]))
     assert_close(out1, g["out_clip0"], 3e-5, 1e-5, "bt-adapter out, 4-D single clip")
+
+
+def test_encode_img_without_qformer_matches_reference():
+    """SURVEY a15': has_qformer=False (st_llm.py:300-301,369-373), fixture from the reference's own encode_img"""
+    sd, g = load_golden("noqformer_small.npz")
+    w = {"vit": {k[len("visual_encoder."):]: v for k, v in sd.items() if k.startswith("visual_encoder.")},
+         "ln_vision": {k[len("ln_vision."):]: v for k, v in sd.items() if k.startswith("ln_vision.")},
+         "llama_proj": {k[len("llama_proj."):]: v for k, v in sd.items() if k.startswith("llama_proj.")}}
+    cfg = dict(vit_depth=int(g["depth"]), vit_heads=int(g["heads"]), has_qformer=False)
+    clips = torch.from_numpy(g["clips"])
+    out5 = O.encode_img(w, clips, cfg)
+    out4 = O.encode_img(w, clips[0], cfg)
+    assert tuple(out5.shape) == (2, 3, 4, 64) == tuple(g["out5"].shape) and tuple(out4.shape) == (3, 4, 64)
+    assert tuple(g["atts5_shape"]) == (2, 3, 4) and tuple(g["atts4_shape"]) == (3, 4) and g["use_image"].tolist() == [0, 1]
+    assert_close(out5, g["out5"], atol=2e-5, rtol=1e-4, what="encode_img has_qformer=False (5-D)")
+    assert_close(out4, g["out4"], atol=2e-5, rtol=1e-4, what="encode_img has_qformer=False (4-D)")
