@@ -59,11 +59,12 @@ int stllm_gemm_f16(const void* A, long long lda, const void* W, long long ldw, v
  *   norm_mode 2 (LayerNorm): C = epi(rstd_m * (x W'^T - mu_m s_n) + b'_n) col_sb[n] = (s_n = sum_k W'_nk,
  *                            b'_n = bias_n + sum_k beta_k W_nk); `bias` must be NULL
  * The statistics come from the GEMM that PRODUCED x: rs_out_mode 1 / 2 makes its epilogue store sum(c^2) / (sum c,
- * sum c^2) of the values it wrote (after bias, activation and residual), per row and per 128-column slot -- plain
- * stores to distinct slots, summed in slot order by the consumer: deterministic, no atomics, no zeroing.  A
- * statistics row is [slots][mode] floats, slots = ceil(columns / 128), with a row stride (rs_*_stride, in floats) that
- * is a multiple of 8; padding floats must be zero.  Both features need tokens on the accumulator lanes and 256-column
- * tiles on the producer: the planner restricts itself accordingly. */
+ * sum c^2) of the values it wrote (after bias, activation and residual), per row and per (column tile, warp half) slot
+ * -- plain stores to distinct slots, summed in slot order by the consumer: deterministic, no atomics, no zeroing.  A
+ * statistics row is [slots][mode] floats with 2 slots per column tile of the producer; a row stride (rs_*_stride, in
+ * floats, multiple of 8) of >= 2 * ceil(columns / 128) * mode covers every tile width the planner picks for a producer
+ * (>= 128 columns); floats of unused slots must be zero.  Both features need tokens on the accumulator lanes (no
+ * swapped operands): the planner restricts itself accordingly. */
 int stllm_gemm_norm_f16(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc, int M,
                         int N, int K, const void* bias, const void* residual, long long ldr, int epilogue,
                         int out_f32, int tile_n, int norm_mode, const float* rs_in, int rs_in_stride,
@@ -132,6 +133,14 @@ int stllm_rope_f16(void* x, long long ldx, const int* pos, const float* cos_t, c
 int stllm_gather_rows_f16(const void* src, long long lds, long long src_rows, const long long* idx, void* dst,
                           long long ldd, int n_rows, int cols, const void* addend, int add_period, int* err_flag,
                           void* stream);
+
+/* dst[i,:] = idx[i] >= 0 ? src0[idx[i],:] : src1[-1 - idx[i],:]  (two-source row gather, int64 idx).
+ * Replaces the per-sample torch.cat / slice-assign chains of st_llm.py:379-432,519-530 (prompt_wrap,
+ * concat_emb_input_output, BOS prepend): src0 = token-embedding table, src1 = flattened video tokens, idx = the row plan
+ * built on the host.  err_flag (optional, device int): set to 1 on an out-of-range index. */
+int stllm_gather_rows2_f16(const void* src0, long long lds0, long long rows0, const void* src1, long long lds1,
+                           long long rows1, const long long* idx, void* dst, long long ldd, int n_rows, int cols,
+                           int* err_flag, void* stream);
 
 /* y[b,:] = mean_t x[b,t,:] (fp32 accumulate).  st_llm.py:466,470. */
 int stllm_mean_frames_f16(const void* x, void* y, int B, int T, long long inner, void* stream);

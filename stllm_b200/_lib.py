@@ -36,6 +36,8 @@ SIGNATURES = {
     "stllm_rope_f16": [c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p],
     "stllm_gather_rows_f16": [c_void_p, c_ll, c_ll, c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p, c_int, c_void_p,
                               c_void_p],
+    "stllm_gather_rows2_f16": [c_void_p, c_ll, c_ll, c_void_p, c_ll, c_ll, c_void_p, c_void_p, c_ll, c_int, c_int,
+                               c_void_p, c_void_p],
     "stllm_mean_frames_f16": [c_void_p, c_void_p, c_int, c_int, c_ll, c_void_p],
     "stllm_residual_merge_f16": [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_ll, c_void_p],
     "stllm_preprocess_frames_u8": [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p,

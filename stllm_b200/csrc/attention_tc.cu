@@ -144,40 +144,48 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   if (warp == 4) {
     // ===================== TMA producer (warp 4: highest id on scheduler 0, see gemm_tcgen05.cu) =====================
-    if (lane == 0) {
+    // warp-uniform loop, one elected lane issues (elect_one(), common.cuh)
+    if (elect_one()) {
       mbar_arrive_expect_tx(q_full, 2 * BLK_BYTES);
       tma_load_3d(&tmQ, q_full, sQ, col0, q0, b);
       tma_load_3d(&tmQ, q_full, sQ + BLK_BYTES, col0 + 64, q0, b);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int j = 0; j < n_tiles; ++j) {
-        mbar_wait(&kv_empty[stage], phase ^ 1);
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(&kv_empty[stage], phase ^ 1);
+      uint8_t* k = sK + stage * 2 * KBLK;
+      uint8_t* v = sV + stage * 2 * KBLK;
+      if (elect_one()) {
         mbar_arrive_expect_tx(&kv_full[stage], 4 * KBLK);
-        uint8_t* k = sK + stage * 2 * KBLK;
-        uint8_t* v = sV + stage * 2 * KBLK;
         tma_load_3d(&tmK, &kv_full[stage], k, col0, j * TKV, b);
         tma_load_3d(&tmK, &kv_full[stage], k + KBLK, col0 + 64, j * TKV, b);
         tma_load_3d(&tmV, &kv_full[stage], v, col0, j * TKV, b);
         tma_load_3d(&tmV, &kv_full[stage], v + KBLK, col0 + 64, j * TKV, b);
-        if (++stage == 2) { stage = 0; phase ^= 1; }
       }
+      __syncwarp();
+      if (++stage == 2) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 5) {
     // ===================== MMA issuer (warp 5: highest id on scheduler 1) =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc_pv = make_idesc_f16_bmn(TQ, DV);
-      mbar_wait(q_ready, 0);
+    // Warp-uniform control flow; the elected lane issues tcgen05.mma / commit from uniform registers.  From a divergent
+    // lane-0 region every UTCHMMA sits in a waterfall loop (~87 cycles per issue, profiles/r02_mma_pace.log) -- more than
+    // the 32-64 tensor-pipe cycles of the N = 64 / 96 / 128 MMAs here, i.e. the kernel was issue-bound.
+    constexpr uint32_t idesc_pv = make_idesc_f16_bmn(TQ, DV);
+    mbar_wait(q_ready, 0);
+    tc_fence_after();
+    const uint32_t aq = smem_u32(sQ);
+    // S_j = Q K_j^T into S buffer (j & 1); only ceil16(valid keys) columns are computed for a ragged last tile
+    auto issue_qk = [&](int j) {
+      const int stage = j & 1;
+      mbar_wait(&kv_full[stage], (uint32_t)((j >> 1) & 1));
       tc_fence_after();
-      const uint32_t aq = smem_u32(sQ);
-      // S_j = Q K_j^T into S buffer (j & 1); only ceil16(valid keys) columns are computed for a ragged last tile
-      auto issue_qk = [&](int j) {
-        const int stage = j & 1;
-        mbar_wait(&kv_full[stage], (uint32_t)((j >> 1) & 1));
-        tc_fence_after();
-        int nk = kv_end - j * TKV;
-        nk = nk > TKV ? TKV : ((nk + 15) & ~15);
-        const uint32_t idesc_qk = make_idesc_f16(TQ, nk, false);
-        const uint32_t bk = smem_u32(sK + stage * 2 * KBLK);
+      int nk = kv_end - j * TKV;
+      nk = nk > TKV ? TKV : ((nk + 15) & ~15);
+      const uint32_t idesc_qk = make_idesc_f16(TQ, nk, false);
+      const uint32_t bk = smem_u32(sK + stage * 2 * KBLK);
+      if (elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < DK / 16; ++ks) {
           const uint32_t aoff = (uint32_t)((ks >> 2) * BLK_BYTES + (ks & 3) * 32);
@@ -186,17 +194,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                       idesc_qk, ks > 0 ? 1u : 0u);
         }
         umma_commit(&s_full[stage]);
-      };
-      issue_qk(0);
-      for (int j = 0; j < n_tiles; ++j) {
-        const int stage = j & 1;
-        if (j + 1 < n_tiles) issue_qk(j + 1);      // overlaps the softmax of tile j
-        mbar_wait(p_full, (uint32_t)(j & 1));      // P_j written to smem, O rescaled
-        tc_fence_after();
-        int nk = kv_end - j * TKV;
-        nk = nk > TKV ? TKV : ((nk + 15) & ~15);
-        const uint32_t ap = smem_u32(sK + stage * 2 * KBLK);    // P_j lives in the consumed K stage
-        const uint32_t bv = smem_u32(sV + stage * 2 * KBLK);
+      }
+      __syncwarp();
+    };
+    issue_qk(0);
+    for (int j = 0; j < n_tiles; ++j) {
+      const int stage = j & 1;
+      if (j + 1 < n_tiles) issue_qk(j + 1);      // overlaps the softmax of tile j
+      mbar_wait(p_full, (uint32_t)(j & 1));      // P_j written to smem, O rescaled
+      tc_fence_after();
+      int nk = kv_end - j * TKV;
+      nk = nk > TKV ? TKV : ((nk + 15) & ~15);
+      const uint32_t ap = smem_u32(sK + stage * 2 * KBLK);    // P_j lives in the consumed K stage
+      const uint32_t bv = smem_u32(sV + stage * 2 * KBLK);
+      if (elect_one()) {
+#pragma unroll 4
         for (int ks = 0; ks < nk / 16; ++ks) {
           umma_f16_ss(tmem_O, make_sdesc_k_sw128(ap + ks * 32), make_sdesc_mn_sw128(bv + ks * 2048, KBLK), idesc_pv,
                       (j > 0 || ks > 0) ? 1u : 0u);
@@ -204,6 +216,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         umma_commit(&kv_empty[stage]);   // K/V stage free once QK^T and PV of this tile are done
         umma_commit(pv_done);
       }
+      __syncwarp();
     }
   } else {
     // ===================== softmax warps: thread = query row =====================

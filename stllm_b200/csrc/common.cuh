@@ -180,6 +180,26 @@ DEVI void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
 }
 DEVI void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// One elected lane of a fully converged warp (elect.sync, deterministic: always the same lane for the same mask).
+// The single-thread tcgen05.mma / tcgen05.commit / TMA issue sites use `if (elect_one()) ...` inside WARP-UNIFORM control
+// flow instead of `if (lane == 0) { whole loop }`: with a divergent lane-0 region ptxas cannot prove the operands
+// warp-uniform and wraps every UTCHMMA / UTCBAR / UTMALDG in a "waterfall" loop (ELECT + 5 x R2UR.BROADCAST + BRA.U.ANY)
+// that costs ~87 cycles per MMA issue -- measured on B200 (scripts/ubench/mma_pace.cu, profiles/r02_mma_pace.log): a
+// K = 64 k-block of four N = 128 MMAs takes 349 cycles issued from a lane-0 region, 256 (= the tensor pipe's time) issued
+// through elect_one() from uniform registers.
+DEVI uint32_t elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t"
+      ".reg .b32 rx;\n\t"
+      ".reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "@px mov.s32 %0, 1;\n\t"
+      "}"
+      : "+r"(pred));
+  return pred;
+}
+
 // ----------------------------------------------------------------------------------------------
 // misc
 // ----------------------------------------------------------------------------------------------

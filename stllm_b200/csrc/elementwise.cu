@@ -132,6 +132,32 @@ __global__ void gather_rows_kernel(const __half* __restrict__ src, long long lds
   }
 }
 
+// dst[r] = idx[r] >= 0 ? src0[idx[r]] : src1[-1 - idx[r]]   -- the LLM input of a batch in ONE launch: token-embedding
+// rows and video-token rows selected by the host-built row plan (stllm_b200/prompt_assembly.py; st_llm.py:379-432,519-530)
+__global__ void gather_rows2_kernel(const __half* __restrict__ src0, long long lds0, long long rows0,
+                                    const __half* __restrict__ src1, long long lds1, long long rows1,
+                                    const long long* __restrict__ idx, __half* __restrict__ dst, long long ldd, int n_rows,
+                                    int cols, int* __restrict__ err) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int cv = cols >> 3;
+  const long long total = (long long)n_rows * cv;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % cv);
+    const long long r = i / cv;
+    const long long s = idx[r];
+    const long long s1 = -1 - s;
+    const bool first = s >= 0;
+    if (first ? (s >= rows0) : (s1 >= rows1)) {
+      if (err != nullptr) *err = 1;
+      continue;
+    }
+    const __half* row = first ? src0 + s * lds0 : src1 + s1 * lds1;
+    reinterpret_cast<uint4*>(dst + r * ldd)[c] = __ldg(reinterpret_cast<const uint4*>(row) + c);
+  }
+}
+
 // x: [B, T, inner] -> y: [B, inner], mean over T with fp32 accumulation (torch.mean on fp16 does the same)
 __global__ void mean_frames_kernel(const __half* __restrict__ x, __half* __restrict__ y, int B, int T,
                                    long long inner) {
@@ -452,6 +478,19 @@ extern "C" int stllm_gather_rows_f16(const void* src, long long lds, long long s
   const long long total = (long long)n_rows * (cols / 8);
   STLLM_CHECK_CUDA(stllm_launch(gather_rows_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream, (const __half*)src, lds, idx, (__half*)dst, ldd, n_rows, cols, src_rows, (const __half*)addend, add_period, err_flag));
     return STLLM_OK;
+}
+
+extern "C" int stllm_gather_rows2_f16(const void* src0, long long lds0, long long rows0, const void* src1, long long lds1,
+                                      long long rows1, const long long* idx, void* dst, long long ldd, int n_rows, int cols,
+                                      int* err_flag, void* stream) {
+  STLLM_CHECK_ARG(src0 && src1 && idx && dst && n_rows > 0 && cols > 0 && cols % 8 == 0);
+  STLLM_CHECK_ARG(lds0 % 8 == 0 && lds1 % 8 == 0 && ldd % 8 == 0 && rows0 >= 0 && rows1 >= 0);
+  STLLM_CHECK_ARG((((uintptr_t)src0 | (uintptr_t)src1 | (uintptr_t)dst) & 15) == 0);
+  const long long total = (long long)n_rows * (cols / 8);
+  STLLM_CHECK_CUDA(stllm_launch(gather_rows2_kernel, dim3(grid_for(total, 256)), dim3(256), 0, (cudaStream_t)stream,
+                                (const __half*)src0, lds0, rows0, (const __half*)src1, lds1, rows1, idx, (__half*)dst, ldd,
+                                n_rows, cols, err_flag));
+  return STLLM_OK;
 }
 
 extern "C" int stllm_mean_frames_f16(const void* x, void* y, int B, int T, long long inner, void* stream) {

@@ -57,9 +57,10 @@ struct GemmParams {
   //   consumer side: A holds the UN-normalised rows x, W holds gamma-scaled weights W' = gamma (.) W, and
   //     mode 1 (RMSNorm):   C = rstd_m * (x W'^T)                              rstd_m = rsqrt(sumsq_m / K + eps)
   //     mode 2 (LayerNorm): C = rstd_m * (x W'^T - mu_m * s_n) + b'_n          s_n = sum_k W'_nk, b'_n = b_n + beta.W_n
-  //   producer side: the kernel that writes x stores, per row and per 128-column slot, sum(x) / sum(x^2) of the
-  //   values it wrote (plain stores to distinct slots, summed in slot order by the consumer: deterministic, no
-  //   atomics, no zeroing).  Row layout: [slots][mode] floats, row stride rs_*_stride floats (multiple of 8).
+  //   producer side: the kernel that writes x stores, per row and per (column tile, warp half) slot, sum(x) / sum(x^2)
+  //   of the values it wrote (plain stores to distinct slots, summed in slot order by the consumer: deterministic, no
+  //   atomics, no zeroing).  Row layout: [slots][mode] floats, slots = 2 * column tiles of the producer, row stride
+  //   rs_*_stride floats (multiple of 8, unused slots stay zero).
   int norm_mode;
   const float* rs_in;
   int rs_in_stride;
@@ -230,10 +231,11 @@ DEVI void rowctx_begin(RowCtx& rc, const GemmParams& p, int row, bool row_ok) {
     }
   }
 }
-// `col0`: first global output column of the 128 columns this thread covered in this tile (slot = col0 / 128)
-DEVI void rowctx_end(const RowCtx& rc, const GemmParams& p, int row, bool row_ok, int col0) {
+// `slot`: statistics slot of the columns this thread covered in this tile = 2 * (column tile) + (warp half): every
+// (tile, half) pair writes its own slot, whatever the tile width; the consumer sums ALL slots of the row in slot order.
+DEVI void rowctx_end(const RowCtx& rc, const GemmParams& p, int row, bool row_ok, int slot) {
   if (p.rs_out == nullptr || !row_ok) return;
-  const int off = (col0 >> 7) * p.rs_out_mode;
+  const int off = slot * p.rs_out_mode;
   if (off + p.rs_out_mode > p.rs_out_stride) return;
   float* dst = p.rs_out + (long long)row * p.rs_out_stride + off;
   if (p.rs_out_mode == 1) {
@@ -637,59 +639,66 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 
   if (warp == WARP_TMA) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      long long w_acc = 0;
-      int n_pre = 0;   // k-blocks whose weight tile is already in flight (stages 0..n_pre-1, first work item)
-      if (p.w_prefetch) {
-        WorkIter peek = it;
-        if (peek.next(tile, kb0, kb1)) {
-          const int n_blk = tile / p.m_tiles;
-          n_pre = (kb1 - kb0 < STAGES) ? (kb1 - kb0) : STAGES;
+    // The WHOLE warp runs the (warp-uniform) loop; one elected lane issues (see elect_one() in common.cuh).
+    int stage = 0;
+    uint32_t phase = 0;
+    long long w_acc = 0;
+    int n_pre = 0;   // k-blocks whose weight tile is already in flight (stages 0..n_pre-1, first work item)
+    if (p.w_prefetch) {
+      WorkIter peek = it;
+      if (peek.next(tile, kb0, kb1)) {
+        const int n_blk = tile / p.m_tiles;
+        n_pre = (kb1 - kb0 < STAGES) ? (kb1 - kb0) : STAGES;
+        if (elect_one()) {
           for (int s = 0; s < n_pre; ++s) {
             mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
             tma_load_2d(&tmB, &full_bar[s], smem + s * L::STAGE_BYTES + L::A_BYTES, (kb0 + s) * BK, n_blk * BN, p.hint_b);
           }
         }
+        __syncwarp();
       }
-      pdl_wait();
-      int issued = 0;
-      while (it.next(tile, kb0, kb1)) {
-        const int m_blk = tile % p.m_tiles, n_blk = tile / p.m_tiles;
-        for (int kb = kb0; kb < kb1; ++kb, ++issued) {
-          w_acc += mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * L::STAGE_BYTES;
-          uint8_t* sb = sa + L::A_BYTES;
+    }
+    pdl_wait();
+    int issued = 0;
+    while (it.next(tile, kb0, kb1)) {
+      const int m_blk = tile % p.m_tiles, n_blk = tile / p.m_tiles;
+      for (int kb = kb0; kb < kb1; ++kb, ++issued) {
+        w_acc += mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * L::STAGE_BYTES;
+        uint8_t* sb = sa + L::A_BYTES;
+        if (elect_one()) {
           if (issued >= n_pre) {
             mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
             tma_load_2d(&tmB, &full_bar[stage], sb, kb * BK, n_blk * BN, p.hint_b);
           }
           tma_load_2d(&tmA, &full_bar[stage], sa, kb * BK, m_blk * BM, p.hint_a);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
-      atomicAdd(&g_gemm_prof[0], (unsigned long long)w_acc);
     }
+    if (lane == 0) atomicAdd(&g_gemm_prof[0], (unsigned long long)w_acc);
   } else if (warp == WARP_MMA) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_f16(BM, BN, false);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      long long w_full = 0, w_acc = 0;
-      const long long t_start = clock64();
-      while (it.next(tile, kb0, kb1)) {
-        w_acc += mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+    // Warp-uniform loop, one elected lane issues tcgen05.mma / tcgen05.commit straight from uniform registers: a k-block of
+    // four MMAs then costs the tensor pipe's time (4 x BN / 2 cycles), not 4 x ~87 cycles of waterfall issue.
+    constexpr uint32_t idesc = make_idesc_f16(BM, BN, false);
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    long long w_full = 0, w_acc = 0;
+    const long long t_start = clock64();
+    while (it.next(tile, kb0, kb1)) {
+      w_acc += mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      for (int kb = kb0; kb < kb1; ++kb) {
+        w_full += mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          w_full += mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
-          const uint32_t sb = sa + L::A_BYTES;
+        const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+        const uint32_t sb = sa + L::A_BYTES;
+        if (elect_one()) {
 #pragma unroll
           for (int kk = 0; kk < BK / 16; ++kk) {
             const uint64_t da = make_sdesc_k_sw128(sa + kk * 32);
@@ -697,11 +706,15 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
             umma_f16_ss(d_tmem, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      if (elect_one()) umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (lane == 0) {
       atomicAdd(&g_gemm_prof[1], (unsigned long long)w_full);
       atomicAdd(&g_gemm_prof[2], (unsigned long long)w_acc);
       if (blockIdx.x == 0) {
@@ -741,7 +754,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       }
       epilogue_segment<EPI>(p, rc, t_acc, half_idx * CHUNKS_PER_WARP, (half_idx + 1) * CHUNKS_PER_WARP, row, row < p.M,
                             row_in_tile, n_blk * BN, min(p.N, (n_blk + 1) * BN), kb0 > 0, n_parts, 1, lane);
-      if (kb0 == 0) rowctx_end(rc, p, row, row < p.M, n_blk * BN + half_idx * CHUNKS_PER_WARP * 32);
+      if (kb0 == 0) rowctx_end(rc, p, row, row < p.M, n_blk * 2 + half_idx);
       // all TMEM reads of this warp for this segment are done -> release the accumulator stage
       tc_fence_before();
       __syncwarp();
@@ -844,18 +857,19 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
 
   if (warp == WARP_TMA) {
     // ===================== TMA producer (both CTAs) =====================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      long long w_acc = 0;
-      int a_blk, b_blk;
-      // operand roles: the weight operand is the lane operand in SWAP mode, the column operand otherwise
-      int n_pre = 0;
-      if (p.w_prefetch) {
-        WorkIter peek = it;
-        if (peek.next(tile, kb0, kb1)) {
-          decode(tile, a_blk, b_blk);
-          n_pre = (kb1 - kb0 < STAGES2) ? (kb1 - kb0) : STAGES2;
+    // warp-uniform loop, one elected lane issues (elect_one(), common.cuh)
+    int stage = 0;
+    uint32_t phase = 0;
+    long long w_acc = 0;
+    int a_blk, b_blk;
+    // operand roles: the weight operand is the lane operand in SWAP mode, the column operand otherwise
+    int n_pre = 0;
+    if (p.w_prefetch) {
+      WorkIter peek = it;
+      if (peek.next(tile, kb0, kb1)) {
+        decode(tile, a_blk, b_blk);
+        n_pre = (kb1 - kb0 < STAGES2) ? (kb1 - kb0) : STAGES2;
+        if (elect_one()) {
           for (int s = 0; s < n_pre; ++s) {
             uint8_t* sa = smem + s * L::STAGE_BYTES;
             if (is_leader) mbar_arrive_expect_tx(&full_bar[s], stage_tx);
@@ -863,30 +877,35 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
             else tma_load_2d_2sm(&tmB, &full_bar[s], sa + L::A_BYTES, (kb0 + s) * BK, b_blk * bn + (int)cta_rank * (bn / 2), p.hint_b);
           }
         }
+        __syncwarp();
       }
-      pdl_wait();
-      TRACE(2);
-      int issued = 0;
-      while (it.next(tile, kb0, kb1)) {
-        decode(tile, a_blk, b_blk);
-        const int row_a = a_blk * 256 + (int)cta_rank * 128;
-        const int row_b = b_blk * bn + (int)cta_rank * (bn / 2);
-        for (int kb = kb0; kb < kb1; ++kb, ++issued) {
-          w_acc += mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * L::STAGE_BYTES;
-          uint8_t* sb = sa + L::A_BYTES;
-          const bool pre = issued < n_pre;   // weight tile of this k-block already requested
+    }
+    pdl_wait();
+    if (lane == 0) TRACE(2);
+    int issued = 0;
+    while (it.next(tile, kb0, kb1)) {
+      decode(tile, a_blk, b_blk);
+      const int row_a = a_blk * 256 + (int)cta_rank * 128;
+      const int row_b = b_blk * bn + (int)cta_rank * (bn / 2);
+      for (int kb = kb0; kb < kb1; ++kb, ++issued) {
+        w_acc += mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sa = smem + stage * L::STAGE_BYTES;
+        uint8_t* sb = sa + L::A_BYTES;
+        const bool pre = issued < n_pre;   // weight tile of this k-block already requested
+        if (elect_one()) {
           if (is_leader && !pre) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
           if (!(pre && SWAP)) tma_load_2d_2sm(&tmA, &full_bar[stage], sa, kb * BK, row_a, p.hint_a);
           if (!(pre && !SWAP)) tma_load_2d_2sm(&tmB, &full_bar[stage], sb, kb * BK, row_b, p.hint_b);
-          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
         }
+        __syncwarp();
+        if (++stage == STAGES2) { stage = 0; phase ^= 1; }
       }
-      atomicAdd(&g_gemm_prof[0], (unsigned long long)w_acc);
     }
+    if (lane == 0) atomicAdd(&g_gemm_prof[0], (unsigned long long)w_acc);
   } else if (warp == WARP_MMA) {
     // ===================== MMA issuer (leader CTA only) =====================
-    if (is_leader && lane == 0) {
+    // warp-uniform loop; the elected lane issues tcgen05.mma.cta_group::2 / multicast commits from uniform registers
+    if (is_leader) {
       const uint32_t idesc = make_idesc_f16(256, bn, false);
       int stage = 0;
       uint32_t phase = 0;
@@ -902,33 +921,44 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN2_MAX);
         for (int kb = kb0; kb < kb1; ++kb) {
           w_full += mbar_wait(&full_bar[stage], phase);
-          if (first) { TRACE(3); first = false; c_first = clock64(); w_full_first = w_full; }
+          if (first) {
+            if (lane == 0) TRACE(3);
+            first = false;
+            c_first = clock64();
+            w_full_first = w_full;
+          }
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
           const uint32_t sb = sa + L::A_BYTES;
+          if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < BK / 16; ++kk) {
-            const uint64_t da = make_sdesc_k_sw128(sa + kk * 32);
-            const uint64_t db = make_sdesc_k_sw128(sb + kk * 32);
-            umma_f16_ss_2sm(d_tmem, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+            for (int kk = 0; kk < BK / 16; ++kk) {
+              const uint64_t da = make_sdesc_k_sw128(sa + kk * 32);
+              const uint64_t db = make_sdesc_k_sw128(sb + kk * 32);
+              umma_f16_ss_2sm(d_tmem, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+            }
+            umma_commit_2sm(&empty_bar[stage], 3);   // frees this smem slot in BOTH CTAs
           }
-          umma_commit_2sm(&empty_bar[stage], 3);   // frees this smem slot in BOTH CTAs
+          __syncwarp();
           if (++stage == STAGES2) { stage = 0; phase ^= 1; }
         }
-        umma_commit_2sm(&tmem_full_bar[acc], 3);   // accumulators of both CTAs complete
+        if (elect_one()) umma_commit_2sm(&tmem_full_bar[acc], 3);   // accumulators of both CTAs complete
+        __syncwarp();
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      TRACE(4);
-      if (p.trace && blockIdx.x < 160) {
-        g_gemm_trace[p.trace - 1][blockIdx.x][8] = (unsigned long long)(clock64() - c_first);
-        g_gemm_trace[p.trace - 1][blockIdx.x][9] = (unsigned long long)(w_full - w_full_first);
-        g_gemm_trace[p.trace - 1][blockIdx.x][10] = (unsigned long long)w_acc;
-      }
-      atomicAdd(&g_gemm_prof[1], (unsigned long long)w_full);
-      atomicAdd(&g_gemm_prof[2], (unsigned long long)w_acc);
-      if (blockIdx.x == 0) {
-        atomicAdd(&g_gemm_prof[4], (unsigned long long)(clock64() - t_start));
-        atomicAdd(&g_gemm_prof[5], 1ull);
+      if (lane == 0) {
+        TRACE(4);
+        if (p.trace && blockIdx.x < 160) {
+          g_gemm_trace[p.trace - 1][blockIdx.x][8] = (unsigned long long)(clock64() - c_first);
+          g_gemm_trace[p.trace - 1][blockIdx.x][9] = (unsigned long long)(w_full - w_full_first);
+          g_gemm_trace[p.trace - 1][blockIdx.x][10] = (unsigned long long)w_acc;
+        }
+        atomicAdd(&g_gemm_prof[1], (unsigned long long)w_full);
+        atomicAdd(&g_gemm_prof[2], (unsigned long long)w_acc);
+        if (blockIdx.x == 0) {
+          atomicAdd(&g_gemm_prof[4], (unsigned long long)(clock64() - t_start));
+          atomicAdd(&g_gemm_prof[5], 1ull);
+        }
       }
     }
   } else {
@@ -981,7 +1011,7 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
         }
         epilogue_segment<EPI>(p, rc, t_acc, c_begin, c_end, row, row < p.M, row_in_slot, b_blk * bn,
                               min(p.N, (b_blk + 1) * bn), kb0 > 0, n_parts, 2, lane);
-        if (kb0 == 0) rowctx_end(rc, p, row, row < p.M, b_blk * bn + c_begin * 32);
+        if (kb0 == 0) rowctx_end(rc, p, row, row < p.M, b_blk * 2 + half_idx);
       }
       tc_fence_before();
       __syncwarp();
@@ -1141,22 +1171,30 @@ int dispatch_epi_2cta(int epi, const CUtensorMap& tmA, const CUtensorMap& tmB, c
 }
 
 // ------------------------------------------------------------------------------------------------
-// Cost model, in SM cycles -- from the per-CTA timelines measured on B200 (profiles/r01_gemm_timeline.md):
-//   * CTA-pair engine: one k-block (K = 64) of a 256 x bn tile takes ~555 cycles for EVERY bn in 128..256 (and for the
-//     swapped 144 / 192-token tiles): the tensor pipe is paced by the 128-row A operand of each MMA, not by N, so only
-//     N = 256 tiles reach the pipe's peak (92 % measured) and narrower tiles cost the same time for less work.
-//   * one-CTA engine: 128 x 256 tiles are operand-ingest bound (48 KB per k-block and SM at ~73 B/cycle = 675 cycles).
-//   * the MMA issuer never waits for operands (0.0 % measured) -- time = (k-blocks on the busiest CTA) x k-block time
-//     + ~2 us dependency resolution + ~0.8 us first operand round trip + ~3.6 us un-overlapped last epilogue.
-// => minimise waves x k-blocks; narrower or swapped tiles only pay when they remove a whole wave.
+// Cost model, in SM cycles -- re-fitted in round 2 (profiles/r02_mma_pace.log, profiles/r02_gemm_sweep_a.log) after the
+// MMA issue path was fixed (elect_one(), common.cuh).  With the operands in uniform registers a K = 64 k-block costs
+//     pipe   = 4 MMAs x max(64, N_per_SM / 2) cycles      (128-row A per SM: N = 256 -> 512, 192 -> 384, 128 -> 256;
+//                                                          ~60 cycles is the floor of one tcgen05.mma issue)
+//     ingest = operand bytes per SM and k-block / B_cyc    (L2 -> SMEM when every SM pulls: ~70 B/cycle/SM for the
+//                                                          CTA-pair tiles, ~88 for the one-CTA 128 x 256 tile)
+//     k-block time = max(pipe, ingest)
+// so 256 x 192 / 256 x 176 pair tiles are ~25 % cheaper per k-block than 256 x 256 and win wherever they do not add a
+// wave (round 1 measured ~555 cycles for EVERY width: that was the ~87-cycle waterfall issue of each MMA from a
+// divergent lane-0 region, not the tensor pipe).  time = waves x (k-blocks x k-block time + tile fixed) + epilogue tail.
 // ------------------------------------------------------------------------------------------------
-constexpr double PAIR_KB_CYCLES = 555.0;
-constexpr double INGEST_B_PER_CYCLE = 73.0;
+constexpr double PAIR_INGEST_B_PER_CYCLE = 70.0;
+constexpr double ONE_INGEST_B_PER_CYCLE = 88.0;
 constexpr double TILE_FIXED_CYCLES = 400.0;
 
-double kb_cycles(int cols, int bytes_per_sm) {
-  const double ing = bytes_per_sm / INGEST_B_PER_CYCLE;
-  return ing > PAIR_KB_CYCLES ? ing : PAIR_KB_CYCLES;
+double kb_cycles_pair(int bn) {
+  const double pipe = 4.0 * (bn / 2 > 64 ? bn / 2 : 64);
+  const double ing = (16384.0 + 64.0 * bn) / PAIR_INGEST_B_PER_CYCLE;
+  return pipe > ing ? pipe : ing;
+}
+double kb_cycles_one(int bn) {
+  const double pipe = 4.0 * (bn / 2 > 64 ? bn / 2 : 64);
+  const double ing = (16384.0 + 128.0 * bn) / ONE_INGEST_B_PER_CYCLE;
+  return pipe > ing ? pipe : ing;
 }
 double sched_cost(int tiles, int workers, int k_blocks, double kb_cost, double epi_tail, bool sk_possible) {
   const int full = tiles / workers, rem = tiles % workers;
@@ -1180,8 +1218,10 @@ int env_int(const char* name, int dflt) {
   return e != nullptr ? atoi(e) : dflt;
 }
 
-GemmPlan plan_gemm(int M, int N, int K, int epi, bool allow_swap = true, bool only_256 = false) {
-  static const int flex = env_int("STLLM_GEMM_FLEX", 1);   // 0: round-1 selection (tiles of 64/128/256 columns only)
+// `stats_out`: the epilogue writes per-row statistics (rs_out): tile columns are split between two warp halves, one
+// statistics slot each -> any pair width >= 128 works (2 x column tiles slots), one-CTA tiles need BN = 256.
+GemmPlan plan_gemm(int M, int N, int K, int epi, bool allow_swap = true, bool stats_out = false) {
+  static const int flex = env_int("STLLM_GEMM_FLEX", 1);   // 0: tiles of 64/128/256 columns only
   static const int swap_ok = env_int("STLLM_GEMM_SWAP", 1);
   const int k_blocks = (K + BK - 1) / BK;
   const int sms = num_sms(), clusters = sms / 2;
@@ -1191,25 +1231,27 @@ GemmPlan plan_gemm(int M, int N, int K, int epi, bool allow_swap = true, bool on
     if (cost < best.cost) best = GemmPlan{engine, bn, cost};
   };
   // one-CTA engine
-  consider(0, 256, sched_cost(mt * ((N + 255) / 256), sms, k_blocks, kb_cycles(256, 16384 + 256 * 128), 14.0 * 256, true));
-  if (!only_256) consider(0, 128, 1.03 * sched_cost(mt * ((N + 127) / 128), sms, k_blocks, kb_cycles(128, 16384 + 128 * 128), 14.0 * 128, false));
-  if (!only_256) consider(0, 64, 1.03 * sched_cost(mt * ((N + 63) / 64), sms, k_blocks, kb_cycles(64, 16384 + 64 * 128), 14.0 * 64, false));
+  consider(0, 256, sched_cost(mt * ((N + 255) / 256), sms, k_blocks, kb_cycles_one(256), 14.0 * 256, true));
+  if (!stats_out) consider(0, 128, sched_cost(mt * ((N + 127) / 128), sms, k_blocks, kb_cycles_one(128), 14.0 * 128, false));
+  if (!stats_out) consider(0, 64, sched_cost(mt * ((N + 63) / 64), sms, k_blocks, kb_cycles_one(64), 14.0 * 64, false));
   // CTA-pair engine: 256 rows x bn columns per cluster
   const int m2 = (M + 255) / 256;
   if (M > 128) {
-    for (int bn = 256; bn >= ((flex && !only_256) ? 96 : 256); bn -= 16) {   // widest first: ties go to the wider tile
+    const int bn_min = !flex ? 256 : (stats_out ? 128 : 96);
+    for (int bn = 256; bn >= bn_min; bn -= 16) {   // widest first: ties go to the wider tile
       const int tiles = m2 * ((N + bn - 1) / bn);
-      const double c = sched_cost(tiles, clusters, k_blocks, kb_cycles(bn, 16384 + bn * 64), 14.0 * bn, bn == 256);
-      consider(1, bn, bn == 256 ? c : 1.03 * c);
+      consider(1, bn, sched_cost(tiles, clusters, k_blocks, kb_cycles_pair(bn), 14.0 * bn, bn == 256));
     }
   }
-  // swapped operands: 256 features x bn tokens per cluster (transposed epilogue: slightly dearer per element)
-  if (flex && swap_ok && allow_swap && N >= 256 && (epi != EPI_SWIGLU || N % 2 == 0)) {
+  // swapped operands: 256 features x bn tokens per cluster.  The transposed epilogue (lane-pair exchange, 4-byte
+  // accesses) is ~4x dearer per element than the row-wise one: swapping only pays when the mainloop saving is large
+  // (measured: Llama q|k|v, lm_head), not for one-wave GEMMs whose whole epilogue is exposed (o_proj, down)
+  if (flex && swap_ok && allow_swap && !stats_out && N >= 256 && (epi != EPI_SWIGLU || N % 2 == 0)) {
     const int f2 = (N + 255) / 256;
     const int m16 = ((M + 15) / 16) * 16;
     for (int bn = m16 < 256 ? m16 : 256; bn >= 16; bn -= 16) {
       const int tiles = f2 * ((M + bn - 1) / bn);
-      consider(2, bn, 1.05 * sched_cost(tiles, clusters, k_blocks, kb_cycles(bn, 16384 + bn * 64), 20.0 * bn, false));
+      consider(2, bn, 1.03 * sched_cost(tiles, clusters, k_blocks, kb_cycles_pair(bn), 60.0 * bn, false));
     }
   }
   return best;
@@ -1288,7 +1330,7 @@ extern "C" int stllm_gemm_f16(const void* A, long long lda, const void* W, long 
 
 // GEMM with a LayerNorm / RMSNorm of the A rows folded in, and/or per-row statistics of C written for the NEXT folded
 // GEMM (see GemmParams).  norm_mode 0: none; 1: RMSNorm; 2: LayerNorm (col_sb = [N][2] (s_n, b'_n), `bias` must be
-// NULL).  Statistics rows: [slots][mode] floats with slots = ceil(columns / 128), row stride rs_*_stride floats
+// NULL).  Statistics rows: [slots][mode] floats, 2 slots per column tile of the producer (<= 2 * ceil(columns / 128)), row stride rs_*_stride floats
 // (multiple of 8, >= slots * mode; padding must be zero).  rs_out_mode 0: none; 1: sum c^2; 2: (sum c, sum c^2).
 // W must already be scaled by the norm weight (W' = gamma (.) W).
 extern "C" int stllm_gemm_norm_f16(const void* A, long long lda, const void* W, long long ldw, void* C, long long ldc,
@@ -1346,7 +1388,8 @@ int gemm_impl(const void* A, long long lda, const void* W, long long ldw, void* 
   STLLM_CHECK_ARG(pl.bn >= 16 && pl.bn <= 256 && pl.bn % 16 == 0);
   const bool swap = pl.engine == 2;
   STLLM_CHECK_ARG(!(swap && fused_rows));
-  STLLM_CHECK_ARG(na.rs_out == nullptr || pl.bn == 256);   // statistics slots are 128 columns = one warp's share of a 256 tile
+  // statistics slots: 2 per column tile (one per warp half)
+  STLLM_CHECK_ARG(na.rs_out == nullptr || na.rs_out_stride >= na.rs_out_mode * 2 * ((N + pl.bn - 1) / pl.bn));
   // lane operand (128-row boxes) and column operand (bn or bn/2-row boxes)
   const void* lane_ptr = swap ? W : A;
   const void* col_ptr = swap ? A : W;

@@ -117,9 +117,11 @@ def gemm(a, w, bias=None, residual=None, epilogue=EPI_NONE, out=None, out_dtype=
 
 def row_stats_buffer(n_buffers, rows, cols, mode, device):
     """zeroed per-row statistics buffers [n_buffers, rows, stride] for the folded norms: `cols` = width of the
-    normalised rows, one slot of `mode` floats per 128 columns, row stride padded to 8 floats.  Every slot is rewritten
-    by the producing GEMM on each forward, the padding stays zero: no per-step zeroing is needed."""
-    stride = (((cols + 127) // 128) * mode + 7) // 8 * 8
+    normalised rows.  The producing GEMM writes one slot of `mode` floats per (column tile, warp half) -- 2 slots per tile
+    of >= 128 columns, so 2 * ceil(cols / 128) slots cover every tile width the planner may pick; the consumer sums all
+    slots in order.  Row stride padded to 8 floats.  Live slots are rewritten on each forward, the others stay zero: no
+    per-step zeroing is needed."""
+    stride = (2 * ((cols + 127) // 128) * mode + 7) // 8 * 8
     return torch.zeros(n_buffers, rows, stride, dtype=torch.float32, device=device)
 
 
@@ -271,6 +273,27 @@ def gather_rows(src, idx, out=None, addend=None):
                                            addend.shape[0] if addend is not None else 0, ctypes.c_void_p(0),
                                            _stream())
     _lib.check(rc, "stllm_gather_rows_f16")
+    launch_count += 1
+    return out
+
+
+def gather_rows2(src0, src1, idx, out=None):
+    """out[i, :] = src0[idx[i], :] if idx[i] >= 0 else src1[-1 - idx[i], :]   (fp16 [R, C] sources, int64 idx [n])"""
+    global launch_count
+    _need_cuda(src0, src1, idx, out)
+    for s in (src0, src1):
+        assert s.dim() == 2 and s.stride(1) == 1 and s.dtype == torch.float16
+    assert src0.shape[1] == src1.shape[1]
+    idx = idx.to(torch.int64).contiguous()
+    n = idx.numel()
+    if out is None:
+        out = torch.empty((n, src0.shape[1]), dtype=torch.float16, device=src0.device)
+    if n == 0:
+        return out
+    rc = _lib.load().stllm_gather_rows2_f16(_ptr(src0), src0.stride(0), src0.shape[0], _ptr(src1), src1.stride(0),
+                                            src1.shape[0], _ptr(idx), _ptr(out), out.stride(0), n, src0.shape[1],
+                                            ctypes.c_void_p(0), _stream())
+    _lib.check(rc, "stllm_gather_rows2_f16")
     launch_count += 1
     return out
 

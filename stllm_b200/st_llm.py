@@ -19,6 +19,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from . import prompt_assembly as PA
 from .eva_vit import create_eva_vit_g, VisionTransformer
 from .llama import (BaseModelOutputWithPast, CausalLMOutputWithPast, KVCache, LlamaConfig, LlamaModel)
 from .qformer import BertConfig, BertLMHeadModel
@@ -204,48 +205,63 @@ class STLLMModel(nn.Module):
     # the north_star's name for the same function (VideoChat2 naming)
     encode_videoQformer_visual = encode_img
 
+    # ---- sequence assembly: host-built row plan + one two-source gather per LLM pass (prompt_assembly.py) ----------
+    def _prompt_token_ids(self, prompts, batch):
+        """token ids before / after `<ImageHere>` per sample (st_llm.py:385-389); every distinct prompt is tokenised once"""
+        if isinstance(prompts, str):
+            prompts = [prompts] * batch
+        cache, before, after = {}, [], []
+        for prompt in list(prompts)[:batch]:
+            if prompt not in cache:
+                p_before, p_after = PA.split_prompt(prompt)
+                tb = self.llama_tokenizer(p_before, return_tensors="pt", add_special_tokens=False).input_ids
+                ta = self.llama_tokenizer(p_after, return_tensors="pt",
+                                          add_special_tokens=self.qformer_text_input).input_ids
+                cache[prompt] = (tb.reshape(-1).cpu().numpy().astype(np.int64),
+                                 ta.reshape(-1).cpu().numpy().astype(np.int64))
+            before.append(cache[prompt][0])
+            after.append(cache[prompt][1])
+        return before, after
+
+    def _gather_plan(self, rows, video2d):
+        """rows: int64 [B, S] row codes (device) -> [B, S, D] embeddings in ONE launch"""
+        w = self.embed_tokens.weight
+        w = w if w.dtype == torch.float16 else w.half()
+        out = ops.gather_rows2(w, video2d, rows.reshape(-1))
+        return out.view(rows.shape[0], rows.shape[1], w.shape[1])
+
     @torch.no_grad()
     def prompt_wrap(self, img_embeds, atts_img, prompts):
-        """st_llm.py:379-407"""
-        if prompts:
-            emb_lists = []
-            if isinstance(prompts, str):
-                prompts = [prompts] * len(img_embeds)
-            dev = img_embeds.device
-            for each_img_embed, each_prompt in zip(img_embeds, prompts):
-                p_before, p_after = each_prompt.split("<ImageHere>")
-                p_before_tokens = self.llama_tokenizer(p_before, return_tensors="pt", add_special_tokens=False).to(dev)
-                p_after_tokens = self.llama_tokenizer(p_after, return_tensors="pt",
-                                                      add_special_tokens=self.qformer_text_input).to(dev)
-                p_before_embed = self._embed(p_before_tokens.input_ids) \
-                    if min(p_before_tokens.input_ids.shape) != 0 else None
-                p_after_embed = self._embed(p_after_tokens.input_ids)
-                if len(each_img_embed.size()) == 2:
-                    each_img_embed = each_img_embed[None]
-                wrapped_emb = torch.cat([p_before_embed, each_img_embed, p_after_embed], dim=1) \
-                    if p_before_embed is not None else torch.cat([each_img_embed, p_after_embed], dim=1)
-                emb_lists.append(wrapped_emb)
-            emb_lens = [emb.shape[1] for emb in emb_lists]
-            pad_emb = self._embed(torch.tensor(self.llama_tokenizer.pad_token_id, device=dev))
-            wrapped_embs = pad_emb.expand(len(emb_lens), max(emb_lens), -1).clone()
-            wrapped_atts = torch.zeros([len(emb_lens), max(emb_lens)], dtype=torch.int, device=dev)
-            for i, emb in enumerate(emb_lists):
-                wrapped_embs[i, :emb_lens[i]] = emb
-                wrapped_atts[i, :emb_lens[i]] = 1
-            return wrapped_embs, wrapped_atts
-        return img_embeds, atts_img
+        """st_llm.py:379-407 for callers that hold embeddings: [before | img | after] per sample, right-padded with
+        embed(pad).  Not used by forward(), which plans the whole sequence (answer, BOS, padding) at once."""
+        if not prompts:
+            return img_embeds, atts_img
+        B = img_embeds.shape[0]
+        vid = img_embeds.reshape(B, -1, img_embeds.shape[-1])
+        before, after = self._prompt_token_ids(prompts, B)
+        plan = PA.plan_sequences(PA.video_row_codes(B, vid.shape[1]), before, after, None, None,
+                                 self.llama_tokenizer.pad_token_id)
+        dev = img_embeds.device
+        embs = self._gather_plan(torch.from_numpy(plan.rows).to(dev), vid.reshape(-1, vid.shape[-1]).contiguous())
+        return embs, torch.from_numpy(plan.attention_mask).to(device=dev, dtype=torch.int)
 
+    @torch.no_grad()
     def concat_emb_input_output(self, input_embs, input_atts, output_embs, output_atts):
-        """st_llm.py:409-432"""
-        input_lens, cat_embs, cat_atts = [], [], []
-        lens_host = input_atts.sum(dim=1).tolist()
-        for i in range(input_embs.size(0)):
-            input_len = int(lens_host[i])
-            input_lens.append(input_len)
-            cat_embs.append(torch.cat([input_embs[i][:input_len], output_embs[i], input_embs[i][input_len:]]))
-            cat_atts.append(torch.cat([input_atts[i][:input_len], output_atts[i].to(input_atts.dtype),
-                                       input_atts[i][input_len:]]))
-        return torch.stack(cat_embs), torch.stack(cat_atts), input_lens
+        """st_llm.py:409-432 for callers that hold embeddings: splice the answer block in after each sample's valid
+        inputs -- one two-source gather over (input rows, answer rows)."""
+        B, W, D = input_embs.shape
+        La = output_embs.shape[1]
+        atts_host = input_atts.cpu().numpy()
+        rows = torch.from_numpy(PA.splice_rows(atts_host, La)).to(input_embs.device)
+        embs = ops.gather_rows2(input_embs.reshape(B * W, D).contiguous(), output_embs.reshape(B * La, D).contiguous(),
+                                rows.reshape(-1)).view(B, W + La, D)
+        n = atts_host.sum(axis=1)
+        out_atts = output_atts.cpu().numpy().astype(np.int64)
+        pos = np.arange(W + La)[None, :]
+        atts = np.where(pos < n[:, None], 1, 0).astype(np.int64)
+        in_ans = (pos >= n[:, None]) & (pos < n[:, None] + La)
+        atts[in_ans] = out_atts.reshape(-1)
+        return embs, torch.from_numpy(atts).to(input_embs.device), [int(v) for v in n]
 
     def get_residual_index(self, sample_segments, total_segments, devices):
         """st_llm.py:434-445"""
@@ -275,70 +291,62 @@ class STLLMModel(nn.Module):
 
     @torch.no_grad()
     def forward(self, samples):
-        """st_llm.py:447-546"""
+        """st_llm.py:447-546: samples -> (inputs_embeds, attention_mask, unmask_inputs_embeds, unmask_attention_mask,
+        targets).  Encoder and aggregation run in the kernels; everything after them is ONE host-built row plan per LLM
+        pass (prompt_assembly.plan_sequences) + one gather launch, instead of the reference's per-sample cat/pad loops."""
         image = samples["image"]
-        instruction = samples["instruction_input"] if "instruction_input" in samples else None
+        prompts = samples["instruction_input"] if "instruction_input" in samples else None
         use_image = False
-        if self.pre_encoding:
-            img_embeds = _linear(self.llama_proj, image.half())
-            atts_img = torch.ones(img_embeds.size()[:-1], dtype=torch.long, device=image.device)
+        if self.pre_encoding:                                            # st_llm.py:452-455
+            video = _linear(self.llama_proj, image.half())
         else:
-            if self.qformer_text_input:
-                qformer_text_input = [it.split("Human: ")[1].split(" ###")[0] for it in instruction]
-            else:
-                qformer_text_input = None
-            img_embeds, atts_img, use_image = self.encode_img(image, qformer_text_input)
+            q_text = [it.split("Human: ")[1].split(" ###")[0] for it in prompts] if self.qformer_text_input else None
+            video, _, use_image = self.encode_img(image, q_text)
         if not use_image:
-            img_embeds = self.aggregate_video(img_embeds)
-        B, _, L, D = img_embeds.size()
-        dev = img_embeds.device
-        unmask_img_embeds = None
-        if not use_image and self.use_mask:
+            video = self.aggregate_video(video)
+        if video.dim() != 4:
+            raise ValueError("video tokens must be [B, 1, L, D] here (set video_input to all | mean | residual)")
+        B, _, L, D = video.size()
+        dev = video.device
+        keep = None
+        if not use_image and self.use_mask:                              # st_llm.py:482-493 (numpy RNG order preserved)
             self.img_len = L
             rate = np.random.normal(0.5, 0.1)
             mask_rate = float(np.clip(rate, 0.1, 0.7)) if getattr(self, "fixed_mask_rate", None) is None \
                 else float(self.fixed_mask_rate)
             mask_cpu = RandomMaskingGenerator(L, mask_rate, B, "cpu").unsqueeze(1)
             self.mask = mask_cpu.to(dev)
-            unmask_img_embeds = img_embeds
-            unmask_atts_img = torch.ones(unmask_img_embeds.size()[:-1], dtype=torch.long, device=dev)
-            keep = torch.nonzero(~mask_cpu.reshape(-1)).reshape(-1).to(dev)     # row-major order == img_embeds[~mask]
-            img_embeds = ops.gather_rows(img_embeds.reshape(B * L, D), keep).view(B, 1, -1, D)
-            atts_img = torch.ones(img_embeds.size()[:-1], dtype=torch.long, device=dev)
-            self.mask_img_len = img_embeds.size(2)
-
-        img_embeds, atts_img = self.prompt_wrap(img_embeds, atts_img, instruction)
-        self.llama_tokenizer.padding_side = "right"
-        text = [t + self.llama_tokenizer.eos_token for t in samples["answer"]] if self.qformer_text_input \
-            else [t + self.end_sym for t in samples["answer"]]
-        to_regress_tokens = self.llama_tokenizer(text, return_tensors="pt", padding="longest", truncation=True,
-                                                 max_length=self.max_txt_len, add_special_tokens=False).to(dev)
-        to_regress_embeds = self._embed(to_regress_tokens.input_ids)
-        inputs_embeds, attention_mask, input_lens = self.concat_emb_input_output(
-            img_embeds, atts_img, to_regress_embeds, to_regress_tokens.attention_mask)
-        if unmask_img_embeds is not None:
-            unmask_img_embeds, unmask_atts_img = self.prompt_wrap(unmask_img_embeds, unmask_atts_img, instruction)
-            unmask_inputs_embeds, unmask_attention_mask, _ = self.concat_emb_input_output(
-                unmask_img_embeds, unmask_atts_img, to_regress_embeds, to_regress_tokens.attention_mask)
-        if not self.qformer_text_input:
-            batch_size = img_embeds.shape[0]
-            bos = torch.ones([batch_size, 1], dtype=to_regress_tokens.input_ids.dtype,
-                             device=dev) * self.llama_tokenizer.bos_token_id
-            bos_embeds = self._embed(bos)
-            atts_bos = atts_img[:, :1]
-            inputs_embeds = torch.cat([bos_embeds, inputs_embeds], dim=1)
-            attention_mask = torch.cat([atts_bos, attention_mask], dim=1)
-            if unmask_img_embeds is not None:
-                unmask_inputs_embeds = torch.cat([bos_embeds, unmask_inputs_embeds], dim=1)
-                unmask_attention_mask = torch.cat([atts_bos, unmask_attention_mask], dim=1)
-        part_targets = to_regress_tokens.input_ids.masked_fill(
-            to_regress_tokens.input_ids == self.llama_tokenizer.pad_token_id, -100)
-        targets = torch.ones([inputs_embeds.shape[0], inputs_embeds.shape[1]], dtype=torch.long, device=dev).fill_(-100)
-        offset = 0 if self.qformer_text_input else 1
-        for i, target in enumerate(part_targets):
-            targets[i, input_lens[i] + offset:input_lens[i] + len(target) + offset] = target
-        if unmask_img_embeds is None:
-            unmask_inputs_embeds, unmask_attention_mask = None, None
+            keep = ~mask_cpu.reshape(B, L).numpy()
+            self.mask_img_len = int(keep[0].sum())
+        if not prompts:
+            raise ValueError("samples['instruction_input'] with an <ImageHere> placeholder is required")
+        tok = self.llama_tokenizer
+        before, after = self._prompt_token_ids(prompts, B)
+        tok.padding_side = "right"                                       # st_llm.py:497
+        text = [t + (tok.eos_token if self.qformer_text_input else self.end_sym) for t in samples["answer"]]
+        ans = tok(text, return_tensors="pt", padding="longest", truncation=True, max_length=self.max_txt_len,
+                  add_special_tokens=False)
+        a_ids, a_att = ans.input_ids.cpu().numpy(), ans.attention_mask.cpu().numpy()
+        bos = None if self.qformer_text_input else tok.bos_token_id       # st_llm.py:519-530
+        plans = [PA.plan_sequences(PA.video_row_codes(B, L, keep), before, after, a_ids, a_att, tok.pad_token_id, bos)]
+        if keep is not None:
+            plans.append(PA.plan_sequences(PA.video_row_codes(B, L), before, after, a_ids, a_att, tok.pad_token_id, bos))
+        # one host -> device copy for all integer planes of all passes
+        flat = np.concatenate([np.concatenate([p.rows.reshape(-1), p.attention_mask.reshape(-1)]) for p in plans]
+                              + [plans[0].targets.reshape(-1)])
+        packed = torch.from_numpy(flat).to(dev)
+        video2d = video.reshape(B * L, D)
+        video2d = video2d if video2d.is_contiguous() else video2d.contiguous()
+        outs, o = [], 0
+        for p in plans:
+            n = p.rows.size
+            rows = packed[o:o + n].view(p.rows.shape)
+            att = packed[o + n:o + 2 * n].view(p.rows.shape)
+            o += 2 * n
+            outs.append((self._gather_plan(rows, video2d), att))
+        targets = packed[o:].view(plans[0].targets.shape)
+        inputs_embeds, attention_mask = outs[0]
+        unmask_inputs_embeds, unmask_attention_mask = outs[1] if keep is not None else (None, None)
         return inputs_embeds, attention_mask, unmask_inputs_embeds, unmask_attention_mask, targets
 
     @classmethod

@@ -217,24 +217,85 @@ def flow_weights(seed=0):
 
 
 @torch.no_grad()
-def golden_flow(ref):
+def golden_flow(ref, text=True):
     """Whole training-branch hot path a1-a22 through the reference's own methods:
     STLLMForCausalLM.forward(samples) -> STLLMLlamaModel.forward -> STLLMModel.forward (encode_img, residual
-    aggregation, dynamic mask, prompt_wrap, concat, targets) -> LLM masked+unmasked passes -> MVM + CE loss."""
+    aggregation, dynamic mask, prompt_wrap, concat, targets) -> LLM masked+unmasked passes -> MVM + CE loss.
+    text=True: the InstructBLIP layout (Q-Former text input, video first, img_start 0) -> stllm_flow.npz;
+    text=False: the MiniGPT-4 layout (BOS + 7-token prefix, img_start 8, st_llm.py:71,519-530) -> stllm_flow_minigpt4.npz.
+    The integer planes of STLLMModel.forward (attention masks, targets) are stored too: they pin the sequence assembly."""
     import json
     from tests.flow_fixture import build_reference_flow, flow_samples, weights_checksum
-    llm, M, sd = build_reference_flow(ref)
-    samples = flow_samples()
+    llm, M, sd = build_reference_flow(ref, text=text)
+    samples = flow_samples(text=text)
     np.random.seed(1237)
     out = llm(samples=samples)
-    _save("stllm_flow.npz", loss=out.loss.numpy(), logits_head=out.logits[:, :, :64].numpy(),
-          logits_shape=np.array(out.logits.shape), mask=M.mask.numpy(), img_len=M.img_len,
-          mask_img_len=M.mask_img_len, residual_index=M.residual_index.numpy(),
-          weights_checksum=np.float64(weights_checksum(sd)))
-    # the reference's own state-dict keys (the checkpoint contract of SURVEY section 5)
-    keys = {k: list(v.shape) for k, v in llm.state_dict().items()}
-    with open(os.path.join(HERE, "stllm_flow_state_dict_keys.json"), "w") as f:
-        json.dump(keys, f, indent=0, sort_keys=True)
+    mask, img_len, mask_img_len = M.mask.numpy().copy(), M.img_len, M.mask_img_len
+    np.random.seed(1237)
+    emb, att, emb_u, att_u, targets = M(samples)          # the reference's own STLLMModel.forward, same RNG state
+    assert np.array_equal(M.mask.numpy(), mask)
+    _save("stllm_flow.npz" if text else "stllm_flow_minigpt4.npz", loss=out.loss.numpy(),
+          logits_head=out.logits[:, :, :64].numpy(), logits_shape=np.array(out.logits.shape), mask=mask, img_len=img_len,
+          mask_img_len=mask_img_len, residual_index=M.residual_index.numpy(),
+          weights_checksum=np.float64(weights_checksum(sd)), attention_mask=att.numpy(),
+          unmask_attention_mask=att_u.numpy(), targets=targets.numpy(), inputs_embeds_head=emb[:, :, :16].numpy(),
+          unmask_inputs_embeds_head=emb_u[:, :, :16].numpy())
+    if text:
+        # the reference's own state-dict keys (the checkpoint contract of SURVEY section 5)
+        keys = {k: list(v.shape) for k, v in llm.state_dict().items()}
+        with open(os.path.join(HERE, "stllm_flow_state_dict_keys.json"), "w") as f:
+            json.dump(keys, f, indent=0, sort_keys=True)
+
+
+@torch.no_grad()
+def golden_assembly(ref):
+    """The host half of the reference's STLLMModel.forward (st_llm.py:447-546: mask draw + compaction, prompt_wrap,
+    concat_emb_input_output, BOS, targets) run UNMODIFIED on a stub object whose encode_img returns seeded video tokens
+    (D = 8): ragged prompts and answers, both prompt layouts, with and without the dynamic mask -> assembly_kat.npz.
+    Pins stllm_b200/prompt_assembly.py bit-exactly (everything here is copies and integer logic)."""
+    import torch.nn as nn
+    st = ref.st_llm
+    B, T, Q, D, V = 3, 2, 4, 8, 64
+    g = torch.Generator().manual_seed(77)
+    table = torch.randn(V, D, generator=g)
+    video = torch.randn(B, T, Q, D, generator=g)
+    answers = ["yes", "a man is slicing bread on a table in the kitchen", "two dogs"]
+    cases = {
+        "text": dict(text=True, end_sym="\n", prompts=[
+            "<ImageHere>###Human: what happens ? ###Assistant: ",
+            "<ImageHere>###Human: describe the video in detail please ###Assistant: ",
+            "<ImageHere>###Human: why ###Assistant: "]),
+        "minigpt4": dict(text=False, end_sym=" ###", prompts=[
+            "### Human : < Video > clip <ImageHere> </Video> what happens ? ###Assistant: ",
+            "### Human : < Video > clip <ImageHere> </Video> describe the video in detail please ###Assistant: ",
+            "###Human: <Video> <ImageHere> </Video> why ###Assistant: "]),        # a shorter prefix too (ragged before)
+        "same_prompt": dict(text=True, end_sym="\n", prompts="<ImageHere>###Human: what is shown ? ###Assistant: "),
+    }
+    out = dict(table=table.numpy(), video=video.numpy(), answers=np.array(answers))
+    for name, c in cases.items():
+        for use_mask in (False, True):
+            M = st.STLLMModel.__new__(st.STLLMModel)
+            nn.Module.__init__(M)
+            M.pre_encoding, M.video_input, M.use_mask, M.mvm_decode = False, "all", use_mask, False
+            M.qformer_text_input, M.max_txt_len, M.end_sym = c["text"], 8, c["end_sym"]
+            M.llama_tokenizer = fake_tokenizer.FakeTokenizer(V, pad_token_id=0, bos_token_id=1, eos_token_id=2)
+            M.embed_tokens = nn.Embedding(V, D)
+            M.embed_tokens.weight.data.copy_(table)
+            M.encode_img = lambda image, text: (video.clone(), torch.ones(B, T, Q, dtype=torch.long), False)
+            prompts = c["prompts"] if isinstance(c["prompts"], list) else [c["prompts"]] * B
+            samples = {"image": torch.zeros(B, T, 3, 2, 2), "instruction_input": prompts, "answer": answers}
+            np.random.seed(4321)
+            emb, att, emb_u, att_u, targets = st.STLLMModel.forward(M, samples)
+            key = f"{name}.mask{int(use_mask)}."
+            out[key + "prompts"] = np.array(prompts)
+            out[key + "inputs_embeds"] = emb.numpy()
+            out[key + "attention_mask"] = att.numpy()
+            out[key + "targets"] = targets.numpy()
+            if use_mask:
+                out[key + "mask"] = M.mask.numpy()
+                out[key + "unmask_inputs_embeds"] = emb_u.numpy()
+                out[key + "unmask_attention_mask"] = att_u.numpy()
+    _save("assembly_kat.npz", **out)
 
 
 @torch.no_grad()
@@ -271,8 +332,8 @@ def golden_noqformer(ref):
 
 if __name__ == "__main__":
     ref = ref_shim.load_reference()
-    which = sys.argv[1:] or ["vit", "qformer", "qformer_text", "llama", "mask", "flow", "btadapter", "preprocess",
-                             "noqformer"]
+    which = sys.argv[1:] or ["vit", "qformer", "qformer_text", "llama", "mask", "flow", "flow_minigpt4", "assembly",
+                             "btadapter", "preprocess", "noqformer", "generate"]
     if "vit" in which:
         golden_vit(ref)
     if "qformer" in which:
@@ -285,6 +346,10 @@ if __name__ == "__main__":
         golden_mask(ref)
     if "flow" in which:
         golden_flow(ref)
+    if "flow_minigpt4" in which:
+        golden_flow(ref, text=False)
+    if "assembly" in which:
+        golden_assembly(ref)
     if "btadapter" in which:
         golden_btadapter(ref)
     if "preprocess" in which:
