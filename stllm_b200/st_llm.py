@@ -498,14 +498,16 @@ class STLLMForCausalLM(nn.Module):
     # ---- generation (greedy / beam / sampling) over the kernel forward ------------------------------------
     @torch.no_grad()
     def generate(self, inputs_embeds=None, input_ids=None, max_new_tokens=20, stopping_criteria=None, num_beams=1,
-                 do_sample=False, min_length=1, top_p=1.0, repetition_penalty=1.0, length_penalty=1.0,
-                 temperature=1.0, eos_token_id=None, pad_token_id=None, attention_mask=None, **unused):
+                 do_sample=False, min_length=0, top_p=1.0, repetition_penalty=1.0, length_penalty=1.0,
+                 temperature=1.0, eos_token_id=None, pad_token_id=None, attention_mask=None, hf_semantics=None, **unused):
+        """HF GenerationMixin.generate for the options the reference passes (conversation.py:231-243); hf_semantics:
+        "4.28" (pinned by the reference, default) | "5" (installed release, fixture-pinned) -- see generation.py"""
         from .generation import generate as _generate
         return _generate(self, inputs_embeds=inputs_embeds, input_ids=input_ids, max_new_tokens=max_new_tokens,
                          stopping_criteria=stopping_criteria, num_beams=num_beams, do_sample=do_sample,
                          min_length=min_length, top_p=top_p, repetition_penalty=repetition_penalty,
                          length_penalty=length_penalty, temperature=temperature, eos_token_id=eos_token_id,
-                         pad_token_id=pad_token_id, attention_mask=attention_mask)
+                         pad_token_id=pad_token_id, attention_mask=attention_mask, hf_semantics=hf_semantics)
 
     # ---- construction -------------------------------------------------------------------------------------
     @classmethod

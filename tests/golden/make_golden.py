@@ -330,6 +330,70 @@ def golden_noqformer(ref):
           **_sd_arrays("w.", sd))
 
 
+GEN_CASES = {
+    # name: generate kwargs (the harness settings of SURVEY 3A / conversation.py:231-243: do_sample False, min_length 1, ...).
+    # min_length counts the prompt when generate() gets inputs_embeds only (installed transformers: `_prepare_generated_length`
+    # subtracts the prompt length), so values below prompt_len = 19 are no-ops -- like the reference's min_length = 1.
+    "greedy": dict(num_beams=1, max_new_tokens=24, min_length=1, repetition_penalty=1.0, length_penalty=1.0),
+    "greedy_rp15_min6": dict(num_beams=1, max_new_tokens=24, min_length=19 + 6, repetition_penalty=1.5, length_penalty=1.0),
+    "beam5": dict(num_beams=5, max_new_tokens=24, min_length=1, repetition_penalty=1.0, length_penalty=1.0),
+    "beam5_rp15": dict(num_beams=5, max_new_tokens=24, min_length=1, repetition_penalty=1.5, length_penalty=1.0),
+    "beam5_min8_lp2": dict(num_beams=5, max_new_tokens=20, min_length=19 + 8, repetition_penalty=1.0, length_penalty=2.0),
+    "beam3_lp05_short": dict(num_beams=3, max_new_tokens=6, min_length=1, repetition_penalty=1.2, length_penalty=0.5),
+    "beam5_noeos_maxlen": dict(num_beams=5, max_new_tokens=10, min_length=19 + 11, repetition_penalty=1.0, length_penalty=1.0),
+    "beam4_rp13_lp15": dict(num_beams=4, max_new_tokens=16, min_length=19 + 3, repetition_penalty=1.3, length_penalty=1.5),
+}
+GEN_MODEL = dict(hidden=256, heads=2, layers=2, inter=512, vocab=96, prompt_len=19)
+
+
+def build_reference_generate_model(ref, seed=11):
+    """small reference STLLMForCausalLM (head dim 128: the decode engine's shape) with a peaky next-token distribution"""
+    st = ref.st_llm
+    torch.manual_seed(seed)
+    m = GEN_MODEL
+    cfg = st.StllmConfig(hidden_size=m["hidden"], num_attention_heads=m["heads"], num_key_value_heads=m["heads"],
+                         intermediate_size=m["inter"], num_hidden_layers=m["layers"], vocab_size=m["vocab"],
+                         max_position_embeddings=256, rms_norm_eps=1e-6, attn_implementation="eager", pad_token_id=0,
+                         bos_token_id=1, eos_token_id=2)
+    llm = st.STLLMForCausalLM(cfg).eval()
+    g = torch.Generator().manual_seed(seed)
+    for n, p in llm.named_parameters():
+        if p.dim() >= 2:
+            std = 0.05
+            if "embed_tokens" in n:
+                std = 1.0
+            if "lm_head" in n:
+                std = 0.35                      # peaky distributions: decisions are robust to fp16 rounding
+            p.data.copy_(torch.randn(p.shape, generator=g) * std)
+        else:
+            p.data.copy_(1.0 + 0.1 * torch.randn(p.shape, generator=g))
+    llm.lm_head.weight.data[2] *= 2.5           # EOS (id 2) wins often enough that finished hypotheses compete
+    _round_fp16_(llm)
+    return llm
+
+
+@torch.no_grad()
+def golden_generate(ref):
+    """Token ids of the reference's OWN `STLLMForCausalLM.generate(inputs_embeds=...)` (inherited HF GenerationMixin; the
+    transformers release installed here executes it -- recorded in the file) for greedy and beam search with the harness
+    settings; 3 prompts per case.  Also the per-step decision margins, so that a fixture whose decisions hinge on fp16
+    rounding is rejected when it is made."""
+    import transformers
+    llm = build_reference_generate_model(ref)
+    m = GEN_MODEL
+    g = torch.Generator().manual_seed(5)
+    prompts = (torch.randn(3, m["prompt_len"], m["hidden"], generator=g)).half().float()
+    out = dict(prompts=prompts.numpy(), transformers_version=np.array(transformers.__version__),
+               **_sd_arrays("w.", llm.state_dict()))
+    for name, kw in GEN_CASES.items():
+        for pi in range(prompts.shape[0]):
+            ids = llm.generate(inputs_embeds=prompts[pi:pi + 1], do_sample=False, top_p=0.9, temperature=1.0, **kw)
+            assert ids.shape[0] == 1
+            out[f"{name}.p{pi}"] = ids[0].numpy()
+            print(name, pi, ids[0].tolist())
+    _save("generate_small.npz", **out)
+
+
 if __name__ == "__main__":
     ref = ref_shim.load_reference()
     which = sys.argv[1:] or ["vit", "qformer", "qformer_text", "llama", "mask", "flow", "flow_minigpt4", "assembly",
@@ -356,3 +420,5 @@ if __name__ == "__main__":
         golden_preprocess()
     if "noqformer" in which:
         golden_noqformer(ref)
+    if "generate" in which:
+        golden_generate(ref)

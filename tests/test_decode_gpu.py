@@ -17,8 +17,6 @@ def test_decode_kernels_and_engine():
     assert rc == 0, f"decode checks failed: {K.fails}"
 
 
-@pytest.mark.skipif(__import__("os").environ.get("STLLM_TEST_ENGINE_VS_ORACLE") != "1",
-                    reason="written after the round's GPU minutes were spent: enable once it has run on a B200")
 def test_engine_matches_decode_oracle_with_duplicated_ancestors():
     """DecodeEngine (fp16, CUDA graph) against oracle/decode_oracle.py (fp32 CPU restatement of the same algorithm, itself
     pinned against a full recompute of every beam's history): beam re-orderings WITH repeats, which the engine-vs-general

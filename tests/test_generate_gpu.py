@@ -61,15 +61,62 @@ def _assert_follows_argmax(llm, emb, tokens, tie=2e-2):
 
 def test_generate_engine_and_general_route_agree(monkeypatch):
     """batch-1 generate runs on the decode engine (csrc/decode.cu, CUDA graph); STLLM_DECODE_ENGINE=0 forces the
-    general kernels: both must produce argmax-consistent greedy tokens and the same beam result up to near-ties"""
+    general kernels: both must produce argmax-consistent greedy tokens and THE SAME beam token ids"""
     llm, sd, g = _small_llm()
     emb = torch.from_numpy(g["inputs_embeds"])[:1, :12].cuda().half()
     eng = llm.generate(inputs_embeds=emb, max_new_tokens=10, num_beams=1, do_sample=False, eos_token_id=-1)
+    beam_e = llm.generate(inputs_embeds=emb, max_new_tokens=8, num_beams=5, do_sample=False)
     monkeypatch.setenv("STLLM_DECODE_ENGINE", "0")
     gen = llm.generate(inputs_embeds=emb, max_new_tokens=10, num_beams=1, do_sample=False, eos_token_id=-1)
+    beam_g = llm.generate(inputs_embeds=emb, max_new_tokens=8, num_beams=5, do_sample=False)
     monkeypatch.delenv("STLLM_DECODE_ENGINE")
     assert eng.shape == gen.shape == (1, 10)
     _assert_follows_argmax(llm, emb, eng[0].tolist())
     _assert_follows_argmax(llm, emb, gen[0].tolist())
-    beam_e = llm.generate(inputs_embeds=emb, max_new_tokens=8, num_beams=5, do_sample=False)
     assert beam_e.shape[0] == 1 and 1 <= beam_e.shape[1] <= 8 and int(beam_e.max()) < 128
+    assert beam_e[0].tolist() == beam_g[0].tolist(), (beam_e, beam_g)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# token ids of the reference's OWN generate (tests/golden/generate_small.npz, written by STLLMForCausalLM.generate of the
+# reference through HF GenerationMixin): the CUDA path must reproduce them exactly, on the decode engine and on the general
+# kernels, greedy and beam search with repetition penalty / min_length / length penalty.
+# ----------------------------------------------------------------------------------------------------------------------
+GEN_CASES = {
+    "greedy": dict(num_beams=1, max_new_tokens=24, min_length=1, repetition_penalty=1.0, length_penalty=1.0),
+    "greedy_rp15_min6": dict(num_beams=1, max_new_tokens=24, min_length=19 + 6, repetition_penalty=1.5, length_penalty=1.0),
+    "beam5": dict(num_beams=5, max_new_tokens=24, min_length=1, repetition_penalty=1.0, length_penalty=1.0),
+    "beam5_rp15": dict(num_beams=5, max_new_tokens=24, min_length=1, repetition_penalty=1.5, length_penalty=1.0),
+    "beam5_min8_lp2": dict(num_beams=5, max_new_tokens=20, min_length=19 + 8, repetition_penalty=1.0, length_penalty=2.0),
+    "beam3_lp05_short": dict(num_beams=3, max_new_tokens=6, min_length=1, repetition_penalty=1.2, length_penalty=0.5),
+    "beam5_noeos_maxlen": dict(num_beams=5, max_new_tokens=10, min_length=19 + 11, repetition_penalty=1.0, length_penalty=1.0),
+    "beam4_rp13_lp15": dict(num_beams=4, max_new_tokens=16, min_length=19 + 3, repetition_penalty=1.3, length_penalty=1.5),
+}
+_gen_llm = None
+
+
+def _generate_llm():
+    global _gen_llm
+    if _gen_llm is None:
+        from stllm_b200.st_llm import STLLMForCausalLM, StllmConfig
+        sd, g = load_golden("generate_small.npz")
+        cfg = StllmConfig(hidden_size=256, num_attention_heads=2, intermediate_size=512, num_hidden_layers=2, vocab_size=96,
+                          max_position_embeddings=256, rms_norm_eps=1e-6, pad_token_id=0, bos_token_id=1, eos_token_id=2)
+        llm = STLLMForCausalLM(cfg)
+        res = llm.load_state_dict(sd, strict=False)
+        assert not res.unexpected_keys, res.unexpected_keys
+        _gen_llm = (llm.half().cuda(), g)
+    return _gen_llm
+
+
+@pytest.mark.parametrize("route", ["engine", "general"])
+@pytest.mark.parametrize("name", list(GEN_CASES))
+def test_generate_token_ids_equal_the_reference_generate(name, route, monkeypatch):
+    llm, g = _generate_llm()
+    if route == "general":
+        monkeypatch.setenv("STLLM_DECODE_ENGINE", "0")
+    prompts = torch.from_numpy(g["prompts"]).cuda().half()
+    for pi in range(prompts.shape[0]):
+        out = llm.generate(inputs_embeds=prompts[pi:pi + 1], do_sample=False, top_p=0.9, temperature=1.0, hf_semantics="5",
+                           **GEN_CASES[name])
+        assert out[0].tolist() == g[f"{name}.p{pi}"].tolist(), (name, route, pi)

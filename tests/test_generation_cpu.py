@@ -150,14 +150,33 @@ def test_eos_min_length_and_padding_rules():
 def test_repetition_penalty_and_top_p_filter():
     logits = torch.tensor([[2.0, -1.0, 0.5, 0.0]])
     gen = torch.tensor([[0, 1]])
-    out = G._process_logits(logits, gen, cur_len=3, min_length=1, eos_ids=[], repetition_penalty=2.0, temperature=1.0)
+    out = G._process_scores(logits.clone(), gen, min_length=1, eos_ids=[], repetition_penalty=2.0)
     assert torch.allclose(out, torch.tensor([[1.0, -2.0, 0.5, 0.0]]))   # positive / 2, negative * 2 (HF rule)
-    out = G._process_logits(logits, gen, cur_len=1, min_length=3, eos_ids=[2], repetition_penalty=1.0, temperature=0.5)
-    assert math.isinf(float(out[0, 2])) and torch.allclose(out[0, [0, 1, 3]], torch.tensor([4.0, -2.0, 0.0]))
+    out = G._process_scores(logits.clone(), gen, min_length=3, eos_ids=[2], repetition_penalty=1.0)
+    assert math.isinf(float(out[0, 2])) and torch.allclose(out[0, [0, 1, 3]], torch.tensor([2.0, -1.0, 0.0]))
+    out = G._process_scores(logits.clone(), gen, min_length=2, eos_ids=[2], repetition_penalty=1.0)
+    assert torch.isfinite(out).all()                                     # history as long as min_length: EOS allowed
     p = torch.tensor([[0.5, 0.3, 0.15, 0.05]]).log()
     kept = torch.isfinite(G._top_p_filter(p, 0.8))
     assert kept.tolist() == [[True, True, False, False]]                 # smallest set with mass >= 0.8
     assert torch.isfinite(G._top_p_filter(p, 1.0)).all()
+
+
+def test_min_length_counts_the_prompt_in_hf5_and_the_dummy_bos_in_hf428():
+    assert G._effective_min_length(1, 576, "5") == 0          # the harnesses' min_length=1 is a no-op on either release
+    assert G._effective_min_length(580, 576, "5") == 4
+    assert G._effective_min_length(1, 576, "4.28") == 1       # [dummy BOS] already has length 1: EOS allowed at once
+    lm = FakeLM(vocab=5, eos=2, seed=5)
+    lm._logits_for = lambda hist: torch.tensor([0.0, 0.0, 9.0, 0.0, 0.0])
+    for sem, want_len in (("4.28", 4), ("5", 7)):             # prompt S=3: "5" bans EOS for min_length - 3 = ... tokens
+        out = G.generate(lm, inputs_embeds=_emb(), max_new_tokens=12, num_beams=1, min_length=4 if sem == "4.28" else 9,
+                         hf_semantics=sem)
+        assert out.shape[1] == want_len and out[0, -1].item() == 2 and (out[0, :-1] != 2).all(), (sem, out)
+
+
+def test_beam_sample_is_rejected_loudly():
+    with pytest.raises(NotImplementedError):
+        G.generate(FakeLM(), inputs_embeds=_emb(), max_new_tokens=3, num_beams=2, do_sample=True)
 
 
 def test_sampling_is_seeded_and_respects_top_p():
