@@ -71,6 +71,11 @@ int stllm_gemm_norm_f16(const void* A, long long lda, const void* W, long long l
                         const float* col_sb, float norm_eps, float* rs_out, int rs_out_mode, int rs_out_stride,
                         void* stream);
 
+/* Stream-K scheduling of the ragged last wave of stllm_gemm_f16 (fp32 partial tiles through the workspace): -1 = follow
+ * the STLLM_GEMM_SK environment variable (default: off -- it loses under the power cap), 0 = off,
+ * 1 = selective rule, 2 = every shape (used by the parity tests to exercise the fix-up path). */
+int stllm_set_gemm_streamk(int mode);
+
 /* The configuration the cost model picks for a shape (host only, no launch): out3 = {engine: 0 one-CTA, 1 CTA pair,
  * 2 CTA pair with swapped operands; tile columns; estimated SM cycles}. */
 int stllm_gemm_plan(int M, int N, int K, int epilogue, long long* out3);

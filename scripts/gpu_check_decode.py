@@ -75,7 +75,12 @@ def linear_case(R, N, K, norm_mode=0, epi=ops.EPI_NONE, residual=False, alias=Fa
                       residual=res, epilogue=epi)
     torch.cuda.synchronize()
     name = f"decode_linear R={R} N={N} K={K} norm={norm_mode} epi={epi} res={int(residual)} alias={int(alias)} pad={x_pad}"
-    return report(name, out, ref, atol=2e-2, rtol=1e-2)
+    # fp32 accumulation, one fp16 rounding of the result: north_star's rtol 1e-3 / atol 1e-4 for the plain and folded forms;
+    # the explicit RMSNorm form (norm_mode 2) rounds the normalised activations to fp16 first, like the reference: +1 ulp
+    atol, rtol = (1e-4, 1e-3) if norm_mode != 2 else (1e-3, 2e-3)
+    if epi == ops.EPI_SWIGLU:
+        atol = max(atol, 2e-4 * ref.abs().max().item())
+    return report(name, out, ref, atol=atol, rtol=rtol)
 
 
 def attn_setup(R, H, Sp, n_gen, l_max, mask=False, seed=0):
@@ -437,65 +442,88 @@ def time_generate(layers, beams, S=576, new_tokens=64):
     return res
 
 
+CASES = []     # (name, callable -> bool); tests/test_decode_gpu.py parametrises over them
+
+
+def _c(fn, *a, **kw):
+    name = f"{len(CASES):03d}:{fn.__name__} " + " ".join(str(x) for x in a) + "".join(f" {k}={v}" for k, v in kw.items())
+
+    def run():
+        torch.manual_seed(len(name))
+        return bool(fn(*a, **kw))
+    CASES.append((name, run))
+
+
+def build_cases():
+    if CASES:
+        return CASES
+    # ---- decode_linear: tiny first ----
+    _c(linear_case, 1, 16, 32)
+    _c(linear_case, 1, 16, 64)
+    _c(linear_case, 3, 48, 96)                       # K*2 % 128 == 64: no smem padding
+    _c(linear_case, 8, 256, 256)
+    _c(linear_case, 5, 200, 512)                     # N not a multiple of 16
+    _c(linear_case, 5, 100, 512, residual=True)
+    _c(linear_case, 2, 768, 256, norm_mode=1)
+    _c(linear_case, 2, 768, 256, norm_mode=2)
+    _c(linear_case, 2, 1024, 256, norm_mode=1, epi=ops.EPI_SWIGLU)
+    _c(linear_case, 2, 256, 512, residual=True, alias=True)
+    _c(linear_case, 4, 128, 256, norm_mode=2, x_pad=8)
+    # Vicuna-7B shapes
+    _c(linear_case, 5, 12288, 4096, norm_mode=1)
+    _c(linear_case, 5, 12288, 4096, norm_mode=2)
+    _c(linear_case, 1, 4096, 4096, residual=True, alias=True)
+    _c(linear_case, 5, 22016, 4096, norm_mode=1, epi=ops.EPI_SWIGLU)
+    _c(linear_case, 8, 22016, 4096, norm_mode=2, epi=ops.EPI_SWIGLU)
+    _c(linear_case, 5, 4096, 11008, residual=True, alias=True)
+    _c(linear_case, 8, 4096, 11008, residual=True)
+    _c(linear_case, 5, 32000, 4096, norm_mode=2)
+    _c(linear_case, 1, 32001, 4096, norm_mode=2)     # vocab with the added [PAD] (st_llm.py:306-310)
+    # ---- rope + cache append ----
+    _c(rope_append_case, 5, 32, 576, 0, 16)
+    _c(rope_append_case, 1, 2, 12, 7, 8)
+    _c(rope_append_case, 8, 32, 100, 15, 16)
+    # ---- attention ----
+    _c(attn_case, 1, 2, 12, 0, 8, 1)
+    _c(attn_case, 1, 2, 12, 3, 8, 4)
+    _c(attn_case, 3, 2, 5, 6, 8, 4)                   # fewer prefix keys than splits*... (empty slices)
+    _c(attn_case, 5, 32, 576, 0, 64, 4)
+    _c(attn_case, 5, 32, 576, 37, 64, 4)
+    _c(attn_case, 5, 32, 577, 63, 64, 3, mask=True)
+    _c(attn_case, 8, 32, 1500, 299, 300, 4)
+    _c(attn_case, 2, 4, 0, 5, 8, 2)                   # no prefix at all
+    _c(attn_case, 5, 32, 576, 20, 64, 1)
+    # ---- fused rope + append + attention + merge ----
+    _c(attn_fused_case, 1, 2, 12, 0, 8, 1)
+    _c(attn_fused_case, 1, 2, 12, 3, 8, 4)
+    _c(attn_fused_case, 3, 2, 5, 6, 8, 4)
+    _c(attn_fused_case, 5, 32, 576, 0, 64, 5)
+    _c(attn_fused_case, 5, 32, 576, 37, 64, 5, repeats=3)
+    _c(attn_fused_case, 5, 32, 576, 38, 64, 4, prefetch=True)
+    _c(attn_fused_case, 5, 32, 577, 63, 64, 3, mask=True)      # > 128 prompt keys per split: second batch of loads
+    _c(attn_fused_case, 8, 32, 1500, 299, 300, 12)
+    _c(attn_fused_case, 8, 32, 1500, 299, 300, 4)
+    _c(attn_fused_case, 2, 4, 0, 5, 8, 2)
+    _c(attn_fused_case, 1, 32, 576, 150, 256, 5)               # greedy: all 16 warps on one beam's generated keys
+    _c(attn_fused_case, 5, 32, 576, 20, 64, 1)
+    # ---- engine vs the general kernels (model.forward + KVCache) ----
+    _c(engine_vs_general, 2, 256, 512, 2, 128, 12, 1, 5, use_graph=False)
+    _c(engine_vs_general, 2, 256, 512, 2, 128, 12, 3, 6, use_graph=True, mask=True)
+    _c(engine_vs_general, 2, 4096, 11008, 32, 32000, 64, 5, 6, use_graph=True)
+    return CASES
+
+
 def main():
     print(torch.cuda.get_device_name(0), flush=True)
     torch.manual_seed(0)
     t0 = time.time()
     if "--time-only" in sys.argv:
         return timings()
-    # ---- decode_linear: tiny first ----
-    linear_case(1, 16, 32)
-    linear_case(1, 16, 64)
-    linear_case(3, 48, 96)                       # K*2 % 128 == 64: no smem padding
-    linear_case(8, 256, 256)
-    linear_case(5, 200, 512)                     # N not a multiple of 16
-    linear_case(5, 100, 512, residual=True)
-    linear_case(2, 768, 256, norm_mode=1)
-    linear_case(2, 768, 256, norm_mode=2)
-    linear_case(2, 1024, 256, norm_mode=1, epi=ops.EPI_SWIGLU)
-    linear_case(2, 256, 512, residual=True, alias=True)
-    linear_case(4, 128, 256, norm_mode=2, x_pad=8)
-    # Vicuna-7B shapes
-    linear_case(5, 12288, 4096, norm_mode=1)
-    linear_case(5, 12288, 4096, norm_mode=2)
-    linear_case(1, 4096, 4096, residual=True, alias=True)
-    linear_case(5, 22016, 4096, norm_mode=1, epi=ops.EPI_SWIGLU)
-    linear_case(8, 22016, 4096, norm_mode=2, epi=ops.EPI_SWIGLU)
-    linear_case(5, 4096, 11008, residual=True, alias=True)
-    linear_case(8, 4096, 11008, residual=True)
-    linear_case(5, 32000, 4096, norm_mode=2)
-    linear_case(1, 32001, 4096, norm_mode=2)     # vocab with the added [PAD] (st_llm.py:306-310)
-    # ---- rope + cache append ----
-    rope_append_case(5, 32, 576, 0, 16)
-    rope_append_case(1, 2, 12, 7, 8)
-    rope_append_case(8, 32, 100, 15, 16)
-    # ---- attention ----
-    attn_case(1, 2, 12, 0, 8, 1)
-    attn_case(1, 2, 12, 3, 8, 4)
-    attn_case(3, 2, 5, 6, 8, 4)                   # fewer prefix keys than splits*... (empty slices)
-    attn_case(5, 32, 576, 0, 64, 4)
-    attn_case(5, 32, 576, 37, 64, 4)
-    attn_case(5, 32, 577, 63, 64, 3, mask=True)
-    attn_case(8, 32, 1500, 299, 300, 4)
-    attn_case(2, 4, 0, 5, 8, 2)                   # no prefix at all
-    attn_case(5, 32, 576, 20, 64, 1)
-    # ---- fused rope + append + attention + merge ----
-    attn_fused_case(1, 2, 12, 0, 8, 1)
-    attn_fused_case(1, 2, 12, 3, 8, 4)
-    attn_fused_case(3, 2, 5, 6, 8, 4)
-    attn_fused_case(5, 32, 576, 0, 64, 5)
-    attn_fused_case(5, 32, 576, 37, 64, 5, repeats=3)
-    attn_fused_case(5, 32, 576, 38, 64, 4, prefetch=True)
-    attn_fused_case(5, 32, 577, 63, 64, 3, mask=True)      # > 128 prompt keys per split: second batch of loads
-    attn_fused_case(8, 32, 1500, 299, 300, 12)
-    attn_fused_case(8, 32, 1500, 299, 300, 4)
-    attn_fused_case(2, 4, 0, 5, 8, 2)
-    attn_fused_case(1, 32, 576, 150, 256, 5)               # greedy: all 16 warps on one beam's generated keys
-    attn_fused_case(5, 32, 576, 20, 64, 1)
-    # ---- engine vs the general kernels (model.forward + KVCache) ----
-    engine_vs_general(2, 256, 512, 2, 128, 12, 1, 5, use_graph=False)
-    engine_vs_general(2, 256, 512, 2, 128, 12, 3, 6, use_graph=True, mask=True)
-    engine_vs_general(2, 4096, 11008, 32, 32000, 64, 5, 6, use_graph=True)
+    only = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--only=")]
+    for name, fn in build_cases():
+        if only and not any(o in name for o in only):
+            continue
+        fn()
     print(f"decode checks done in {time.time() - t0:.1f}s; failures: {len(fails)}", flush=True)
     for f in fails:
         print("  FAILED:", f)

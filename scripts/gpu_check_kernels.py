@@ -8,8 +8,6 @@ import time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
-os.environ.setdefault("STLLM_GEMM_SK", "2")  # exercise the hybrid stream-K schedule in the 256/512 cases
-
 from stllm_b200 import ops
 
 torch.manual_seed(0)
@@ -40,7 +38,7 @@ def report(name, got, ref, atol, rtol):
     return ok
 
 
-def gemm_case(M, N, K, epi=ops.EPI_NONE, bias=False, residual=False, tile_n=0, out_f32=False, lda_pad=0):
+def gemm_case(M, N, K, epi=ops.EPI_NONE, bias=False, residual=False, tile_n=0, out_f32=False, lda_pad=0, sk=None):
     a_full = torch.randn(M, K + lda_pad, device=dev, dtype=torch.float16) * 0.5
     a = a_full[:, :K]
     w = torch.randn(N, K, device=dev, dtype=torch.float16) * 0.05
@@ -58,14 +56,28 @@ def gemm_case(M, N, K, epi=ops.EPI_NONE, bias=False, residual=False, tile_n=0, o
         ref = torch.nn.functional.silu(ref[:, 0::2]) * ref[:, 1::2]
     if residual:
         ref = ref + r.float()
-    out = ops.gemm(a, w, bias=b, residual=r, epilogue=epi, tile_n=tile_n,
-                   out_dtype=torch.float32 if out_f32 else torch.float16)
-    torch.cuda.synchronize()
-    name = f"gemm M={M} N={N} K={K} epi={epi} bias={int(bias)} res={int(residual)} tn={tile_n} f32={int(out_f32)} pad={lda_pad}"
-    return report(name, out, ref, atol=2e-2 if not out_f32 else 5e-3, rtol=1e-2)
+    from stllm_b200 import _lib as _L
+    if sk is not None:          # stream-K treatment of the last wave (off in the product): exercise the fix-up path
+        _L.check(_L.load().stllm_set_gemm_streamk(sk), "stllm_set_gemm_streamk")
+    try:
+        out = ops.gemm(a, w, bias=b, residual=r, epilogue=epi, tile_n=tile_n,
+                       out_dtype=torch.float32 if out_f32 else torch.float16)
+        torch.cuda.synchronize()
+    finally:
+        if sk is not None:
+            _L.load().stllm_set_gemm_streamk(-1)
+    name = f"gemm M={M} N={N} K={K} epi={epi} bias={int(bias)} res={int(residual)} tn={tile_n} f32={int(out_f32)} pad={lda_pad} sk={sk}"
+    # north_star's tolerance (rtol 1e-3 / atol 1e-4) is attainable here and asserted: fp32 accumulation, ONE fp16 rounding
+    # of the result (relative 2^-11 = 4.9e-4).  The absolute floor carries the fp32 summation-ORDER noise between two correct
+    # fp32 sums (~ sqrt(K) eps |terms|; measured 5e-5 at |ref| 8, K = 4096, fp32 output): 1e-4 up to |ref| 5, 2e-5 |ref|max above.
+    floor = max(1e-4, 2e-5 * ref.abs().max().item())
+    atol, rtol = (floor, 1e-3) if not out_f32 else (floor, 1e-5)
+    if epi == ops.EPI_SWIGLU:
+        atol = max(atol, 1e-4 * ref.abs().max().item() / 8)   # silu(g) * u of two O(10) numbers: the floor scales with the range
+    return report(name, out, ref, atol=atol, rtol=rtol)
 
 
-def norm_gemm_case(M, N, K, mode, epi=ops.EPI_NONE, residual=False, tile_n=0):
+def norm_gemm_case(M, N, K, mode, epi=ops.EPI_NONE, residual=False, tile_n=0, producer_tile=0):
     """GEMM with a folded RMSNorm (mode 1) / LayerNorm (mode 2) against norm -> fp16 -> linear in fp32 torch, with the
     row statistics produced by a preceding GEMM's rs_out epilogue (so both halves of the fusion are exercised)"""
     eps = 1e-6
@@ -75,13 +87,14 @@ def norm_gemm_case(M, N, K, mode, epi=ops.EPI_NONE, residual=False, tile_n=0):
     r0 = torch.randn(M, K, device=dev, dtype=torch.float16) * 0.5 + 0.3
     stats = ops.row_stats_buffer(1, M, K, mode, dev)[0]
     stats.zero_()                            # as in the product: live slots are rewritten, the others stay zero
-    x = ops.gemm(a0, w0, residual=r0, rs_out=stats, rs_out_mode=mode)
+    x = ops.gemm(a0, w0, residual=r0, rs_out=stats, rs_out_mode=mode, tile_n=producer_tile)
     xf = x.float()
     ref_stats = torch.stack((xf.sum(1), (xf * xf).sum(1)), 1) if mode == 2 else (xf * xf).sum(1, keepdim=True)
     got_stats = stats.view(M, -1, mode).sum(1)
-    ok1 = report(f"gemm rs_out mode={mode} M={M} K={K}", got_stats, ref_stats, atol=2e-2, rtol=2e-3)
+    # statistics are fp32 sums of the fp32 pre-rounding values; the reference sums the fp16-rounded outputs: rel 2^-11 / sqrt(K)
+    ok1 = report(f"gemm rs_out mode={mode} M={M} K={K}", got_stats, ref_stats, atol=2e-2, rtol=1e-3)
     stats2 = stats.clone()
-    ops.gemm(a0, w0, residual=r0, rs_out=stats2, rs_out_mode=mode)
+    ops.gemm(a0, w0, residual=r0, rs_out=stats2, rs_out_mode=mode, tile_n=producer_tile)
     report(f"gemm rs_out deterministic mode={mode} M={M}", stats2, stats, 0, 0)
     gamma = torch.randn(K, device=dev) * 0.2 + 1.0
     beta = torch.randn(K, device=dev) * 0.1
@@ -93,24 +106,39 @@ def norm_gemm_case(M, N, K, mode, epi=ops.EPI_NONE, residual=False, tile_n=0):
         hn = (xf * torch.rsqrt((xf * xf).mean(-1, keepdim=True) + eps)).half().float() * gamma.half().float()
         ref = hn.half().float() @ w.float().t()
         w2 = (w.float() * gamma.half().float()[None, :]).half().contiguous()
+        exact = torch.rsqrt((xf * xf).mean(-1, keepdim=True) + eps) * (xf @ w2.float().t())
         kw = dict(norm=ops.NORM_RMS, rs_in=stats, norm_eps=eps)
     else:
         hn = torch.nn.functional.layer_norm(xf, (K,), gamma, beta, eps)
         ref = hn.half().float() @ w.float().t() + b.float()
         w2 = (w.float() * gamma[None, :]).half().contiguous()
         sb = torch.stack((w2.float().sum(1), b.float() + w.float() @ beta), 1).contiguous()
+        mu = xf.mean(-1, keepdim=True)
+        rstd = torch.rsqrt(xf.var(-1, unbiased=False, keepdim=True) + eps)
+        exact = rstd * (xf @ w2.float().t() - mu * sb[:, 0][None, :]) + sb[:, 1][None, :]
         kw = dict(norm=ops.NORM_LN, rs_in=stats, col_sb=sb, norm_eps=eps)
-    if epi == ops.EPI_GELU:
-        ref = torch.nn.functional.gelu(ref)
-    elif epi == ops.EPI_SWIGLU:
-        ref = torch.nn.functional.silu(ref[:, 0::2]) * ref[:, 1::2]
-    if residual:
-        ref = ref + r.float()
+
+    def act(t):
+        if epi == ops.EPI_GELU:
+            t = torch.nn.functional.gelu(t)
+        elif epi == ops.EPI_SWIGLU:
+            t = torch.nn.functional.silu(t[:, 0::2]) * t[:, 1::2]
+        return t + r.float() if residual else t
+    ref, exact = act(ref), act(exact)
     out = ops.gemm(x, w2, residual=r, epilogue=epi, tile_n=tile_n, **kw)
     torch.cuda.synchronize()
-    # SwiGLU multiplies two O(10) numbers: the element-wise bound scales with the output range
-    ok2 = report(f"gemm folded norm mode={mode} M={M} N={N} K={K} epi={epi} res={int(residual)} tn={tile_n}", out, ref,
-                 atol=3e-2 if epi != ops.EPI_SWIGLU else 1e-3 * ref.abs().max().item(), rtol=2e-2)
+    rmax = ref.abs().max().item()
+    tag = f"mode={mode} M={M} N={N} K={K} epi={epi} res={int(residual)} tn={tile_n}"
+    # (a) against the SAME arithmetic in fp32 (normalise in fp32, packed weights): the kernel is one fp16 rounding away ->
+    #     north_star's rtol 1e-3, absolute floor for the summation-order / cancellation noise (LayerNorm subtracts mu * s_n)
+    floor = max(2e-4, 4e-5 * rmax) * (4.0 if mode == 2 else 1.0)
+    ok2 = report("gemm folded norm vs exact fp32 " + tag, out, exact, atol=floor, rtol=1e-3)
+    # (b) against the reference's ROUNDING SEQUENCE (normalise -> fp16 -> GEMM): K independently rounded terms differ, the
+    #     result by ~ sqrt(K) * 2^-11 * |term| (1.6e-3 rms at K = 4096, 5 sigma over 7 M elements = 8e-3, measured 8.5e-3):
+    #     north_star's one-rounding tolerance cannot hold against this reference; asserted: rtol 2e-3 + atol 1.2e-2 (|ref| <= 17)
+    ok3 = report("gemm folded norm vs reference rounding sequence " + tag, out, ref,
+                 atol=1.2e-2 if epi != ops.EPI_SWIGLU else 8e-4 * rmax, rtol=2e-3)
+    ok2 = ok2 and ok3
     return ok1 and ok2
 
 
@@ -150,7 +178,9 @@ def attn_case(B, H, Sq, Skv, D, causal=False, mask=False, prescale=False, packed
                         q_prescale=scale if prescale else 0.0)
     torch.cuda.synchronize()
     name = f"attn B={B} H={H} Sq={Sq} Skv={Skv} D={D} causal={int(causal)} mask={int(mask)} pre={int(prescale)} packed={int(packed)}"
-    return report(name, out.reshape(-1, D), ref.reshape(-1, D), atol=4e-3, rtol=1e-2)
+    # P is rounded to fp16 before P V (as FlashAttention does) and the output once more: atol 1e-4 is not attainable,
+    # asserted: rtol 1e-3 + atol 1.5e-3 (measured max 1.1e-3 at |ref| 4, 2.8e-4 at |ref| 1)
+    return report(name, out.reshape(-1, D), ref.reshape(-1, D), atol=1.5e-3, rtol=1e-3)
 
 
 def time_gemm(M, N, K, epi=ops.EPI_NONE, variants=(0, 257, 513), rounds=5, iters=10, bias=False, residual=False):
@@ -184,190 +214,257 @@ def time_gemm(M, N, K, epi=ops.EPI_NONE, variants=(0, 257, 513), rounds=5, iters
     print(f"TIME gemm M={M} N={N} K={K} epi={epi}: {txt}  best={best}  plan={ops.gemm_plan(M, N, K, epi)}", flush=True)
 
 
+CASES = []          # (name, callable -> bool), built by build_cases(); tests/test_kernels_gpu.py parametrises over them
+
+
+def _case(name, fn):
+    CASES.append((f"{len(CASES):03d}:{name}", fn))
+
+
+def _g(*a, **kw):
+    _case("gemm " + " ".join(str(x) for x in a) + "".join(f" {k}={v}" for k, v in kw.items()), lambda: gemm_case(*a, **kw))
+
+
+def _n(*a, **kw):
+    _case("norm_gemm " + " ".join(str(x) for x in a) + "".join(f" {k}={v}" for k, v in kw.items()),
+          lambda: norm_gemm_case(*a, **kw))
+
+
+def _a(tc, *a, **kw):
+    def run():
+        from stllm_b200 import _lib as _L
+        _L.load().stllm_set_attention_tc(tc)
+        try:
+            return attn_case(*a, **kw)
+        finally:
+            _L.load().stllm_set_attention_tc(1)
+    _case(f"attn tc={tc} " + " ".join(str(x) for x in a) + "".join(f" {k}={v}" for k, v in kw.items()), run)
+
+
+def build_cases():
+    if CASES:
+        return CASES
+    # --- GEMM: start tiny so a descriptor bug shows on the simplest case ---
+    _g(128, 128, 64, tile_n=128)
+    _g(128, 256, 64, tile_n=256)
+    _g(128, 128, 128, tile_n=128)
+    _g(128, 128, 512, tile_n=128)
+    _g(256, 512, 256, tile_n=128)
+    _g(256, 512, 256, tile_n=256)
+    _g(100, 200, 72, tile_n=128)           # ragged M, N, K
+    _g(100, 200, 72, tile_n=256)
+    _g(4112, 4224, 1408, bias=True)         # ViT qkv
+    _g(4112, 1408, 1408, bias=True, residual=True)
+    _g(4112, 6144, 1408, epi=ops.EPI_GELU, bias=True)
+    _g(4112, 1408, 6144, bias=True, residual=True)
+    _g(4096, 1408, 640, bias=True)          # patch embed (K padded 588 -> 640)
+    _g(576, 12288, 4096)                    # llama qkv
+    _g(576, 22016, 4096, epi=ops.EPI_SWIGLU)
+    _g(576, 4096, 11008, residual=True)
+    _g(576, 32000, 4096)
+    _g(64, 32001, 4096, out_f32=True)       # odd N -> scalar tail path
+    _g(512, 4096, 768, bias=True)           # llama_proj
+    _g(32, 1024, 4096, epi=ops.EPI_RELU, bias=True)
+    _g(1, 4096, 4096)                       # decode-like M=1
+    _g(300, 768, 768, bias=True, lda_pad=8) # strided A (ld != K)
+    # --- 128 x 64 tiles (small-M GEMMs of the Q-Former) ---
+    _g(512, 768, 3072, bias=True, residual=True, tile_n=64)
+    _g(512, 2304, 768, bias=True, tile_n=64)
+    _g(512, 3072, 768, epi=ops.EPI_GELU, bias=True, tile_n=64)
+    _g(100, 200, 72, tile_n=64)
+    _g(32, 1024, 4096, epi=ops.EPI_RELU, bias=True, tile_n=64)
+    _g(64, 1000, 512, epi=ops.EPI_SWIGLU, tile_n=64)
+    # --- hybrid stream-K schedule (STLLM_GEMM_SK=2: on for 256/512) vs pure data-parallel (257/513) ---
+    for tn in (256, 512, 128, 1024 + 192):
+        for sk in (2, None):
+            _g(4112, 1408, 6144, bias=True, residual=True, tile_n=tn, sk=sk)
+            _g(4112, 1408, 1408, bias=True, residual=True, tile_n=tn, sk=sk)
+            _g(576, 4096, 11008, residual=True, tile_n=tn, sk=sk)
+            _g(576, 4096, 4096, residual=True, tile_n=tn, sk=sk)
+            _g(576, 12288, 4096, tile_n=tn, sk=sk)
+            _g(576, 32000, 4096, tile_n=tn, sk=sk)
+            _g(300, 700, 4096, bias=True, tile_n=tn, sk=sk)
+    _g(100, 200, 72 * 64, tile_n=256, sk=2)       # 1 tile, K long: split across many CTAs
+    _g(100, 200, 72 * 64, tile_n=512, sk=2)
+    _g(576, 4096, 11008, residual=True, tile_n=257, sk=2)
+    _g(576, 4096, 11008, residual=True, tile_n=513, sk=2)
+    for _ in range(3):                             # repeated launches: flags must return to zero
+        _g(576, 4096, 11008, residual=True, tile_n=256, sk=2)
+        _g(576, 4096, 11008, residual=True, tile_n=512, sk=2)
+    # --- CTA-pair (cta_group::2) kernel, tile_n=512 ---
+    _g(256, 256, 64, tile_n=512)
+    _g(256, 256, 512, tile_n=512)
+    _g(512, 1024, 256, tile_n=512)
+    _g(100, 200, 72, tile_n=512)
+    _g(4112, 4224, 1408, bias=True, tile_n=512)
+    _g(4112, 6144, 1408, epi=ops.EPI_GELU, bias=True, tile_n=512)
+    _g(4112, 1408, 6144, bias=True, residual=True, tile_n=512)
+    _g(576, 22016, 4096, epi=ops.EPI_SWIGLU, tile_n=512)
+    _g(576, 4096, 11008, residual=True, tile_n=512)
+    _g(64, 32001, 4096, out_f32=True, tile_n=512)
+    # --- CTA-pair engine with a flexible tile width (tile_n = 1024 + bn; half chunks when bn % 32 == 16) ---
+    for bn in (16, 32, 48, 96, 112, 144, 176, 208, 240):
+        _g(300, 700, 256, bias=True, residual=True, tile_n=1024 + bn)
+    _g(4112, 1408, 1408, bias=True, residual=True, tile_n=1024 + 176)
+    _g(4112, 6144, 1408, epi=ops.EPI_GELU, bias=True, tile_n=1024 + 240)
+    _g(4112, 1408, 6144, bias=True, residual=True, tile_n=1024 + 176)
+    _g(4112, 1408, 6144, bias=True, residual=True, tile_n=1024 + 176 + 1)
+    _g(576, 22016, 4096, epi=ops.EPI_SWIGLU, tile_n=1024 + 144)
+    _g(64, 1000, 512, epi=ops.EPI_SWIGLU, tile_n=1024 + 48)
+    _g(100, 200, 72, tile_n=1024 + 80, out_f32=True)
+    # --- CTA-pair engine with swapped operands (tile_n = 2048 + bn: 256 features x bn tokens, transposed epilogue) ---
+    for bn in (16, 32, 48, 64, 96, 144, 192, 256):
+        _g(300, 700, 256, bias=True, residual=True, tile_n=2048 + bn)
+    _g(576, 12288, 4096, tile_n=2048 + 192)
+    _g(576, 4096, 4096, residual=True, tile_n=2048 + 144)
+    _g(576, 22016, 4096, epi=ops.EPI_SWIGLU, tile_n=2048 + 192)
+    _g(576, 4096, 11008, residual=True, tile_n=2048 + 144)
+    _g(576, 32000, 4096, tile_n=2048 + 144)
+    _g(64, 32001, 4096, out_f32=True, tile_n=2048 + 64)     # odd N, fp32 out
+    _g(5, 32001, 4096, tile_n=2048 + 16)                    # decode-like, odd N and odd ldc -> scalar stores
+    _g(1, 4096, 4096, tile_n=2048 + 16)
+    _g(512, 3072, 768, epi=ops.EPI_GELU, bias=True, tile_n=2048 + 64)
+    _g(32, 1024, 4096, epi=ops.EPI_RELU, bias=True, tile_n=2048 + 32)
+    _g(64, 1000, 512, epi=ops.EPI_SWIGLU, residual=True, tile_n=2048 + 32)
+    _g(300, 768, 768, bias=True, lda_pad=8, tile_n=2048 + 48)
+    for _ in range(3):                                             # back-to-back launches (PDL + weight prefetch)
+        _g(576, 4096, 4096, residual=True)
+        _g(4112, 1408, 1408, bias=True, residual=True)
+    # --- LayerNorm / RMSNorm folded into the GEMM + row statistics from the producing GEMM (any producer tile width) ---
+    _n(576, 12288, 4096, 1)
+    _n(576, 22016, 4096, 1, epi=ops.EPI_SWIGLU)
+    _n(576, 22016, 4096, 1, epi=ops.EPI_SWIGLU, tile_n=257)
+    _n(300, 700, 512, 1, residual=True, tile_n=129)
+    _n(5, 1024, 4096, 1)
+    _n(4112, 4224, 1408, 2)
+    _n(4112, 6144, 1408, 2, epi=ops.EPI_GELU)
+    _n(4112, 6144, 1408, 2, epi=ops.EPI_GELU, tile_n=257)
+    _n(300, 700, 512, 2, residual=True, tile_n=1024 + 176)
+    _n(300, 700, 512, 2, tile_n=65)
+    for ptile in (257, 1024 + 128 + 1, 1024 + 176 + 1, 1024 + 192 + 1, 1024 + 240 + 1):   # producer tile widths
+        _n(576, 1024, 4096, 1, producer_tile=ptile)
+        _n(700, 512, 1408, 2, producer_tile=ptile)
+    # --- attention: tcgen05 kernel (ViT / Llama prefill shapes) and mma.sync kernel on the same cases ---
+    for tc in (1, 0):
+        _a(tc, 2, 16, 257, 257, 88, prescale=True, packed=True)   # ViT
+        _a(tc, 16, 16, 257, 257, 88, prescale=True, packed=True)  # ViT, config-2 size
+        _a(tc, 3, 12, 32, 32, 64)                                  # Q-Former self (no text)
+        _a(tc, 3, 12, 44, 44, 64, mask=True)                       # Q-Former self with text + padding mask
+        _a(tc, 3, 12, 32, 257, 64)                                 # Q-Former cross
+        _a(tc, 1, 32, 576, 576, 128, causal=True, packed=True)     # Llama prefill
+        _a(tc, 2, 32, 320, 320, 128, causal=True, mask=True)       # Llama prefill with right padding
+        _a(tc, 2, 32, 1, 300, 128, causal=True)                    # decode step
+        _a(tc, 1, 4, 130, 130, 128, causal=True)
+        _a(tc, 1, 2, 100, 300, 128, causal=True)                   # Sq != Skv (cached prefix)
+        _a(tc, 2, 3, 257, 257, 88)                                 # non-packed, no prescale
+        _a(tc, 1, 32, 2048, 2048, 128, causal=True, packed=True)   # max_position_embeddings
+        _a(tc, 3, 16, 257, 257, 88, prescale=True, packed=True)    # odd batch
+        _a(tc, 2, 16, 200, 200, 88, prescale=True, packed=True)    # fewer tokens than the ViT (interpolated grids)
+    _case("layernorm 4112x1408 eps1e-6", lambda: misc_case("ln1"))
+    _case("layernorm 333x768 eps1e-12", lambda: misc_case("ln2"))
+    _case("rmsnorm 576x4096", lambda: misc_case("rms"))
+    _case("im2col + vit_assemble", lambda: misc_case("im2col"))
+    _case("rope", lambda: misc_case("rope"))
+    _case("gather_rows / gather_rows2", lambda: misc_case("gather"))
+    _case("mean_frames / residual_merge", lambda: misc_case("merge"))
+    _case("cosine_loss / cross_entropy", lambda: misc_case("loss"))
+    return CASES
+
+
+def misc_case(which):
+    ok = True
+    if which == "ln1":
+        x = torch.randn(4112, 1408, device=dev, dtype=torch.float16) * 3 + 0.5
+        g = torch.randn(1408, device=dev) * 0.2 + 1
+        b = torch.randn(1408, device=dev) * 0.1
+        # one fp16 rounding of an fp32 result: north_star's tolerance
+        ok &= report("layernorm 4112x1408 eps1e-6", ops.layernorm(x, g, b, 1e-6),
+                     torch.nn.functional.layer_norm(x.float(), (1408,), g, b, 1e-6), 1e-4, 1e-3)
+    elif which == "ln2":
+        x = torch.randn(333, 768, device=dev, dtype=torch.float16)
+        g = torch.randn(768, device=dev) * 0.2 + 1
+        b = torch.randn(768, device=dev) * 0.1
+        ok &= report("layernorm 333x768 eps1e-12", ops.layernorm(x, g, b, 1e-12),
+                     torch.nn.functional.layer_norm(x.float(), (768,), g, b, 1e-12), 1e-4, 1e-3)
+    elif which == "rms":
+        x = torch.randn(576, 4096, device=dev, dtype=torch.float16) * 2
+        w = (torch.randn(4096, device=dev) * 0.2 + 1).half()
+        ref = (x.float() * torch.rsqrt(x.float().pow(2).mean(-1, keepdim=True) + 1e-6)).half().float() * w.float()
+        # two fp16 roundings as in the reference (w * fp16(x * rstd)): a 1-ulp difference of the inner rounding (rsqrt
+        # approximation at a rounding boundary) is allowed -> rtol 2e-3 (measured: 2 of 2.4 M elements above 1e-3)
+        ok &= report("rmsnorm 576x4096", ops.rmsnorm(x, w, 1e-6), ref, 1e-4, 2e-3)
+    elif which == "im2col":
+        img = torch.randn(3, 3, 224, 224, device=dev)
+        cols = ops.im2col_patch(img, 14, 640)
+        ref = torch.nn.functional.unfold(img, kernel_size=14, stride=14).transpose(1, 2).reshape(-1, 588)
+        ok &= report("im2col fp32 in", cols[:, :588], ref.half(), 0, 0)
+        ok &= report("im2col pad zero", cols[:, 588:], torch.zeros_like(cols[:, 588:]), 0, 0)
+        cols16 = ops.im2col_patch(img.half(), 14, 640)
+        ok &= report("im2col fp16 in", cols16[:, :588], ref.half(), 0, 0)
+        patches = torch.randn(3 * 256, 1408, device=dev, dtype=torch.float16)
+        cls = torch.randn(1408, device=dev, dtype=torch.float16)
+        pos = torch.randn(257, 1408, device=dev, dtype=torch.float16)
+        xa = ops.vit_assemble(patches, cls, pos, 3, 256)
+        ref = torch.cat([cls.expand(3, 1, 1408), patches.view(3, 256, 1408)], 1) + pos
+        ok &= report("vit_assemble", xa.reshape(-1, 1408), ref.reshape(-1, 1408), 0, 0)
+    elif which == "rope":
+        S, H, D = 70, 32, 128
+        qkv = torch.randn(S, 3 * H * D, device=dev, dtype=torch.float16)
+        cos_t, sin_t = ops.rope_tables(D, 2048)
+        pos_ids = torch.arange(S, device=dev, dtype=torch.int32) + 5
+        qk = qkv[:, :2 * H * D].float().view(S, 2 * H, D)
+        c = torch.cat([cos_t, cos_t], -1)[pos_ids.long()][:, None, :]
+        s_ = torch.cat([sin_t, sin_t], -1)[pos_ids.long()][:, None, :]
+        rot = torch.cat([-qk[..., D // 2:], qk[..., :D // 2]], -1)
+        ref = (qk * c + rot * s_).reshape(S, 2 * H * D)
+        vref = qkv[:, 2 * H * D:].clone()
+        ops.rope_(qkv, pos_ids, cos_t, sin_t, 2 * H, D)
+        ok &= report("rope q,k", qkv[:, :2 * H * D], ref, 1e-4, 1e-3)
+        ok &= report("rope leaves v", qkv[:, 2 * H * D:], vref, 0, 0)
+    elif which == "gather":
+        src = torch.randn(1000, 4096, device=dev, dtype=torch.float16)
+        idx = torch.randint(0, 1000, (777,), device=dev)
+        ok &= report("gather_rows", ops.gather_rows(src, idx), src[idx], 0, 0)
+        src1 = torch.randn(300, 4096, device=dev, dtype=torch.float16)
+        codes = torch.randint(-300, 1000, (999,), device=dev)
+        ref = torch.where((codes >= 0)[:, None], src[codes.clamp(min=0)], src1[(-1 - codes).clamp(min=0)])
+        ok &= report("gather_rows2 (two sources)", ops.gather_rows2(src, src1, codes), ref, 0, 0)
+    elif which == "merge":
+        x = torch.randn(2, 16, 32, 4096, device=dev, dtype=torch.float16)
+        ok &= report("mean_frames", ops.mean_frames(x).reshape(-1, 4096), x.float().mean(1).reshape(-1, 4096), 1e-4, 1e-3)
+        gl = torch.randn(2, 32, 4096, device=dev, dtype=torch.float16)
+        ridx = torch.tensor([2, 6, 10, 14], device=dev)
+        ok &= report("residual_merge", ops.residual_merge(x, gl, ridx).reshape(-1, 4096),
+                     (x[:, ridx] + gl[:, None]).reshape(-1, 4096), 0, 0)
+    elif which == "loss":
+        a = torch.randn(512, 4096, device=dev, dtype=torch.float16)
+        bb = torch.randn(512, 4096, device=dev, dtype=torch.float16)
+        an, bn = a.float() / a.float().norm(dim=-1, keepdim=True), bb.float() / bb.float().norm(dim=-1, keepdim=True)
+        ok &= report("cosine_loss", ops.cosine_loss(a, bb).view(1, 1), (2 - 2 * (an * bn).sum(-1)).mean().view(1, 1), 1e-5, 1e-5)
+        logits = torch.randn(100, 32000, device=dev, dtype=torch.float16) * 3
+        labels = torch.randint(0, 32000, (100,), device=dev)
+        labels[::3] = -100
+        ok &= report("cross_entropy", ops.cross_entropy(logits, labels).view(1, 1),
+                     torch.nn.functional.cross_entropy(logits.float(), labels, ignore_index=-100).view(1, 1), 1e-5, 1e-5)
+    else:
+        raise KeyError(which)
+    return bool(ok)
+
+
 def main():
     print(torch.cuda.get_device_name(0), "SMs:", torch.cuda.get_device_properties(0).multi_processor_count)
     t0 = time.time()
-    # --- GEMM: start tiny so a descriptor bug shows on the simplest case ---
-    gemm_case(128, 128, 64, tile_n=128)
-    gemm_case(128, 256, 64, tile_n=256)
-    gemm_case(128, 128, 128, tile_n=128)
-    gemm_case(128, 128, 512, tile_n=128)
-    gemm_case(256, 512, 256, tile_n=128)
-    gemm_case(256, 512, 256, tile_n=256)
-    gemm_case(100, 200, 72, tile_n=128)           # ragged M, N, K
-    gemm_case(100, 200, 72, tile_n=256)
-    gemm_case(4112, 4224, 1408, bias=True)         # ViT qkv
-    gemm_case(4112, 1408, 1408, bias=True, residual=True)
-    gemm_case(4112, 6144, 1408, epi=ops.EPI_GELU, bias=True)
-    gemm_case(4112, 1408, 6144, bias=True, residual=True)
-    gemm_case(4096, 1408, 640, bias=True)          # patch embed (K padded 588 -> 640)
-    gemm_case(576, 12288, 4096)                    # llama qkv
-    gemm_case(576, 22016, 4096, epi=ops.EPI_SWIGLU)
-    gemm_case(576, 4096, 11008, residual=True)
-    gemm_case(576, 32000, 4096)
-    gemm_case(64, 32001, 4096, out_f32=True)       # odd N -> scalar tail path
-    gemm_case(512, 4096, 768, bias=True)           # llama_proj
-    gemm_case(32, 1024, 4096, epi=ops.EPI_RELU, bias=True)
-    gemm_case(1, 4096, 4096)                       # decode-like M=1
-    gemm_case(300, 768, 768, bias=True, lda_pad=8) # strided A (ld != K)
-    # --- 128 x 64 tiles (small-M GEMMs of the Q-Former) ---
-    gemm_case(512, 768, 3072, bias=True, residual=True, tile_n=64)
-    gemm_case(512, 2304, 768, bias=True, tile_n=64)
-    gemm_case(512, 3072, 768, epi=ops.EPI_GELU, bias=True, tile_n=64)
-    gemm_case(100, 200, 72, tile_n=64)
-    gemm_case(32, 1024, 4096, epi=ops.EPI_RELU, bias=True, tile_n=64)
-    gemm_case(64, 1000, 512, epi=ops.EPI_SWIGLU, tile_n=64)
-    # --- hybrid stream-K schedule (default for 256/512) vs pure data-parallel (257/513) ---
-    for tn in (256, 512, 128):
-        gemm_case(4112, 1408, 6144, bias=True, residual=True, tile_n=tn)
-        gemm_case(4112, 1408, 1408, bias=True, residual=True, tile_n=tn)
-        gemm_case(576, 4096, 11008, residual=True, tile_n=tn)
-        gemm_case(576, 4096, 4096, residual=True, tile_n=tn)
-        gemm_case(576, 12288, 4096, tile_n=tn)
-        gemm_case(576, 32000, 4096, tile_n=tn)
-        gemm_case(300, 700, 4096, bias=True, tile_n=tn)
-    gemm_case(100, 200, 72 * 64, tile_n=256)       # 1 tile, K long: split across many CTAs
-    gemm_case(100, 200, 72 * 64, tile_n=512)
-    gemm_case(576, 4096, 11008, residual=True, tile_n=257)
-    gemm_case(576, 4096, 11008, residual=True, tile_n=513)
-    for _ in range(3):                             # repeated launches: flags must return to zero
-        gemm_case(576, 4096, 11008, residual=True, tile_n=256)
-        gemm_case(576, 4096, 11008, residual=True, tile_n=512)
-    # --- CTA-pair (cta_group::2) kernel, tile_n=512 ---
-    gemm_case(256, 256, 64, tile_n=512)
-    gemm_case(256, 256, 512, tile_n=512)
-    gemm_case(512, 1024, 256, tile_n=512)
-    gemm_case(100, 200, 72, tile_n=512)
-    gemm_case(4112, 4224, 1408, bias=True, tile_n=512)
-    gemm_case(4112, 6144, 1408, epi=ops.EPI_GELU, bias=True, tile_n=512)
-    gemm_case(4112, 1408, 6144, bias=True, residual=True, tile_n=512)
-    gemm_case(576, 22016, 4096, epi=ops.EPI_SWIGLU, tile_n=512)
-    gemm_case(576, 4096, 11008, residual=True, tile_n=512)
-    gemm_case(64, 32001, 4096, out_f32=True, tile_n=512)
-    # --- CTA-pair engine with a flexible tile width (tile_n = 1024 + bn; half chunks when bn % 32 == 16) ---
-    for bn in (16, 32, 48, 96, 112, 144, 176, 208, 240):
-        gemm_case(300, 700, 256, bias=True, residual=True, tile_n=1024 + bn)
-    gemm_case(4112, 1408, 1408, bias=True, residual=True, tile_n=1024 + 176)
-    gemm_case(4112, 6144, 1408, epi=ops.EPI_GELU, bias=True, tile_n=1024 + 240)
-    gemm_case(4112, 1408, 6144, bias=True, residual=True, tile_n=1024 + 176)
-    gemm_case(4112, 1408, 6144, bias=True, residual=True, tile_n=1024 + 176 + 1)
-    gemm_case(576, 22016, 4096, epi=ops.EPI_SWIGLU, tile_n=1024 + 144)
-    gemm_case(64, 1000, 512, epi=ops.EPI_SWIGLU, tile_n=1024 + 48)
-    gemm_case(100, 200, 72, tile_n=1024 + 80, out_f32=True)
-    # --- CTA-pair engine with swapped operands (tile_n = 2048 + bn: 256 features x bn tokens, transposed epilogue) ---
-    for bn in (16, 32, 48, 64, 96, 144, 192, 256):
-        gemm_case(300, 700, 256, bias=True, residual=True, tile_n=2048 + bn)
-    gemm_case(576, 12288, 4096, tile_n=2048 + 192)
-    gemm_case(576, 4096, 4096, residual=True, tile_n=2048 + 144)
-    gemm_case(576, 22016, 4096, epi=ops.EPI_SWIGLU, tile_n=2048 + 192)
-    gemm_case(576, 4096, 11008, residual=True, tile_n=2048 + 144)
-    gemm_case(576, 32000, 4096, tile_n=2048 + 144)
-    gemm_case(64, 32001, 4096, out_f32=True, tile_n=2048 + 64)     # odd N, fp32 out
-    gemm_case(5, 32001, 4096, tile_n=2048 + 16)                    # decode-like, odd N and odd ldc -> scalar stores
-    gemm_case(1, 4096, 4096, tile_n=2048 + 16)
-    gemm_case(512, 3072, 768, epi=ops.EPI_GELU, bias=True, tile_n=2048 + 64)
-    gemm_case(32, 1024, 4096, epi=ops.EPI_RELU, bias=True, tile_n=2048 + 32)
-    gemm_case(64, 1000, 512, epi=ops.EPI_SWIGLU, residual=True, tile_n=2048 + 32)
-    gemm_case(300, 768, 768, bias=True, lda_pad=8, tile_n=2048 + 48)
-    for _ in range(3):                                             # back-to-back launches (PDL + weight prefetch)
-        gemm_case(576, 4096, 4096, residual=True)
-        gemm_case(4112, 1408, 1408, bias=True, residual=True)
-    # --- LayerNorm / RMSNorm folded into the GEMM + row statistics from the producing GEMM ---
-    norm_gemm_case(576, 12288, 4096, 1)
-    norm_gemm_case(576, 22016, 4096, 1, epi=ops.EPI_SWIGLU)
-    norm_gemm_case(576, 22016, 4096, 1, epi=ops.EPI_SWIGLU, tile_n=257)
-    norm_gemm_case(300, 700, 512, 1, residual=True, tile_n=129)
-    norm_gemm_case(5, 1024, 4096, 1)
-    norm_gemm_case(4112, 4224, 1408, 2)
-    norm_gemm_case(4112, 6144, 1408, 2, epi=ops.EPI_GELU)
-    norm_gemm_case(4112, 6144, 1408, 2, epi=ops.EPI_GELU, tile_n=257)
-    norm_gemm_case(300, 700, 512, 2, residual=True, tile_n=1024 + 176)
-    norm_gemm_case(300, 700, 512, 2, tile_n=65)
-    # --- attention: tcgen05 kernel (ViT / Llama prefill shapes) and mma.sync kernel on the same cases ---
-    from stllm_b200 import _lib as _L
-    for tc in (1, 0):
-        _L.load().stllm_set_attention_tc(tc)
-        print(f"-- attention kernels with tcgen05 path {'ON' if tc else 'OFF'}")
-        attn_case(2, 16, 257, 257, 88, prescale=True, packed=True)   # ViT
-        attn_case(16, 16, 257, 257, 88, prescale=True, packed=True)  # ViT, config-2 size
-        attn_case(3, 12, 32, 32, 64)                                  # Q-Former self (no text)
-        attn_case(3, 12, 44, 44, 64, mask=True)                       # Q-Former self with text + padding mask
-        attn_case(3, 12, 32, 257, 64)                                 # Q-Former cross
-        attn_case(1, 32, 576, 576, 128, causal=True, packed=True)     # Llama prefill
-        attn_case(2, 32, 320, 320, 128, causal=True, mask=True)       # Llama prefill with right padding
-        attn_case(2, 32, 1, 300, 128, causal=True)                    # decode step
-        attn_case(1, 4, 130, 130, 128, causal=True)
-        attn_case(1, 2, 100, 300, 128, causal=True)                   # Sq != Skv (cached prefix)
-        attn_case(2, 3, 257, 257, 88)                                 # non-packed, no prescale
-        attn_case(1, 32, 2048, 2048, 128, causal=True, packed=True)   # max_position_embeddings
-    _L.load().stllm_set_attention_tc(1)
-    # --- norms ---
-    x = torch.randn(4112, 1408, device=dev, dtype=torch.float16) * 3 + 0.5
-    g = torch.randn(1408, device=dev) * 0.2 + 1
-    b = torch.randn(1408, device=dev) * 0.1
-    report("layernorm 4112x1408 eps1e-6", ops.layernorm(x, g, b, 1e-6),
-           torch.nn.functional.layer_norm(x.float(), (1408,), g, b, 1e-6), 2e-3, 2e-3)
-    x = torch.randn(333, 768, device=dev, dtype=torch.float16)
-    g = torch.randn(768, device=dev) * 0.2 + 1
-    b = torch.randn(768, device=dev) * 0.1
-    report("layernorm 333x768 eps1e-12", ops.layernorm(x, g, b, 1e-12),
-           torch.nn.functional.layer_norm(x.float(), (768,), g, b, 1e-12), 2e-3, 2e-3)
-    x = torch.randn(576, 4096, device=dev, dtype=torch.float16) * 2
-    w = (torch.randn(4096, device=dev) * 0.2 + 1).half()
-    ref = (x.float() * torch.rsqrt(x.float().pow(2).mean(-1, keepdim=True) + 1e-6)).half().float() * w.float()
-    report("rmsnorm 576x4096", ops.rmsnorm(x, w, 1e-6), ref, 2e-3, 2e-3)
-    # --- im2col + assemble ---
-    img = torch.randn(3, 3, 224, 224, device=dev)
-    cols = ops.im2col_patch(img, 14, 640)
-    ref = torch.nn.functional.unfold(img, kernel_size=14, stride=14).transpose(1, 2).reshape(-1, 588)
-    report("im2col fp32 in", cols[:, :588], ref.half(), 0, 0)
-    report("im2col pad zero", cols[:, 588:], torch.zeros_like(cols[:, 588:]), 0, 0)
-    cols16 = ops.im2col_patch(img.half(), 14, 640)
-    report("im2col fp16 in", cols16[:, :588], ref.half(), 0, 0)
-    patches = torch.randn(3 * 256, 1408, device=dev, dtype=torch.float16)
-    cls = torch.randn(1408, device=dev, dtype=torch.float16)
-    pos = torch.randn(257, 1408, device=dev, dtype=torch.float16)
-    xa = ops.vit_assemble(patches, cls, pos, 3, 256)
-    ref = torch.cat([cls.expand(3, 1, 1408), patches.view(3, 256, 1408)], 1) + pos
-    report("vit_assemble", xa.reshape(-1, 1408), ref.reshape(-1, 1408), 0, 0)
-    # --- rope ---
-    S, H, D = 70, 32, 128
-    qkv = torch.randn(S, 3 * H * D, device=dev, dtype=torch.float16)
-    cos_t, sin_t = ops.rope_tables(D, 2048)
-    pos_ids = torch.arange(S, device=dev, dtype=torch.int32) + 5
-    qk = qkv[:, :2 * H * D].float().view(S, 2 * H, D)
-    c = torch.cat([cos_t, cos_t], -1)[pos_ids.long()][:, None, :]
-    s_ = torch.cat([sin_t, sin_t], -1)[pos_ids.long()][:, None, :]
-    rot = torch.cat([-qk[..., D // 2:], qk[..., :D // 2]], -1)
-    ref = (qk * c + rot * s_).reshape(S, 2 * H * D)
-    vref = qkv[:, 2 * H * D:].clone()
-    ops.rope_(qkv, pos_ids, cos_t, sin_t, 2 * H, D)
-    report("rope q,k", qkv[:, :2 * H * D], ref, 2e-3, 2e-3)
-    report("rope leaves v", qkv[:, 2 * H * D:], vref, 0, 0)
-    # --- gather / mean / merge / losses ---
-    src = torch.randn(1000, 4096, device=dev, dtype=torch.float16)
-    idx = torch.randint(0, 1000, (777,), device=dev)
-    report("gather_rows", ops.gather_rows(src, idx), src[idx], 0, 0)
-    x = torch.randn(2, 16, 32, 4096, device=dev, dtype=torch.float16)
-    report("mean_frames", ops.mean_frames(x).reshape(-1, 4096), x.float().mean(1).reshape(-1, 4096), 1e-3, 1e-3)
-    gl = torch.randn(2, 32, 4096, device=dev, dtype=torch.float16)
-    ridx = torch.tensor([2, 6, 10, 14], device=dev)
-    report("residual_merge", ops.residual_merge(x, gl, ridx).reshape(-1, 4096),
-           (x[:, ridx] + gl[:, None]).reshape(-1, 4096), 0, 0)
-    a = torch.randn(512, 4096, device=dev, dtype=torch.float16)
-    bb = torch.randn(512, 4096, device=dev, dtype=torch.float16)
-    an, bn = a.float() / a.float().norm(dim=-1, keepdim=True), bb.float() / bb.float().norm(dim=-1, keepdim=True)
-    report("cosine_loss", ops.cosine_loss(a, bb).view(1, 1), (2 - 2 * (an * bn).sum(-1)).mean().view(1, 1), 1e-4, 1e-4)
-    logits = torch.randn(100, 32000, device=dev, dtype=torch.float16) * 3
-    labels = torch.randint(0, 32000, (100,), device=dev)
-    labels[::3] = -100
-    report("cross_entropy", ops.cross_entropy(logits, labels).view(1, 1),
-           torch.nn.functional.cross_entropy(logits.float(), labels, ignore_index=-100).view(1, 1), 1e-3, 1e-3)
+    only = [a.split("=", 1)[1] for a in sys.argv if a.startswith("--only=")]
+    for name, fn in build_cases():
+        if only and not any(o in name for o in only):
+            continue
+        fn()
     print(f"checks done in {time.time()-t0:.1f}s; failures: {len(fails)}")
     for f in fails:
         print("  FAILED:", f)
     # --- timings ---
     if "--no-time" not in sys.argv:
+        from stllm_b200 import _lib as _L
         for (B_, H_, S_, D_, causal_, pre_) in ((16, 16, 257, 88, False, True), (1, 32, 576, 128, True, False),
                                                 (8, 32, 576, 128, True, False)):
             qkv = torch.randn(B_, S_, 3, H_, D_, device=dev, dtype=torch.float16)

@@ -39,6 +39,11 @@ struct AttnTcParams {
   float q_prescale;  // if != 0: q <- fp16(q * q_prescale) before QK^T (eva_vit.py:128)
   float mask_value;
   int causal;
+  // wide-tile kernel (attention_tc_wide_kernel) only: raw q/k/v for the rows / keys that do not fill a tensor-core tile
+  const __half* q; const __half* k; const __half* v;
+  long long q_sb, q_ss, k_sb, k_ss, v_sb, v_ss;   // batch / token strides in elements (heads contiguous: h * DH)
+  int n_left;       // trailing keys (Skv % 128, <= LEFT_MAX) scored on CUDA cores by the softmax threads
+  int n_tail;       // trailing query rows (Sq % 128, <= TAIL_MAX) handled by their own CUDA-core CTAs (blockIdx.y = Sq / 128)
 };
 
 DEVI void tma_load_3d(const CUtensorMap* desc, uint64_t* bar, void* smem_dst, int32_t c0, int32_t c1, int32_t c2) {
@@ -402,6 +407,446 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
 }
 
+// ================================================================================================
+// Wide-tile variant for the ViT shape (non-causal, no key mask, sequence 257 = 2 x 128 + 1; eva_vit.py:128-145).
+//
+// Round 1's kernel walks the 257 keys in five 64-key tiles (the fifth holds ONE key) and gives the 257th query row a
+// whole 128-row tile: 768 CTAs, each a chain of five serial TMA -> MMA -> softmax -> MMA round trips.  It ran at 41 us per
+// layer with the tensor pipe ~10 % busy: latency-bound.  Here
+//   * K/V tiles are 128 keys: two round trips per CTA; one K/V stage and one S buffer per CTA (96 KB smem, 224 TMEM
+//     columns) so that two CTAs still share an SM and fill each other's waits;
+//   * the keys left over after the last full tile (257 = 2 x 128 + 1) never become a tile: the softmax threads score them on
+//     CUDA cores (one 88-long dot product per row and key) and carry their weights next to the TMEM accumulator;
+//   * the query rows left over after the last full 128-row tile (one row per head and frame) go to their own small CTAs
+//     (blockIdx.y == Sq / 128) that never touch the tensor core: q.K^T, softmax and P.V for <= TAIL_MAX rows.
+// Softmax reads S from TMEM twice (row maximum, then exponentials) instead of holding 128 scores per thread in registers.
+// ================================================================================================
+constexpr int WKV = 128;                 // keys per tile
+constexpr int WKBLK = WKV * 128;         // one [128 keys x 64 fp16] swizzled block = 16 KB
+constexpr int LEFT_MAX = 4;
+constexpr int TAIL_MAX = 4;
+constexpr int WIDE_SMEM = 2 * BLK_BYTES + 2 * WKBLK + 2 * WKBLK + 4096 + 1024;   // Q | K (= P) | V | barriers + leftovers
+
+template <int DH>
+__device__ __forceinline__ void attention_tail_rows(const AttnTcParams& p, uint8_t* smem, int h, int b) {
+  // CUDA-core path for the <= TAIL_MAX query rows after the last full tile: 128 threads, thread t scores keys t, t + 128, ...
+  float* sq = reinterpret_cast<float*>(smem);            // [DH] the (pre-scaled, fp16-rounded) query row
+  float* sp = sq + 128;                                  // [Skv] probabilities (unnormalised)
+  float* red = sp + ((p.Skv + 31) & ~31);                // [8] reduction scratch
+  const int t = threadIdx.x;
+  const float sl2 = p.scale * 1.4426950408889634f;
+  const int row0 = (p.Sq / TQ) * TQ;
+  for (int r = 0; r < p.n_tail; ++r) {
+    const int qrow = row0 + r;
+    const __half* qp = p.q + (long long)b * p.q_sb + (long long)qrow * p.q_ss + (long long)h * DH;
+    if (t < DH) {
+      float x = __half2float(qp[t]);
+      if (p.q_prescale != 0.f) x = __half2float(__float2half_rn(x * p.q_prescale));
+      sq[t] = x;
+    }
+    __syncthreads();
+    float mx = -INFINITY;
+    if (t < 128) {
+      for (int key = t; key < p.Skv; key += 128) {
+        const uint4* kp = reinterpret_cast<const uint4*>(p.k + (long long)b * p.k_sb + (long long)key * p.k_ss + (long long)h * DH);
+        float acc = 0.f;
+#pragma unroll
+        for (int c = 0; c < DH / 8; ++c) {
+          const uint4 u = __ldg(kp + c);
+          const __half2* hh = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(hh[i]);
+            acc = fmaf(sq[c * 8 + 2 * i], f.x, acc);
+            acc = fmaf(sq[c * 8 + 2 * i + 1], f.y, acc);
+          }
+        }
+        acc *= sl2;
+        sp[key] = acc;
+        mx = fmaxf(mx, acc);
+      }
+    }
+    mx = warp_max(mx);
+    if ((t & 31) == 0 && t < 128) red[t >> 5] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    float sum = 0.f;
+    if (t < 128) {
+      for (int key = t; key < p.Skv; key += 128) {
+        const float e = exp2f(sp[key] - mx);
+        sp[key] = e;
+        sum += e;
+      }
+    }
+    sum = warp_sum(sum);
+    if ((t & 31) == 0 && t < 128) red[4 + (t >> 5)] = sum;
+    __syncthreads();
+    const float inv = 1.f / (red[4] + red[5] + red[6] + red[7]);
+    // P V: thread (key group kg, 8-feature chunk c) sums its keys kg, kg + 16, ... (independent 16-byte loads, ~16 per
+    // thread), the 16 partial sums of a chunk are then added through shared memory
+    constexpr int NCHUNK = DH / 8;                       // 11 (head dim 88) or 16
+    constexpr int KG = 16;
+    float* part = red + 8;                               // [KG][DH] partial outputs
+    if (t < KG * NCHUNK && NCHUNK * KG <= TC_THREADS) {
+      const int kg = t / NCHUNK, c = t % NCHUNK;
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+      const __half* vp = p.v + (long long)b * p.v_sb + (long long)h * DH + c * 8;
+#pragma unroll 4
+      for (int key = kg; key < p.Skv; key += KG) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(vp + (long long)key * p.v_ss));
+        const __half2* hh = reinterpret_cast<const __half2*>(&u);
+        const float w = sp[key];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __half22float2(hh[i]);
+          acc[2 * i] = fmaf(w, f.x, acc[2 * i]);
+          acc[2 * i + 1] = fmaf(w, f.y, acc[2 * i + 1]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) part[kg * DH + c * 8 + i] = acc[i];
+    }
+    __syncthreads();
+    if (t < DH) {
+      float a = 0.f;
+#pragma unroll
+      for (int kg = 0; kg < KG; ++kg) a += part[kg * DH + t];
+      p.o[(long long)b * p.o_sb + (long long)qrow * p.o_ss + (long long)h * p.o_sh + t] = __float2half_rn(a * inv);
+    }
+    __syncthreads();
+  }
+}
+
+// The <= TAIL_MAX query rows after the last full 128-row tile as their own launch (grid = heads x 1 x batch): with it the
+// tensor-core kernel runs on Sq - tail rows -- for the ViT (257 = 2 x 128 + 1) two query tiles per (frame, head) instead of
+// three, the third of which held ONE row and cost a quarter of the kernel (39.0 -> 29.0 us, profiles/r02_attention.md).
+template <int DH>
+__global__ void __launch_bounds__(TC_THREADS) attention_tail_kernel(const AttnTcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
+  pdl_launch_dependents();
+  pdl_wait();
+  attention_tail_rows<DH>(p, smem, (int)blockIdx.x, (int)blockIdx.z);
+}
+
+template <int DH>
+__global__ void __launch_bounds__(TC_THREADS, 2)
+attention_tc_wide_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                         const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
+  constexpr int DK = (DH == 88) ? 96 : 128;
+  constexpr int DV = (DH == 88) ? 96 : 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.x, b = blockIdx.z;
+  const int n_full_qt = p.Sq / TQ + ((p.Sq % TQ) > p.n_tail ? 1 : 0);   // tiles handled on the tensor core
+  if ((int)blockIdx.y >= n_full_qt) {
+    pdl_launch_dependents();
+    pdl_wait();
+    attention_tail_rows<DH>(p, smem, h, b);
+    return;
+  }
+  uint8_t* sQ = smem;                       // 2 blocks of 16 KB
+  uint8_t* sK = sQ + 2 * BLK_BYTES;         // 2 blocks of 16 KB (128 keys); doubles as P once S = Q K^T has completed
+  uint8_t* sV = sK + 2 * WKBLK;             // 2 blocks of 16 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + 2 * WKBLK);
+  uint64_t* q_full = bars + 0;
+  uint64_t* q_ready = bars + 1;
+  uint64_t* kv_full = bars + 2;
+  uint64_t* kv_empty = bars + 3;
+  uint64_t* s_full = bars + 4;
+  uint64_t* p_full = bars + 5;
+  uint64_t* pv_done = bars + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  __half* s_left_k = reinterpret_cast<__half*>(bars + 16);             // [LEFT_MAX][96] leftover keys
+  __half* s_left_v = s_left_k + LEFT_MAX * 96;                         // [LEFT_MAX][96] leftover values
+
+  const int q0 = (int)blockIdx.y * TQ;
+  const int kv_mma = p.Skv - p.n_left;                                 // keys that go through the tensor core
+  const int n_tiles = (kv_mma + WKV - 1) / WKV;
+  const int col0 = h * DH;
+
+  if (warp == 4 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    mbar_init(q_ready, 128);
+    mbar_init(kv_full, 1);
+    mbar_init(kv_empty, 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(pv_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 5) tmem_alloc(tmem_slot, 256);
+  pdl_launch_dependents();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  pdl_wait();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + WKV;         // S: columns 0..127, O: 128..223
+
+  if (warp == 4) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      mbar_arrive_expect_tx(q_full, 2 * BLK_BYTES);
+      tma_load_3d(&tmQ, q_full, sQ, col0, q0, b);
+      tma_load_3d(&tmQ, q_full, sQ + BLK_BYTES, col0 + 64, q0, b);
+    }
+    __syncwarp();
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(kv_empty, (uint32_t)((j & 1) ^ 1));
+      if (elect_one()) {
+        mbar_arrive_expect_tx(kv_full, 4 * WKBLK);
+        tma_load_3d(&tmK, kv_full, sK, col0, j * WKV, b);
+        tma_load_3d(&tmK, kv_full, sK + WKBLK, col0 + 64, j * WKV, b);
+        tma_load_3d(&tmV, kv_full, sV, col0, j * WKV, b);
+        tma_load_3d(&tmV, kv_full, sV + WKBLK, col0 + 64, j * WKV, b);
+      }
+      __syncwarp();
+    }
+  } else if (warp == 5) {
+    // ===================== MMA issuer =====================
+    constexpr uint32_t idesc_pv = make_idesc_f16_bmn(TQ, DV);
+    mbar_wait(q_ready, 0);
+    tc_fence_after();
+    const uint32_t aq = smem_u32(sQ), bk = smem_u32(sK), bv = smem_u32(sV);
+    for (int j = 0; j < n_tiles; ++j) {
+      mbar_wait(kv_full, (uint32_t)(j & 1));
+      tc_fence_after();
+      int nk = kv_mma - j * WKV;
+      nk = nk > WKV ? WKV : ((nk + 15) & ~15);
+      const uint32_t idesc_qk = make_idesc_f16(TQ, nk, false);
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < DK / 16; ++ks) {
+          const uint32_t aoff = (uint32_t)((ks >> 2) * BLK_BYTES + (ks & 3) * 32);
+          const uint32_t boff = (uint32_t)((ks >> 2) * WKBLK + (ks & 3) * 32);
+          umma_f16_ss(tmem_S, make_sdesc_k_sw128(aq + aoff), make_sdesc_k_sw128(bk + boff), idesc_qk, ks > 0 ? 1u : 0u);
+        }
+        umma_commit(s_full);
+      }
+      __syncwarp();
+      mbar_wait(p_full, (uint32_t)(j & 1));      // P_j written over the K tile, O rescaled
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll 4
+        for (int ks = 0; ks < nk / 16; ++ks) {
+          const uint32_t aoff = (uint32_t)((ks >> 2) * BLK_BYTES + (ks & 3) * 32);   // P: [128 rows x 64 keys] blocks
+          umma_f16_ss(tmem_O, make_sdesc_k_sw128(bk + aoff), make_sdesc_mn_sw128(bv + ks * 2048, WKBLK), idesc_pv,
+                      (j > 0 || ks > 0) ? 1u : 0u);
+        }
+        umma_commit(kv_empty);                   // the K (= P) and V tiles are free once P V has completed
+        umma_commit(pv_done);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== softmax warps: thread = query row =====================
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const int qrow = q0 + r;
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    // leftover keys / values -> smem (one 16-byte chunk per thread), zero padded to 96 columns
+    {
+      const int chunks = p.n_left * 12;
+      for (int i = r; i < 2 * chunks; i += 128) {
+        const int which = i >= chunks, ii = which ? i - chunks : i;
+        const int li = ii / 12, c = ii % 12;
+        const int key = kv_mma + li;
+        uint4 u = make_uint4(0, 0, 0, 0);
+        if (c * 8 < DH) {
+          const __half* src = which ? p.v + (long long)b * p.v_sb + (long long)key * p.v_ss + (long long)h * DH
+                                    : p.k + (long long)b * p.k_sb + (long long)key * p.k_ss + (long long)h * DH;
+          u = __ldg(reinterpret_cast<const uint4*>(src) + c);
+        }
+        *reinterpret_cast<uint4*>((which ? s_left_v : s_left_k) + li * 96 + c * 8) = u;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    // ---- Q fix-up: optional fp16 pre-scale (ViT) and zeroing of the padded contraction columns; leftover scores ----
+    mbar_wait(q_full, 0);
+    float s_left[LEFT_MAX];
+#pragma unroll
+    for (int i = 0; i < LEFT_MAX; ++i) s_left[i] = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < 16; ++c) {               // 16 chunks of 8 columns = 128 contraction columns
+      uint4* ptr = reinterpret_cast<uint4*>(sQ + (c >> 3) * BLK_BYTES + sw_off(r, c & 7));
+      if (c * 8 >= DH) {
+        if (c * 8 < DK) *ptr = make_uint4(0, 0, 0, 0);
+      } else {
+        uint4 u = *ptr;
+        __half2* hh = reinterpret_cast<__half2*>(&u);
+        if (p.q_prescale != 0.f) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(hh[i]);
+            hh[i] = __floats2half2_rn(f.x * p.q_prescale, f.y * p.q_prescale);
+          }
+          *ptr = u;
+        }
+#pragma unroll
+        for (int li = 0; li < LEFT_MAX; ++li) {
+          if (li < p.n_left) {
+            const uint4 kk = *reinterpret_cast<const uint4*>(s_left_k + li * 96 + c * 8);   // broadcast read
+            const __half2* kh = reinterpret_cast<const __half2*>(&kk);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 a = __half22float2(hh[i]), bb = __half22float2(kh[i]);
+              s_left[li] = fmaf(a.x, bb.x, fmaf(a.y, bb.y, s_left[li]));
+            }
+          }
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    mbar_arrive(q_ready);
+
+    const float LOG2E = 1.4426950408889634f;
+    const float sl2 = p.scale * LOG2E;
+    const bool warp_valid = (q0 + quad * 32) < p.Sq;
+    // the leftover keys open the online softmax: m = max of their scores, weights w_i = exp2(s_i - m)
+    float m_run = -INFINITY, l_run = 0.f;
+    float w_left[LEFT_MAX];
+#pragma unroll
+    for (int i = 0; i < LEFT_MAX; ++i) {
+      s_left[i] *= sl2;
+      if (i < p.n_left) m_run = fmaxf(m_run, s_left[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < LEFT_MAX; ++i) {
+      w_left[i] = (i < p.n_left) ? exp2f(s_left[i] - m_run) : 0.f;
+      l_run += w_left[i];
+    }
+    for (int j = 0; j < n_tiles; ++j) {
+      const int kbase = j * WKV;
+      int nk = kv_mma - kbase;
+      nk = nk > WKV ? WKV : nk;
+      const int n_chunks = (nk + 31) >> 5;
+      mbar_wait(s_full, (uint32_t)(j & 1));
+      tc_fence_after();
+      float alpha = 1.f;
+      if (warp_valid) {
+        const uint32_t s_addr = tmem_S + lane_addr;
+        // pass 1: row maximum
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c = 0; c < n_chunks; ++c) {
+          uint32_t s[32];
+          tmem_ld_32x32b_x32(s_addr + c * 32, s);
+          tmem_ld_wait();
+          const int valid = nk - c * 32;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (i < valid) mx = fmaxf(mx, __uint_as_float(s[i]));
+        }
+        mx *= sl2;                                     // sl2 > 0: max commutes with the scale
+        const float m_new = fmaxf(m_run, mx);
+        alpha = exp2f(m_run - m_new);                  // m_run = -inf (no leftover keys, first tile) -> 0
+        // pass 2: P = exp2(S * sl2 - m) -> fp16 -> swizzled smem over the K tile (S_j = Q K_j^T has completed)
+        float sum = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < n_chunks; ++c) {
+          uint32_t s[32];
+          tmem_ld_32x32b_x32(s_addr + c * 32, s);
+          tmem_ld_wait();
+          const int valid = nk - c * 32;
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = (i < valid) ? exp2f(fmaf(__uint_as_float(s[i]), sl2, -m_new)) : 0.f;
+            const float p1 = (i + 1 < valid) ? exp2f(fmaf(__uint_as_float(s[i + 1]), sl2, -m_new)) : 0.f;
+            sum += p0 + p1;
+            pk[i >> 1] = pack_half2(p0, p1);
+          }
+          // the K tile may still be read by Q K^T of THIS tile?  No: s_full fired, i.e. the MMAs that read K have completed.
+          uint8_t* blk = sK + (c >> 1) * BLK_BYTES;      // P block of 64 keys: chunk c -> 16-byte chunks (c & 1) * 4 .. + 3
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            *reinterpret_cast<uint4*>(blk + sw_off(r, (c & 1) * 4 + q)) =
+                make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        }
+        l_run = l_run * alpha + sum;
+        m_run = m_new;
+#pragma unroll
+        for (int i = 0; i < LEFT_MAX; ++i) w_left[i] *= alpha;
+        fence_proxy_async_smem();
+      }
+      // ---- previous P V must be complete before O is rescaled (S and the K tile were released by kv_empty already) ----
+      if (j > 0) {
+        mbar_wait(pv_done, (uint32_t)((j - 1) & 1));
+        tc_fence_after();
+        if (warp_valid && !__all_sync(0xffffffffu, alpha == 1.f)) {
+#pragma unroll 1
+          for (int c = 0; c < DV; c += 32) {
+            uint32_t o[32];
+            tmem_ld_32x32b_x32(tmem_O + lane_addr + c, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st_32x32b_x32(tmem_O + lane_addr + c, o);
+          }
+          tmem_st_wait();
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    // ---- epilogue: (O + sum_i w_i v_left_i) / l -> fp16 -> global ----
+    mbar_wait(pv_done, (uint32_t)((n_tiles - 1) & 1));
+    tc_fence_after();
+    const float inv = l_run > 0.f ? 1.f / l_run : 0.f;
+    __half* orow = p.o + (long long)b * p.o_sb + (long long)qrow * p.o_ss + (long long)h * p.o_sh;
+#pragma unroll 1
+    for (int c = 0; c < DV; c += 32) {
+      uint32_t o[32];
+      tmem_ld_32x32b_x32(tmem_O + lane_addr + c, o);
+      tmem_ld_wait();
+      if (qrow < p.Sq) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int colq = c + q * 8;
+          if (colq < DH) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(o[8 * q + i]);
+#pragma unroll
+            for (int li = 0; li < LEFT_MAX; ++li) {
+              if (li < p.n_left) {
+                const uint4 vv = *reinterpret_cast<const uint4*>(s_left_v + li * 96 + colq);
+                const __half2* vh = reinterpret_cast<const __half2*>(&vv);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 x = __half22float2(vh[i]);
+                  f[2 * i] = fmaf(w_left[li], x.x, f[2 * i]);
+                  f[2 * i + 1] = fmaf(w_left[li], x.y, f[2 * i + 1]);
+                }
+              }
+            }
+            uint4 w;
+            w.x = pack_half2(f[0] * inv, f[1] * inv);
+            w.y = pack_half2(f[2] * inv, f[3] * inv);
+            w.z = pack_half2(f[4] * inv, f[5] * inv);
+            w.w = pack_half2(f[6] * inv, f[7] * inv);
+            *reinterpret_cast<uint4*>(orow + colq) = w;
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                     const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -448,6 +893,21 @@ int launch_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& t
   return STLLM_OK;
 }
 
+template <int DH>
+int launch_tc_wide(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcParams& p,
+                   cudaStream_t stream) {
+  auto kern = attention_tc_wide_kernel<DH>;
+  static bool configured = false;
+  if (!configured) {
+    STLLM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, WIDE_SMEM));
+    configured = true;
+  }
+  const int n_full_qt = p.Sq / TQ + ((p.Sq % TQ) > p.n_tail ? 1 : 0);
+  dim3 grid(p.H, n_full_qt + (p.n_tail > 0 ? 1 : 0), p.B);
+  STLLM_CHECK_CUDA(stllm_launch(kern, grid, dim3(TC_THREADS), WIDE_SMEM, stream, tq, tk, tv, p));
+  return STLLM_OK;
+}
+
 }  // namespace
 
 static int g_attn_tc = -1;   // -1: read STLLM_ATTN_TC on first use (default on)
@@ -474,9 +934,30 @@ int stllm_attention_tc_try(const void* q, const void* k, const void* v, void* ou
       (os[0] % 8))
     return STLLM_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(out) & 15) != 0) return STLLM_ERR_UNSUPPORTED;
+  // wide-tile kernel: the ViT shape (non-causal, no key mask, head dim 88, at least one full 128-key tile)
+  // Measured SLOWER than the 64-key kernel (49 vs 39 us on the ViT shape, profiles/r02_attention.md): kept as an experiment
+  static const int wide_ok = [] { const char* e = getenv("STLLM_ATTN_WIDE"); return (e != nullptr && atoi(e) == 1) ? 1 : 0; }();
+  const bool wide = wide_ok && D == 88 && !causal && key_mask == nullptr && Skv >= WKV && Skv <= 4096 && Sq >= TQ;
   CUtensorMap tq, tk, tv;
   int rc = make_tmap3(&tq, q, H * D, Sq, B, qs[1], qs[0], TQ);
   if (rc != STLLM_OK) return rc;
+  if (wide) {
+    rc = make_tmap3(&tk, k, H * D, Skv, B, ks[1], ks[0], WKV);
+    if (rc != STLLM_OK) return rc;
+    rc = make_tmap3(&tv, v, H * D, Skv, B, vs[1], vs[0], WKV);
+    if (rc != STLLM_OK) return rc;
+    AttnTcParams p;
+    p.o = (__half*)out;
+    p.kmask = nullptr;
+    p.o_sb = os[0]; p.o_ss = os[1]; p.o_sh = os[2];
+    p.B = B; p.H = H; p.Sq = Sq; p.Skv = Skv;
+    p.scale = scale; p.q_prescale = q_prescale; p.mask_value = mask_value; p.causal = 0;
+    p.q = (const __half*)q; p.k = (const __half*)k; p.v = (const __half*)v;
+    p.q_sb = qs[0]; p.q_ss = qs[1]; p.k_sb = ks[0]; p.k_ss = ks[1]; p.v_sb = vs[0]; p.v_ss = vs[1];
+    p.n_left = (Skv % WKV) <= LEFT_MAX ? (Skv % WKV) : 0;
+    p.n_tail = (Sq % TQ) <= TAIL_MAX ? (Sq % TQ) : 0;
+    return launch_tc_wide<88>(tq, tk, tv, p, stream);
+  }
   rc = make_tmap3(&tk, k, H * D, Skv, B, ks[1], ks[0], TKV);
   if (rc != STLLM_OK) return rc;
   rc = make_tmap3(&tv, v, H * D, Skv, B, vs[1], vs[0], TKV);
@@ -487,6 +968,29 @@ int stllm_attention_tc_try(const void* q, const void* k, const void* v, void* ou
   p.o_sb = os[0]; p.o_ss = os[1]; p.o_sh = os[2];
   p.B = B; p.H = H; p.Sq = Sq; p.Skv = Skv;
   p.scale = scale; p.q_prescale = q_prescale; p.mask_value = mask_value; p.causal = causal;
+  p.q = (const __half*)q; p.k = (const __half*)k; p.v = (const __half*)v;
+  p.q_sb = qs[0]; p.q_ss = qs[1]; p.k_sb = ks[0]; p.k_ss = ks[1]; p.v_sb = vs[0]; p.v_ss = vs[1];
+  p.n_left = p.n_tail = 0;
+  // ViT shape: the few query rows after the last full tile go to the CUDA-core tail kernel, the tensor-core kernel runs on
+  // the full tiles only (two launches; the tail launch is 256 small CTAs, ~4 us)
+  static const int tail_ok = [] { const char* e = getenv("STLLM_ATTN_TAIL"); return (e != nullptr && atoi(e) == 0) ? 0 : 1; }();
+  const int tail = Sq % TQ;
+  if (tail_ok && D == 88 && !causal && key_mask == nullptr && Sq > TQ && tail >= 1 && tail <= TAIL_MAX && Skv <= 8192) {
+    AttnTcParams pm = p;
+    pm.Sq = Sq - tail;
+    rc = launch_tc<88>(tq, tk, tv, pm, stream);
+    if (rc != STLLM_OK) return rc;
+    p.n_tail = tail;
+    auto kern = attention_tail_kernel<88>;
+    const int smem = (128 + ((Skv + 31) & ~31) + 8 + 16 * 88) * 4 + 256;
+    static int configured_smem = 0;
+    if (smem > 48 * 1024 && smem > configured_smem) {
+      STLLM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+      configured_smem = smem;
+    }
+    STLLM_CHECK_CUDA(stllm_launch(kern, dim3(H, 1, B), dim3(TC_THREADS), smem, stream, p));
+    return STLLM_OK;
+  }
   if (D == 88) return launch_tc<88>(tq, tk, tv, p, stream);
   return launch_tc<128>(tq, tk, tv, p, stream);
 }

@@ -1091,6 +1091,7 @@ int g_trace_on = 0;
 int g_trace_launch = 0;
 float* g_sk_ws = nullptr;
 int* g_sk_flags = nullptr;
+int g_sk_mode_override = -1;   // stllm_set_gemm_streamk: -1 = follow STLLM_GEMM_SK
 
 // how many leading tiles to schedule stream-K for `tiles` tiles on `workers` CTAs/clusters (0 = none)
 int choose_sk_tiles(int tiles, int workers, int k_blocks) {
@@ -1099,11 +1100,12 @@ int choose_sk_tiles(int tiles, int workers, int k_blocks) {
   // for short-K GEMMs it costs more than it saves -- and end to end (bench.py, 4 alternating runs) even the selective
   // rule loses 1.3 % (726 vs 736 frames/s).  So it is OFF by default: STLLM_GEMM_SK=1 enables the selective rule,
   // =2 enables it for every shape (used by the parity tests to exercise the fix-up path).
-  static int mode = -1;
-  if (mode < 0) {
+  static int env_mode = -1;
+  if (env_mode < 0) {
     const char* e = getenv("STLLM_GEMM_SK");
-    mode = (e != nullptr) ? atoi(e) : 0;
+    env_mode = (e != nullptr) ? atoi(e) : 0;
   }
+  const int mode = g_sk_mode_override >= 0 ? g_sk_mode_override : env_mode;
   if (mode == 0 || g_sk_ws == nullptr) return 0;
   const int rem = tiles % workers;
   if (rem == 0) return 0;
@@ -1269,6 +1271,14 @@ extern "C" int stllm_set_gemm_workspace(void* ptr, long long bytes) {
   STLLM_CHECK_ARG(bytes >= stllm_gemm_workspace_bytes() && ((uintptr_t)ptr & 255) == 0);
   g_sk_flags = reinterpret_cast<int*>(ptr);                               // first 4 KB: flags
   g_sk_ws = reinterpret_cast<float*>(reinterpret_cast<char*>(ptr) + 4096);
+  return STLLM_OK;
+}
+
+// Stream-K treatment of the ragged last wave: -1 = follow the STLLM_GEMM_SK environment variable (default off),
+// 0 = off, 1 = selective rule, 2 = every shape (the parity tests use 2 to exercise the fix-up path).
+extern "C" int stllm_set_gemm_streamk(int mode) {
+  STLLM_CHECK_ARG(mode >= -1 && mode <= 2);
+  g_sk_mode_override = mode;
   return STLLM_OK;
 }
 

@@ -36,7 +36,7 @@ class DecodeEngine:
         max_steps: decode steps that may follow."""
         assert supported(llm, n_rows)
         model = llm.get_model()
-        if model._packed is None:
+        if not model._packed_valid():
             model._pack()
         self.P = model._packed
         cfg = llm.config

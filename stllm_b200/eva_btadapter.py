@@ -19,6 +19,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from .packing import PackedWeightsMixin
 from .eva_vit import Attention, Block, create_eva_vit_g, convert_weights_to_fp16, pack_block, run_block
 
 
@@ -42,7 +43,7 @@ class BTAdapter_Temp(nn.Module):
         nn.init.constant_(self.temporal_fc.bias, 0)
 
 
-class EVAVisionTransformer_BTAdapter(nn.Module):
+class EVAVisionTransformer_BTAdapter(PackedWeightsMixin, nn.Module):
     """eva_btadapter.py:46-250.  `clip` lets tests build the adapter around a shallower ViT-g-width encoder; the
     reference always wraps create_eva_vit_g(224, 0, False, "fp16") (:52-54)."""
 
@@ -97,10 +98,6 @@ class EVAVisionTransformer_BTAdapter(nn.Module):
         self._packed = None
         return super()._apply(fn, *a, **kw)
 
-    def load_state_dict(self, *a, **kw):
-        self._packed = None
-        return super().load_state_dict(*a, **kw)
-
     def _pack(self):
         dev = self.cls_token.device
         D = self.embed_dim
@@ -123,6 +120,7 @@ class EVAVisionTransformer_BTAdapter(nn.Module):
                                b_proj=f16(a.proj.bias), w_fc=f16(blk.temporal_fc.weight),
                                b_fc=f16(blk.temporal_fc.bias)))
         self._packed = P
+        self._mark_packed()
 
     def _spatial_index(self, B, T, P_, dev):
         """row gather branch layout -> frame-major [(b t), 1 + p]: every frame gets the clip's cls row first
@@ -145,7 +143,7 @@ class EVAVisionTransformer_BTAdapter(nn.Module):
         assert H == self.patch_embed.img_size[0] and W == self.patch_embed.img_size[1], \
             f"Input image size ({H}*{W}) doesn't match model ({self.patch_embed.img_size[0]}*{self.patch_embed.img_size[1]})."
         assert T <= self.BTAdapter_position.num_embeddings, "BTAdapter_position holds 64 frame positions"
-        if self._packed is None:
+        if not self._packed_valid():
             self._pack()
         P = self._packed
         if x.dtype not in (torch.float16, torch.float32):

@@ -17,6 +17,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from .packing import PackedWeightsMixin
 
 
 def _trunc_normal_(t, std=0.02):
@@ -129,7 +130,7 @@ def run_block(bw, xt, h, B, n_tok, Hh, d, eps, stats_in=None, stats_mid=None, st
              rs_out_mode=2 if stats_out is not None else 0)
 
 
-class VisionTransformer(nn.Module):
+class VisionTransformer(PackedWeightsMixin, nn.Module):
     """eva_vit.py:244-349.  Options the ST-LLM path never enables (rel-pos bias, layer-scale, drop-path > 0 in
     eval, checkpointing) are rejected loudly rather than silently ignored."""
 
@@ -181,13 +182,6 @@ class VisionTransformer(nn.Module):
         self._packed = None  # .to()/.half()/.cuda() invalidate the packed copies
         return super()._apply(fn, *a, **kw)
 
-    def load_state_dict(self, *a, **kw):
-        self._packed = None
-        return super().load_state_dict(*a, **kw)
-
-    def repack(self):
-        self._packed = None
-
     def _pack(self):
         dev = self.cls_token.device
         f16 = lambda t: t.detach().to(device=dev, dtype=torch.float16).contiguous()
@@ -203,6 +197,7 @@ class VisionTransformer(nn.Module):
         self._packed = dict(w_patch=w_patch, kpad=kpad, kreal=kreal, b_patch=f16(self.patch_embed.proj.bias),
                             cls=f16(self.cls_token).reshape(-1), pos=f16(self.pos_embed).reshape(-1, D), blocks=blocks,
                             fuse=fuse)
+        self._mark_packed()
 
     # ---- forward --------------------------------------------------------------------------------
     @torch.no_grad()
@@ -210,7 +205,7 @@ class VisionTransformer(nn.Module):
         B, C, H, W = x.shape
         assert H == self.patch_embed.img_size[0] and W == self.patch_embed.img_size[1], \
             f"Input image size ({H}*{W}) doesn't match model ({self.patch_embed.img_size[0]}*{self.patch_embed.img_size[1]})."
-        if self._packed is None:
+        if not self._packed_valid():
             self._pack()
         P = self._packed
         if x.dtype not in (torch.float16, torch.float32):

@@ -14,6 +14,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from .packing import PackedWeightsMixin
 
 
 class LlamaConfig:
@@ -120,7 +121,7 @@ class KVCache:
         self.key_mask = self.key_mask.index_select(0, beam_idx)
 
 
-class LlamaModel(nn.Module):
+class LlamaModel(PackedWeightsMixin, nn.Module):
     def __init__(self, config):
         super().__init__()
         self.config = config
@@ -141,13 +142,6 @@ class LlamaModel(nn.Module):
         self._packed = None
         self._rope = None
         return super()._apply(fn, *a, **kw)
-
-    def load_state_dict(self, *a, **kw):
-        self._packed = None
-        return super().load_state_dict(*a, **kw)
-
-    def repack(self):
-        self._packed = None
 
     def _pack(self):
         dev = self.norm.weight.device
@@ -175,6 +169,7 @@ class LlamaModel(nn.Module):
             layers.append(dict(w_qkv=w_qkv, w_o=f16(a.o_proj.weight), w_gu=w_gu, w_down=f16(m.down_proj.weight),
                                ln1=ln1, ln2=ln2))
         self._packed = dict(layers=layers, norm=f16(self.norm.weight), fuse=fuse)
+        self._mark_packed()
 
     def _rope_tables(self, device):
         if self._rope is None or self._rope[0].device != device:
@@ -201,7 +196,7 @@ class LlamaModel(nn.Module):
             w = self.embed_tokens.weight
             inputs_embeds = ops.gather_rows(w if w.dtype == torch.float16 else w.half(), input_ids.reshape(-1)).view(
                 input_ids.shape + (w.shape[1],))
-        if self._packed is None:
+        if not self._packed_valid():
             self._pack()
         P = self._packed
         cfg = self.config

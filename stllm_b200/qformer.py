@@ -14,6 +14,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
+from .packing import PackedWeightsMixin
 
 
 class BertConfig:
@@ -107,7 +108,7 @@ class BertEncoder(nn.Module):
         self.layer = nn.ModuleList([BertLayer(config, i) for i in range(config.num_hidden_layers)])
 
 
-class BertModel(nn.Module):
+class BertModel(PackedWeightsMixin, nn.Module):
     """Qformer.py:677-965 (add_pooling_layer=False as BertLMHeadModel builds it, :977)"""
 
     def __init__(self, config):
@@ -131,13 +132,6 @@ class BertModel(nn.Module):
     def _apply(self, fn, *a, **kw):
         self._packed = None
         return super()._apply(fn, *a, **kw)
-
-    def load_state_dict(self, *a, **kw):
-        self._packed = None
-        return super().load_state_dict(*a, **kw)
-
-    def repack(self):
-        self._packed = None
 
     def _pack(self):
         dev = self.embeddings.LayerNorm.weight.device
@@ -182,6 +176,7 @@ class BertModel(nn.Module):
             P["w_kv_all"] = torch.cat([torch.cat([k, v], 0) for k, v in zip(cross_k, cross_v)], 0).contiguous()
             P["b_kv_all"] = torch.cat([torch.cat([k, v], 0) for k, v in zip(cross_kb, cross_vb)], 0).contiguous()
         self._packed = P
+        self._mark_packed()
 
     @torch.no_grad()
     def forward(self, input_ids=None, attention_mask=None, query_embeds=None, encoder_hidden_states=None,
@@ -190,7 +185,7 @@ class BertModel(nn.Module):
         [N,P,W]; optional input_ids [N,Lt] with attention_mask [N,Q+Lt].  encoder_attention_mask must be all ones
         (it is in every reference call site: st_llm.py:333)."""
         assert query_embeds is not None, "You have to specify query_embeds when input_ids is None"
-        if self._packed is None:
+        if not self._packed_valid():
             self._pack()
         P = self._packed
         cfg = self.config

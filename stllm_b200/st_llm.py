@@ -515,9 +515,40 @@ class STLLMForCausalLM(nn.Module):
         """st_llm.py:149-158: merge sharded `pytorch_model-N-of-M.bin`"""
         pattern = re.compile(rf"{prefix}-(\d+)-of-(\d+).bin")
         sd = {}
-        for fn in [f for f in os.listdir(path) if pattern.match(f)]:
+        for fn in sorted(f for f in os.listdir(path) if pattern.match(f)):
             sd.update(torch.load(os.path.join(path, fn), map_location="cpu"))
         return sd
+
+    @classmethod
+    def load_hf_weights(cls, path):
+        """Every layout `LlamaForCausalLM.from_pretrained` (st_llm.py:164) reads from a local directory: sharded
+        `pytorch_model-N-of-M.bin` (+ index), a single `pytorch_model.bin`, `model.safetensors` or sharded
+        `model-N-of-M.safetensors`.  Raises when the directory holds none of them -- a model that silently keeps its random
+        initialisation is worse than an error."""
+        files = sorted(os.listdir(path))
+        sd = cls.get_state_dict(path)
+        if not sd and "pytorch_model.bin" in files:
+            sd = torch.load(os.path.join(path, "pytorch_model.bin"), map_location="cpu")
+        st_files = [f for f in files if f.endswith(".safetensors")]
+        if not sd and st_files:
+            try:
+                from safetensors.torch import load_file
+            except ImportError as e:
+                raise RuntimeError(f"{path} holds safetensors weights but the safetensors package is missing") from e
+            for fn in st_files:
+                sd.update(load_file(os.path.join(path, fn), device="cpu"))
+        if not sd:
+            raise FileNotFoundError(f"no LLM weights found in {path!r} (looked for pytorch_model-N-of-M.bin, pytorch_model.bin, "
+                                    f"*.safetensors)")
+        return sd
+
+    def repack(self):
+        """drop every packed (fused / norm-folded) fp16 weight copy; they are rebuilt at the next forward.  Loading a state
+        dict or editing parameters in place invalidates them automatically (stllm_b200/packing.py); this is the explicit form."""
+        from .packing import PackedWeightsMixin
+        for m in self.modules():
+            if isinstance(m, PackedWeightsMixin):
+                m.repack()
 
     @classmethod
     def from_config(cls, cfg, **overrides):
@@ -534,12 +565,31 @@ class STLLMForCausalLM(nn.Module):
                       "max_position_embeddings", "rms_norm_eps", "pad_token_id", "bos_token_id", "eos_token_id"):
                 if k in hf and hf[k] is not None:
                     lcfg.setdefault(k, hf[k])
-            sd = cls.get_state_dict(llama_model)
+            sd = cls.load_hf_weights(llama_model)                         # raises when the directory holds no weights
+        elif llama_model and not lcfg:
+            raise FileNotFoundError(f"llama_model={llama_model!r} is not a directory and no llama_config was given: pass the "
+                                    f"HF checkpoint directory (st_llm.py:164) or llama_config=dict(...) for a random-init LLM")
         if cfg.get("lora_r", 0) > 0:
             raise NotImplementedError("LoRA training is outside the hot path (SURVEY section 2: peft_model.py out of scope)")
-        model = cls(StllmConfig(**lcfg))
-        if sd:
-            model.load_state_dict(sd, strict=False)
+        # the reference loads the LLM in fp16 (st_llm.py:164 torch_dtype=torch.float16): build it in fp16 so that a 7B model is
+        # 13.5 GB on the host, not 27, and no per-forward .half() of lm_head / embed_tokens is needed
+        old_dtype = torch.get_default_dtype()
+        torch.set_default_dtype(torch.float16)
+        try:
+            model = cls(StllmConfig(**lcfg))
+        finally:
+            torch.set_default_dtype(old_dtype)
+        if sd is not None:
+            res = model.load_state_dict(sd, strict=False)
+            missing = [k for k in res.missing_keys if "stllm_model" not in k and "rotary_emb.inv_freq" not in k]
+            if missing or res.unexpected_keys:
+                import logging
+                logging.warning("LLM weights from %s: %d missing keys %s, %d unexpected keys %s", llama_model, len(missing),
+                                missing[:8], len(res.unexpected_keys), list(res.unexpected_keys)[:8])
+            if not (set(sd) & set(model.state_dict())):
+                raise RuntimeError(f"{llama_model!r}: none of the {len(sd)} tensors in the checkpoint matches a model parameter "
+                                   f"(first keys {sorted(sd)[:3]}): wrong directory or key layout")
+            model.llm_load_report = dict(missing=missing, unexpected=list(res.unexpected_keys))
         model.get_model().initialize_vision_modules(cfg, **overrides)
         if cfg.get("qformer_text_input", False) and model.get_model().stllm_model.llama_tokenizer is not None:
             n = len(model.get_model().stllm_model.llama_tokenizer)
@@ -561,13 +611,38 @@ class STLLMForCausalLM(nn.Module):
             for key in list(ckpt.keys()):                                 # :197-199 (the released files say llm_proj)
                 if "llm_proj" in key:
                     ckpt[key.replace("llm_proj", "llama_proj")] = ckpt.pop(key)
-            model.load_state_dict(ckpt, strict=False)
+            res = model.load_state_dict(ckpt, strict=False)
+            if res.unexpected_keys:
+                import logging
+                logging.warning("ST-LLM checkpoint %s: %d unexpected keys %s", ckpt_path, len(res.unexpected_keys),
+                                list(res.unexpected_keys)[:8])
+            model.ckpt_load_report = dict(missing=list(res.missing_keys), unexpected=list(res.unexpected_keys))
         return model
 
     @classmethod
     def default_config_path(cls, model_type):
         assert model_type in cls.PRETRAINED_MODEL_CONFIG_DICT, "Unknown model type {}".format(model_type)
         return cls.PRETRAINED_MODEL_CONFIG_DICT[model_type]
+
+    @classmethod
+    def from_pretrained(cls, model_type, **overrides):
+        """base_model.py:56-71: build from the model type's default configuration (stllm_b200/models_api.py holds the four
+        YAML defaults as dicts); `overrides` are merged over its `model` section (checkpoint paths, injected tokenizers,
+        `llama_config` / reduced depths for an offline random-init model)"""
+        from .models_api import default_config
+        cfg = default_config(cls, model_type)["model"]
+        cfg.update(overrides)
+        return cls.from_config(cfg)
+
+    def load_checkpoint(self, url_or_filename):
+        """base_model.py:29-52: load a finetuned checkpoint file ('model' wrapper accepted), strict=False; returns the
+        missing / unexpected key report"""
+        import logging
+        from .models_api import _checkpoint_state_dict
+        msg = self.load_state_dict(_checkpoint_state_dict(url_or_filename), strict=False)
+        logging.info("Missing keys {}".format(msg.missing_keys))
+        logging.info("load checkpoint from %s" % url_or_filename)
+        return msg
 
 
 registry.register_model("st_llm_hf")(STLLMForCausalLM)

@@ -38,6 +38,10 @@ class FakeTokenizer:
                 ids.append(3 + zlib.crc32(w.encode()) % (self.vocab_size - 3))
         return ids
 
+    def decode(self, ids, add_special_tokens=False, skip_special_tokens=False):
+        """ids -> "w<id>" words (no inverse of the hash exists; callers only split / strip the text)"""
+        return " ".join(f"w{int(i)}" for i in (ids.tolist() if hasattr(ids, "tolist") else ids))
+
     def __call__(self, text, return_tensors="pt", padding=False, truncation=False, max_length=None,
                  add_special_tokens=True):
         single = isinstance(text, str)

@@ -5,16 +5,25 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-def test_decode_kernels_and_engine():
-    import sys
+def pytest_generate_tests(metafunc):
+    if "decode_case" in metafunc.fixturenames:
+        import torch
+        if torch.cuda.is_available():
+            from scripts import gpu_check_decode as K
+            names = [n for n, _ in K.build_cases()]
+        else:
+            names = ["needs-gpu"]
+        metafunc.parametrize("decode_case", names)
+
+
+def test_decode_kernel_or_engine_case(decode_case):
+    """one pytest item per case of scripts/gpu_check_decode.py: decode_linear (all norm / epilogue forms, Vicuna shapes),
+    rope + cache append (bit-exact), attention over shared prompt K/V + per-beam suffix through the ancestry table (unfused
+    and fused), engine vs the general-kernel route"""
     from scripts import gpu_check_decode as K
-    argv, sys.argv = sys.argv, ["gpu_check_decode.py", "--no-time"]
-    try:
-        K.fails.clear()
-        rc = K.main()
-    finally:
-        sys.argv = argv
-    assert rc == 0, f"decode checks failed: {K.fails}"
+    fn = dict(K.build_cases())[decode_case]
+    K.fails.clear()
+    assert fn(), f"{decode_case}: {K.fails}"
 
 
 def test_engine_matches_decode_oracle_with_duplicated_ancestors():

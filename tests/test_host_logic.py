@@ -217,14 +217,66 @@ def test_from_config_loads_hf_shards_and_stllm_checkpoint(tmp_path):
     model = STLLMForCausalLM.from_config(cfg)
     assert model.config.hidden_size == 256 and len(model.model.layers) == 2
     sd = model.state_dict()
-    for k, v in {**shard1, **shard2}.items():
-        assert torch.equal(sd[k].float(), v), k
+    for k, v in {**shard1, **shard2}.items():            # the LLM is built in fp16, like the reference (st_llm.py:164)
+        assert sd[k].dtype == torch.float16 and torch.equal(sd[k].float(), v.half().float()), k
+    assert model.llm_load_report["unexpected"] == [] and len(model.llm_load_report["missing"]) > 0
     assert torch.equal(sd["model.stllm_model.llama_proj.weight"].float(), ck["model"]["model.stllm_model.llm_proj.weight"])
     assert torch.equal(sd["model.stllm_model.query_tokens"].float(), ck["model"]["model.stllm_model.query_tokens"])
     # the same checkpoint as a directory of shards (the layout the released ST-LLM weights use)
     ck_dir = tmp_path / "stllm_ckpt_dir"
     ck_dir.mkdir()
     torch.save(ck["model"], ck_dir / "pytorch_model-00001-of-00001.bin")
+    # a single pytorch_model.bin and safetensors are accepted too; an empty directory is an error, not a random-init model
+    single = tmp_path / "vicuna_single"
+    single.mkdir()
+    (single / "config.json").write_text(_json.dumps(hf_cfg))
+    torch.save({**shard1, **shard2}, single / "pytorch_model.bin")
+    m_single = STLLMForCausalLM.from_config(dict(cfg, llama_model=str(single)))
+    assert torch.equal(m_single.state_dict()["lm_head.weight"].float(), shard2["lm_head.weight"].half().float())
+    try:
+        from safetensors.torch import save_file
+        st_dir = tmp_path / "vicuna_st"
+        st_dir.mkdir()
+        (st_dir / "config.json").write_text(_json.dumps(hf_cfg))
+        save_file({k: v.contiguous() for k, v in {**shard1, **shard2}.items()}, str(st_dir / "model.safetensors"))
+        m_st = STLLMForCausalLM.from_config(dict(cfg, llama_model=str(st_dir)))
+        assert torch.equal(m_st.state_dict()["lm_head.weight"].float(), shard2["lm_head.weight"].half().float())
+    except ImportError:
+        pass
+    empty = tmp_path / "vicuna_empty"
+    empty.mkdir()
+    (empty / "config.json").write_text(_json.dumps(hf_cfg))
+    with pytest.raises(FileNotFoundError, match="no LLM weights"):
+        STLLMForCausalLM.from_config(dict(cfg, llama_model=str(empty)))
+    with pytest.raises(FileNotFoundError):
+        STLLMForCausalLM.from_config(dict(cfg, llama_model=str(tmp_path / "does_not_exist"), llama_config=None))
     model2 = STLLMForCausalLM.from_config(dict(cfg, ckpt=str(ck_dir)))
     assert torch.equal(model2.state_dict()["model.stllm_model.llama_proj.bias"].float(),
                        ck["model"]["model.stllm_model.llm_proj.bias"])
+
+
+def test_packed_weights_are_invalidated_by_parent_load_state_dict_and_in_place_edits():
+    """nn.Module.load_state_dict on a PARENT never calls a child's load_state_dict; the packed fp16 copies must
+    still be rebuilt (stllm_b200/packing.py: _load_from_state_dict hook + (address, version) signature of every parameter)"""
+    model = _small_model()
+    llm, vit = model.model, model.model.stllm_model.visual_encoder
+    qf = model.model.stllm_model.Qformer.bert
+    for m in (llm, vit, qf):
+        m._packed = {"stale": True}
+        m._mark_packed()
+        assert m._packed_valid()
+    model.load_state_dict(model.state_dict(), strict=False)          # load on the TOP-LEVEL module
+    assert not llm._packed_valid() and not vit._packed_valid() and not qf._packed_valid()
+    for m in (llm, vit, qf):
+        m._packed = {"stale": True}
+        m._mark_packed()
+    with torch.no_grad():                                             # in-place edits bump the version counter
+        llm.layers[0].mlp.down_proj.weight.mul_(1.0)                  # (edits through `.data` bypass it: call repack())
+        vit.blocks[0].attn.qkv.weight.add_(0.0)
+    assert not llm._packed_valid() and not vit._packed_valid() and qf._packed_valid()
+    model.repack()
+    assert qf._packed is None
+    llm._packed = {"stale": True}
+    llm._mark_packed()
+    model.half()                                                      # dtype change -> new storage
+    assert not llm._packed_valid()
