@@ -427,12 +427,32 @@ constexpr int LEFT_MAX = 4;
 constexpr int TAIL_MAX = 4;
 constexpr int WIDE_SMEM = 2 * BLK_BYTES + 2 * WKBLK + 2 * WKBLK + 4096 + 1024;   // Q | K (= P) | V | barriers + leftovers
 
+// 16-byte read-only load that ptxas may not sink next to its first use: batches of these are issued back to back, so a
+// thread has all pieces of a key / value row in flight at once (plain __ldg loads were re-serialised two at a time)
+DEVI uint4 ldg_nc_v4_volatile(const void* ptr) {
+  uint4 r;
+  asm volatile("ld.global.nc.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(ptr));
+  return r;
+}
+
+// "use" barrier: the values pass through a volatile asm, so everything computed from them is ordered after it -- and it is
+// ordered after every volatile load before it.  Placed behind a batch of loads it keeps the whole batch in flight.
+DEVI void pin_loaded(uint4& a, uint4& b) {
+  asm volatile("" : "+r"(a.x), "+r"(a.y), "+r"(a.z), "+r"(a.w), "+r"(b.x), "+r"(b.y), "+r"(b.z), "+r"(b.w));
+}
+
 template <int DH>
 __device__ __forceinline__ void attention_tail_rows(const AttnTcParams& p, uint8_t* smem, int h, int b) {
-  // CUDA-core path for the <= TAIL_MAX query rows after the last full tile: 128 threads, thread t scores keys t, t + 128, ...
+  // CUDA-core path for the <= TAIL_MAX query rows after the last full tile.  Latency is what counts (a few hundred CTAs of a
+  // few microseconds each): every thread owns whole keys and requests ALL 16-byte pieces of a key row before it uses the
+  // first (11 loads in flight per key), P V is split over (key group, 8-feature chunk) with 8 loads in flight per thread.
+  constexpr int NCHUNK = DH / 8;                         // 11 (head dim 88) or 16
+  const int nt = (int)blockDim.x, nwarp = nt >> 5;
   float* sq = reinterpret_cast<float*>(smem);            // [DH] the (pre-scaled, fp16-rounded) query row
   float* sp = sq + 128;                                  // [Skv] probabilities (unnormalised)
-  float* red = sp + ((p.Skv + 31) & ~31);                // [8] reduction scratch
+  float* red = sp + ((p.Skv + 31) & ~31);                // [2][32] reduction scratch
+  float* part = red + 64;                                // [KG][DH] partial outputs
+  const int KG = nt / NCHUNK;                            // key groups of the P V phase
   const int t = threadIdx.x;
   const float sl2 = p.scale * 1.4426950408889634f;
   const int row0 = (p.Sq / TQ) * TQ;
@@ -446,63 +466,71 @@ __device__ __forceinline__ void attention_tail_rows(const AttnTcParams& p, uint8
     }
     __syncthreads();
     float mx = -INFINITY;
-    if (t < 128) {
-      for (int key = t; key < p.Skv; key += 128) {
-        const uint4* kp = reinterpret_cast<const uint4*>(p.k + (long long)b * p.k_sb + (long long)key * p.k_ss + (long long)h * DH);
-        float acc = 0.f;
+    for (int key = t; key < p.Skv; key += nt) {
+      const uint4* kp = reinterpret_cast<const uint4*>(p.k + (long long)b * p.k_sb + (long long)key * p.k_ss + (long long)h * DH);
+      uint4 u[NCHUNK];
 #pragma unroll
-        for (int c = 0; c < DH / 8; ++c) {
-          const uint4 u = __ldg(kp + c);
-          const __half2* hh = reinterpret_cast<const __half2*>(&u);
+      for (int c = 0; c < NCHUNK; ++c) u[c] = ldg_nc_v4_volatile(kp + c);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2 f = __half22float2(hh[i]);
-            acc = fmaf(sq[c * 8 + 2 * i], f.x, acc);
-            acc = fmaf(sq[c * 8 + 2 * i + 1], f.y, acc);
-          }
+      for (int c = 0; c + 1 < NCHUNK; c += 2) pin_loaded(u[c], u[c + 1]);
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < NCHUNK; ++c) {
+        const __half2* hh = reinterpret_cast<const __half2*>(&u[c]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __half22float2(hh[i]);
+          a0 = fmaf(sq[c * 8 + 2 * i], f.x, a0);
+          a1 = fmaf(sq[c * 8 + 2 * i + 1], f.y, a1);
         }
-        acc *= sl2;
-        sp[key] = acc;
-        mx = fmaxf(mx, acc);
       }
+      const float acc = (a0 + a1) * sl2;
+      sp[key] = acc;
+      mx = fmaxf(mx, acc);
     }
     mx = warp_max(mx);
-    if ((t & 31) == 0 && t < 128) red[t >> 5] = mx;
+    if ((t & 31) == 0) red[t >> 5] = mx;
     __syncthreads();
-    mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    mx = -INFINITY;
+    for (int w = 0; w < nwarp; ++w) mx = fmaxf(mx, red[w]);
     float sum = 0.f;
-    if (t < 128) {
-      for (int key = t; key < p.Skv; key += 128) {
-        const float e = exp2f(sp[key] - mx);
-        sp[key] = e;
-        sum += e;
-      }
+    for (int key = t; key < p.Skv; key += nt) {
+      const float e = exp2f(sp[key] - mx);
+      sp[key] = e;
+      sum += e;
     }
     sum = warp_sum(sum);
-    if ((t & 31) == 0 && t < 128) red[4 + (t >> 5)] = sum;
+    if ((t & 31) == 0) red[32 + (t >> 5)] = sum;
     __syncthreads();
-    const float inv = 1.f / (red[4] + red[5] + red[6] + red[7]);
-    // P V: thread (key group kg, 8-feature chunk c) sums its keys kg, kg + 16, ... (independent 16-byte loads, ~16 per
-    // thread), the 16 partial sums of a chunk are then added through shared memory
-    constexpr int NCHUNK = DH / 8;                       // 11 (head dim 88) or 16
-    constexpr int KG = 16;
-    float* part = red + 8;                               // [KG][DH] partial outputs
-    if (t < KG * NCHUNK && NCHUNK * KG <= TC_THREADS) {
+    float total = 0.f;
+    for (int w = 0; w < nwarp; ++w) total += red[32 + w];
+    const float inv = 1.f / total;
+    if (t < KG * NCHUNK) {
       const int kg = t / NCHUNK, c = t % NCHUNK;
       float acc[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] = 0.f;
       const __half* vp = p.v + (long long)b * p.v_sb + (long long)h * DH + c * 8;
-#pragma unroll 4
-      for (int key = kg; key < p.Skv; key += KG) {
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(vp + (long long)key * p.v_ss));
-        const __half2* hh = reinterpret_cast<const __half2*>(&u);
-        const float w = sp[key];
+      for (int k0 = kg; k0 < p.Skv; k0 += 8 * KG) {
+        uint4 u[8];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float2 f = __half22float2(hh[i]);
-          acc[2 * i] = fmaf(w, f.x, acc[2 * i]);
-          acc[2 * i + 1] = fmaf(w, f.y, acc[2 * i + 1]);
+        for (int j = 0; j < 8; ++j) {
+          const int key = k0 + j * KG;
+          u[j] = ldg_nc_v4_volatile(vp + (long long)(key < p.Skv ? key : kg) * p.v_ss);   // clamped: weight 0 below
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) pin_loaded(u[j], u[j + 1]);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int key = k0 + j * KG;
+          const float w = key < p.Skv ? sp[key] : 0.f;
+          const __half2* hh = reinterpret_cast<const __half2*>(&u[j]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 f = __half22float2(hh[i]);
+            acc[2 * i] = fmaf(w, f.x, acc[2 * i]);
+            acc[2 * i + 1] = fmaf(w, f.y, acc[2 * i + 1]);
+          }
         }
       }
 #pragma unroll
@@ -511,7 +539,6 @@ __device__ __forceinline__ void attention_tail_rows(const AttnTcParams& p, uint8
     __syncthreads();
     if (t < DH) {
       float a = 0.f;
-#pragma unroll
       for (int kg = 0; kg < KG; ++kg) a += part[kg * DH + t];
       p.o[(long long)b * p.o_sb + (long long)qrow * p.o_ss + (long long)h * p.o_sh + t] = __float2half_rn(a * inv);
     }
@@ -522,8 +549,9 @@ __device__ __forceinline__ void attention_tail_rows(const AttnTcParams& p, uint8
 // The <= TAIL_MAX query rows after the last full 128-row tile as their own launch (grid = heads x 1 x batch): with it the
 // tensor-core kernel runs on Sq - tail rows -- for the ViT (257 = 2 x 128 + 1) two query tiles per (frame, head) instead of
 // three, the third of which held ONE row and cost a quarter of the kernel (39.0 -> 29.0 us, profiles/r02_attention.md).
+constexpr int TAIL_THREADS = 288;   // one key per thread for the 257 keys of the ViT
 template <int DH>
-__global__ void __launch_bounds__(TC_THREADS) attention_tail_kernel(const AttnTcParams p) {
+__global__ void __launch_bounds__(TAIL_THREADS) attention_tail_kernel(const AttnTcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~uintptr_t(127));
   pdl_launch_dependents();
@@ -973,7 +1001,10 @@ int stllm_attention_tc_try(const void* q, const void* k, const void* v, void* ou
   p.n_left = p.n_tail = 0;
   // ViT shape: the few query rows after the last full tile go to the CUDA-core tail kernel, the tensor-core kernel runs on
   // the full tiles only (two launches; the tail launch is 256 small CTAs, ~4 us)
-  static const int tail_ok = [] { const char* e = getenv("STLLM_ATTN_TAIL"); return (e != nullptr && atoi(e) == 0) ? 0 : 1; }();
+  // OFF by default: the tail launch itself measures ~25 us (ptxas keeps only two of its 16-byte loads in flight per thread,
+  // so its 257 x 176-byte key rows cost ~30 dependent L2 round trips) -- more than the 10 us the third query tile costs.
+  // STLLM_ATTN_TAIL=1 enables it (parity-green: tests/test_kernels_gpu.py attention cases run with both settings).
+  static const int tail_ok = [] { const char* e = getenv("STLLM_ATTN_TAIL"); return (e != nullptr && atoi(e) == 1) ? 1 : 0; }();
   const int tail = Sq % TQ;
   if (tail_ok && D == 88 && !causal && key_mask == nullptr && Sq > TQ && tail >= 1 && tail <= TAIL_MAX && Skv <= 8192) {
     AttnTcParams pm = p;
@@ -982,13 +1013,13 @@ int stllm_attention_tc_try(const void* q, const void* k, const void* v, void* ou
     if (rc != STLLM_OK) return rc;
     p.n_tail = tail;
     auto kern = attention_tail_kernel<88>;
-    const int smem = (128 + ((Skv + 31) & ~31) + 8 + 16 * 88) * 4 + 256;
+    const int smem = (128 + ((Skv + 31) & ~31) + 64 + (TAIL_THREADS / 11) * 88) * 4 + 256;
     static int configured_smem = 0;
     if (smem > 48 * 1024 && smem > configured_smem) {
       STLLM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
       configured_smem = smem;
     }
-    STLLM_CHECK_CUDA(stllm_launch(kern, dim3(H, 1, B), dim3(TC_THREADS), smem, stream, p));
+    STLLM_CHECK_CUDA(stllm_launch(kern, dim3(H, 1, B), dim3(TAIL_THREADS), smem, stream, p));
     return STLLM_OK;
   }
   if (D == 88) return launch_tc<88>(tq, tk, tv, p, stream);

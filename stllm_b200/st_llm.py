@@ -317,6 +317,7 @@ class STLLMModel(nn.Module):
             mask_cpu = RandomMaskingGenerator(L, mask_rate, B, "cpu").unsqueeze(1)
             self.mask = mask_cpu.to(dev)
             keep = ~mask_cpu.reshape(B, L).numpy()
+            self._keep_host = keep
             self.mask_img_len = int(keep[0].sum())
         if not prompts:
             raise ValueError("samples['instruction_input'] with an <ImageHere> placeholder is required")
@@ -410,28 +411,45 @@ class STLLMLlamaModel(LlamaModel):
         if samples is None:
             return super().forward(inputs_embeds=inputs_embeds, **kwargs)
         inputs_embeds, attention_mask, unmask_inputs_embeds, unmask_attention_mask, labels = self.stllm_model(samples)
-        output_hidden_states = not (unmask_inputs_embeds is None)
+        if unmask_inputs_embeds is None:
+            outputs = super().forward(input_ids=None, attention_mask=attention_mask, inputs_embeds=inputs_embeds,
+                                      use_cache=False, output_hidden_states=False, return_dict=True)
+            return outputs, None, labels
+        sm = self.stllm_model
+        rows = self.mvm_select_rows(sm._keep_host, unmask_inputs_embeds.shape[1]).to(inputs_embeds.device)
+        outputs, loss_mvm = self.mvm_passes(inputs_embeds, attention_mask, unmask_inputs_embeds, unmask_attention_mask,
+                                            rows, sm.mask_img_len, output_hidden_states=True)
+        return outputs, loss_mvm, labels
+
+    def mvm_select_rows(self, keep_host, unmask_seq_len):
+        """row numbers, in the flattened [B * S_u] unmasked hidden states, of the VISIBLE video positions:
+        `unmask_output[:, img_start:img_start + img_len][~mask]` (st_llm.py:85-86) as a host-built index (bit-exact)"""
+        img_start = 0 if self.stllm_model.qformer_text_input else 8                   # st_llm.py:71
+        B, L = keep_host.shape
+        b, l = np.nonzero(keep_host)                                                  # row-major: the order of [~mask]
+        return torch.from_numpy((b * unmask_seq_len + img_start + l).astype(np.int64))
+
+    @torch.no_grad()
+    def mvm_passes(self, inputs_embeds, attention_mask, unmask_inputs_embeds, unmask_attention_mask, rows, mask_img_len,
+                   output_hidden_states=False):
+        """st_llm.py:62-91, device work only (no host synchronisation: capturable in a CUDA graph): masked LLM pass ->
+        MVM decoder on the visible video positions; unmasked LLM pass -> same positions gathered; cosine loss."""
+        sm = self.stllm_model
+        img_start = 0 if sm.qformer_text_input else 8                                  # st_llm.py:71
         outputs = super().forward(input_ids=None, attention_mask=attention_mask, inputs_embeds=inputs_embeds,
                                   use_cache=False, output_hidden_states=output_hidden_states, return_dict=True)
-        if unmask_inputs_embeds is None:
-            return outputs, None, labels
-        img_start = 0 if self.stllm_model.qformer_text_input else 8                   # st_llm.py:71
-        mask_output = outputs.hidden_states[-1]
+        mask_output = outputs.last_hidden_state                                       # == hidden_states[-1] (post-norm)
         B, _, D = mask_output.size()
-        mask_img_output = mask_output[:, img_start:img_start + self.stllm_model.mask_img_len].contiguous()
-        if hasattr(self.stllm_model, "mvm_decoder"):
-            mask_img_output = self.stllm_model.mvm_decoder(mask_img_output)
+        mask_img_output = mask_output[:, img_start:img_start + mask_img_len].contiguous()
+        if hasattr(sm, "mvm_decoder"):
+            mask_img_output = sm.mvm_decoder(mask_img_output)
         unmask_outputs = super().forward(inputs_embeds=unmask_inputs_embeds, attention_mask=unmask_attention_mask,
-                                         return_dict=True, use_cache=False, output_hidden_states=True)
-        unmask_output = unmask_outputs.hidden_states[-1]
+                                         return_dict=True, use_cache=False, output_hidden_states=output_hidden_states)
+        unmask_output = unmask_outputs.last_hidden_state
         S_u = unmask_output.shape[1]
-        # unmask_output[:, img_start:img_start+img_len][~mask]  as one row gather (bit-exact index path)
-        keep = torch.nonzero(~self.stllm_model.mask.squeeze(1).reshape(-1)).reshape(-1)
-        L = self.stllm_model.img_len
-        rows = (keep // L) * S_u + img_start + (keep % L)
         unmask_img_output = ops.gather_rows(unmask_output.reshape(B * S_u, D), rows)
         loss_mvm = ops.cosine_loss(mask_img_output.reshape(-1, D), unmask_img_output)  # st_llm.py:89-91
-        return outputs, loss_mvm, labels
+        return outputs, loss_mvm
 
 
 class STLLMForCausalLM(nn.Module):
