@@ -109,6 +109,12 @@ int stllm_attention_f16(const void* q, const void* k, const void* v, void* out, 
  * tcgen05 kernel; 0 = always the mma.sync kernel. */
 int stllm_set_attention_tc(int on);
 
+/* Experimental variants of the ViT-shape tensor-core attention (measured slower than the default, kept for A/B and parity;
+ * profiles/r02_attention.md): wide = 128-key tiles with the leftover key / trailing query rows on CUDA cores in one kernel;
+ * tail = default kernel on the full 128-row query tiles + a CUDA-core launch for the trailing rows.  -1 = follow the
+ * STLLM_ATTN_WIDE / STLLM_ATTN_TAIL environment variables (default off). */
+int stllm_set_attention_variant(int wide, int tail);
+
 /* y = LayerNorm(x) with fp32 statistics; gamma/beta fp32.  eva_vit.py:157,163; blip2.py:103-109; Qformer.py:65,
  * 282,366; st_llm.py:39. */
 int stllm_layernorm_f16(const void* x, long long ldx, void* y, long long ldy, const float* gamma, const float* beta,

@@ -13,7 +13,13 @@ import types
 
 import torch.nn as nn
 
-REF = os.environ.get("STLLM_REFERENCE", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+# Where the reference's source files are read from: $STLLM_REFERENCE, the read-only tree of the build container, or
+# oracle/_ref/ -- a git-ignored copy of the reference's model / common files that `__graft_entry__.build()` materialises while
+# the tree exists (oracle/materialize_ref.py), so that the GPU box -- which has no /root/reference -- can still time the
+# reference's OWN modules as the CPU baseline (`bench.py --impl reference`, cpu_baseline.kind = "reference").
+REF = os.environ.get("STLLM_REFERENCE") or ("/root/reference" if os.path.isfile("/root/reference/stllm/models/st_llm.py")
+                                             else os.path.join(_HERE, "_ref"))
 _loaded = None
 
 

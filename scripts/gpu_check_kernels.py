@@ -230,15 +230,18 @@ def _n(*a, **kw):
           lambda: norm_gemm_case(*a, **kw))
 
 
-def _a(tc, *a, **kw):
+def _a(tc, *a, variant=(-1, -1), **kw):
     def run():
         from stllm_b200 import _lib as _L
         _L.load().stllm_set_attention_tc(tc)
+        _L.load().stllm_set_attention_variant(*variant)
         try:
             return attn_case(*a, **kw)
         finally:
             _L.load().stllm_set_attention_tc(1)
-    _case(f"attn tc={tc} " + " ".join(str(x) for x in a) + "".join(f" {k}={v}" for k, v in kw.items()), run)
+            _L.load().stllm_set_attention_variant(-1, -1)
+    vtag = {(-1, -1): "", (1, 0): " wide-tile", (0, 1): " tail-kernel"}[variant]
+    _case(f"attn tc={tc}{vtag} " + " ".join(str(x) for x in a) + "".join(f" {k}={v}" for k, v in kw.items()), run)
 
 
 def build_cases():
@@ -360,6 +363,12 @@ def build_cases():
         _a(tc, 1, 32, 2048, 2048, 128, causal=True, packed=True)   # max_position_embeddings
         _a(tc, 3, 16, 257, 257, 88, prescale=True, packed=True)    # odd batch
         _a(tc, 2, 16, 200, 200, 88, prescale=True, packed=True)    # fewer tokens than the ViT (interpolated grids)
+    for variant in ((1, 0), (0, 1)):       # the two default-off ViT attention experiments stay parity-checked
+        _a(1, 2, 16, 257, 257, 88, prescale=True, packed=True, variant=variant)
+        _a(1, 16, 16, 257, 257, 88, prescale=True, packed=True, variant=variant)
+        _a(1, 2, 3, 257, 257, 88, variant=variant)
+        _a(1, 2, 16, 200, 200, 88, prescale=True, packed=True, variant=variant)
+        _a(1, 2, 4, 259, 130, 88, prescale=True, variant=variant)        # 3 tail rows, 2 leftover keys
     _case("layernorm 4112x1408 eps1e-6", lambda: misc_case("ln1"))
     _case("layernorm 333x768 eps1e-12", lambda: misc_case("ln2"))
     _case("rmsnorm 576x4096", lambda: misc_case("rms"))

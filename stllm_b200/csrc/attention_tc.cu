@@ -939,6 +939,15 @@ int launch_tc_wide(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorM
 }  // namespace
 
 static int g_attn_tc = -1;   // -1: read STLLM_ATTN_TC on first use (default on)
+static int g_attn_wide = -1;  // -1: read STLLM_ATTN_WIDE on first use (default off)
+static int g_attn_tail = -1;  // -1: read STLLM_ATTN_TAIL on first use (default off)
+// experiments kept in the library (profiles/r02_attention.md): wide = 128-key tiles + leftover key / tail rows on CUDA cores
+// in one kernel; tail = round-1 kernel on the full query tiles + a CUDA-core launch for the trailing rows.  -1 = environment.
+extern "C" int stllm_set_attention_variant(int wide, int tail) {
+  g_attn_wide = wide;
+  g_attn_tail = tail;
+  return STLLM_OK;
+}
 // debug / A-B switch: 1 = use the tcgen05 attention kernel where it applies, 0 = always the mma.sync kernel
 extern "C" int stllm_set_attention_tc(int on) {
   g_attn_tc = on ? 1 : 0;
@@ -964,7 +973,8 @@ int stllm_attention_tc_try(const void* q, const void* k, const void* v, void* ou
   if ((reinterpret_cast<uintptr_t>(out) & 15) != 0) return STLLM_ERR_UNSUPPORTED;
   // wide-tile kernel: the ViT shape (non-causal, no key mask, head dim 88, at least one full 128-key tile)
   // Measured SLOWER than the 64-key kernel (49 vs 39 us on the ViT shape, profiles/r02_attention.md): kept as an experiment
-  static const int wide_ok = [] { const char* e = getenv("STLLM_ATTN_WIDE"); return (e != nullptr && atoi(e) == 1) ? 1 : 0; }();
+  static const int wide_env = [] { const char* e = getenv("STLLM_ATTN_WIDE"); return (e != nullptr && atoi(e) == 1) ? 1 : 0; }();
+  const int wide_ok = g_attn_wide >= 0 ? g_attn_wide : wide_env;
   const bool wide = wide_ok && D == 88 && !causal && key_mask == nullptr && Skv >= WKV && Skv <= 4096 && Sq >= TQ;
   CUtensorMap tq, tk, tv;
   int rc = make_tmap3(&tq, q, H * D, Sq, B, qs[1], qs[0], TQ);
@@ -1004,7 +1014,8 @@ int stllm_attention_tc_try(const void* q, const void* k, const void* v, void* ou
   // OFF by default: the tail launch itself measures ~25 us (ptxas keeps only two of its 16-byte loads in flight per thread,
   // so its 257 x 176-byte key rows cost ~30 dependent L2 round trips) -- more than the 10 us the third query tile costs.
   // STLLM_ATTN_TAIL=1 enables it (parity-green: tests/test_kernels_gpu.py attention cases run with both settings).
-  static const int tail_ok = [] { const char* e = getenv("STLLM_ATTN_TAIL"); return (e != nullptr && atoi(e) == 1) ? 1 : 0; }();
+  static const int tail_env = [] { const char* e = getenv("STLLM_ATTN_TAIL"); return (e != nullptr && atoi(e) == 1) ? 1 : 0; }();
+  const int tail_ok = g_attn_tail >= 0 ? g_attn_tail : tail_env;
   const int tail = Sq % TQ;
   if (tail_ok && D == 88 && !causal && key_mask == nullptr && Sq > TQ && tail >= 1 && tail <= TAIL_MAX && Skv <= 8192) {
     AttnTcParams pm = p;

@@ -175,7 +175,7 @@ class MaskedTrainPipeline(_GraphedStep):
     and the mask only, not on the frames."""
 
     def __init__(self, model, batch, frames, after_ids, answer_ids, mask_rate=0.5, seed=1237, img_size=224, use_graph=True,
-                 frames_dtype=torch.float32):
+                 frames_dtype=torch.float32, before_ids=None):
         import numpy as np
         from . import prompt_assembly as PA
         from .st_llm import RandomMaskingGenerator
@@ -193,7 +193,8 @@ class MaskedTrainPipeline(_GraphedStep):
         sm.img_len, sm.mask_img_len, sm._keep_host = L, self.mask_img_len, keep
         sm.mask = torch.from_numpy(~keep).unsqueeze(1).to(dev)
         after = [np.asarray(a, dtype=np.int64) for a in after_ids]
-        before = [np.zeros(0, dtype=np.int64)] * batch
+        before = [np.zeros(0, dtype=np.int64)] * batch if before_ids is None else \
+            [np.asarray(b, dtype=np.int64) for b in before_ids]
         a_ids = np.asarray(answer_ids, dtype=np.int64)
         a_att = np.ones_like(a_ids)
         pad = model.config.pad_token_id if model.config.pad_token_id is not None else 0
