@@ -330,6 +330,38 @@ def golden_noqformer(ref):
           **_sd_arrays("w.", sd))
 
 
+@torch.no_grad()
+def golden_pre_encoding(ref):
+    """`pre_encoding=True` (st_llm.py:452-455): samples["image"] already holds Q-Former features [B,T,32,768]; only
+    llama_proj runs, then 'mean' aggregation and the sequence assembly -- the reference's own STLLMModel.forward on a stub
+    object (MiniGPT-4 layout: BOS + prefix) -> pre_encoding_small.npz"""
+    import torch.nn as nn
+    st = ref.st_llm
+    B, T, Q, C, D, V = 2, 3, 32, 768, 128, 80
+    g = torch.Generator().manual_seed(31)
+    M = st.STLLMModel.__new__(st.STLLMModel)
+    nn.Module.__init__(M)
+    M.pre_encoding, M.video_input, M.use_mask, M.mvm_decode = True, "mean", False, False
+    M.qformer_text_input, M.max_txt_len, M.end_sym = False, 8, " ###"
+    M.llama_tokenizer = fake_tokenizer.FakeTokenizer(V, pad_token_id=0, bos_token_id=1, eos_token_id=2)
+    M.embed_tokens = nn.Embedding(V, D)
+    M.llama_proj = nn.Linear(C, D)
+    M.embed_tokens.weight.data.copy_((torch.randn(V, D, generator=g) * 0.5).half().float())
+    M.llama_proj.weight.data.copy_((torch.randn(D, C, generator=g) * 0.05).half().float())
+    M.llama_proj.bias.data.copy_((torch.randn(D, generator=g) * 0.1).half().float())
+    feats = (torch.randn(B, T, Q, C, generator=g)).half().float()
+    samples = {"image": feats,
+               "instruction_input": ["### Human : < Video > clip <ImageHere> </Video> what happens ? ###Assistant: ",
+                                     "### Human : < Video > clip <ImageHere> </Video> describe it ###Assistant: "],
+               "answer": ["a cat sleeps", "two people talk on a bench"]}
+    emb, att, emb_u, att_u, targets = st.STLLMModel.forward(M, samples)
+    assert emb_u is None
+    _save("pre_encoding_small.npz", feats=feats.numpy(), inputs_embeds=emb.numpy(), attention_mask=att.numpy(),
+          targets=targets.numpy(), prompts=np.array(samples["instruction_input"]), answers=np.array(samples["answer"]),
+          **{"w.embed_tokens.weight": M.embed_tokens.weight.numpy(), "w.llama_proj.weight": M.llama_proj.weight.numpy(),
+             "w.llama_proj.bias": M.llama_proj.bias.numpy()})
+
+
 GEN_CASES = {
     # name: generate kwargs (the harness settings of SURVEY 3A / conversation.py:231-243: do_sample False, min_length 1, ...).
     # min_length counts the prompt when generate() gets inputs_embeds only (installed transformers: `_prepare_generated_length`
@@ -397,7 +429,7 @@ def golden_generate(ref):
 if __name__ == "__main__":
     ref = ref_shim.load_reference()
     which = sys.argv[1:] or ["vit", "qformer", "qformer_text", "llama", "mask", "flow", "flow_minigpt4", "assembly",
-                             "btadapter", "preprocess", "noqformer", "generate"]
+                             "btadapter", "preprocess", "noqformer", "generate", "pre_encoding"]
     if "vit" in which:
         golden_vit(ref)
     if "qformer" in which:
@@ -422,3 +454,5 @@ if __name__ == "__main__":
         golden_noqformer(ref)
     if "generate" in which:
         golden_generate(ref)
+    if "pre_encoding" in which:
+        golden_pre_encoding(ref)
