@@ -359,7 +359,8 @@ def gpu_eager_leg(model, frames_dev, ids_dev, args, ours_ms):
     import torch
     from oracle import stllm_oracle as O
     try:
-        w = O.split_state_dict({k: v for k, v in model.state_dict().items()})
+        # everything in fp16, as `model.to(torch.float16)` of demo.py:46 does (the product keeps LayerNorm parameters fp32)
+        w = O.split_state_dict(model.state_dict(), dtype=torch.float16, device=frames_dev.device)
         cfg = dict(vit_depth=args.vit_depth, vit_heads=16, qf_layers=args.qformer_layers, llama_layers=args.llama_layers,
                    llama_heads=32)
         fr = frames_dev.half()
@@ -558,6 +559,8 @@ def decode_leg(model, peaks, dev, steps=48, S=T_FRAMES * Q_TOK + PROMPT_LEN):
         tok = torch.randint(3, V, (beams,), device=dev, generator=g)
         idx = torch.arange(beams, device=dev).flip(0)
         for _ in range(4):
+            if beams > 1:
+                eng.reorder(idx)
             eng.step(tok)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -178,7 +178,8 @@ def bt_adapter_forward(sd, frames, depth, num_heads, bt_depth=3, patch=14, colle
 
 def ln_vision(sd, x, eps=1e-5):
     """blip2.LayerNorm (fp32 LayerNorm, nn default eps), blip2.py:73,103-109; call site st_llm.py:331"""
-    return F.layer_norm(x.float(), (x.shape[-1],), sd["weight"], sd["bias"], eps)
+    ret = F.layer_norm(x.float(), (x.shape[-1],), sd["weight"].float(), sd["bias"].float(), eps)
+    return ret.to(x.dtype)                       # blip2.py:105-109: computed in fp32, cast back to the input dtype
 
 
 # --------------------------------------------------------------------------------------------------
@@ -487,9 +488,12 @@ def assemble_sequence(video_embeds, prompt_embeds, answer_embeds, answer_mask, p
 # --------------------------------------------------------------------------------------------------
 
 
-def split_state_dict(sd):
-    """STLLMForCausalLM.state_dict() (reference key names, st_llm.py / SURVEY section 5) -> oracle sub-dicts, fp32 CPU"""
-    f = {k: (v.detach().float().cpu() if v.is_floating_point() else v.detach().cpu()) for k, v in sd.items()}
+def split_state_dict(sd, dtype=torch.float32, device="cpu"):
+    """STLLMForCausalLM.state_dict() (reference key names, st_llm.py / SURVEY section 5) -> oracle sub-dicts, fp32 CPU by
+    default.  dtype / device select where the SAME arithmetic is evaluated (tests and bench.py's gpu_eager_fp16 leg run it in
+    fp16 or fp32 on the GPU as the library bar / full-depth reference)."""
+    f = {k: (v.detach().to(device=device, dtype=dtype) if v.is_floating_point() else v.detach().to(device=device))
+         for k, v in sd.items()}
     pre = "model.stllm_model."
 
     def sub(prefix):

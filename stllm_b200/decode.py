@@ -100,6 +100,12 @@ class DecodeEngine:
         self.launches_per_step = None
         if use_graph:
             self._capture()
+        if self.R > 1:
+            # first use of the re-ordering path loads torch's index_select / copy kernels (CUDA lazy module loading, ~40 ms
+            # once per process): do it here, not inside the first beam step.  This one-off cost -- landing in the first 10
+            # steps of the first 5-beam engine of a process -- was round 1's "bimodal" 5-beam timing (3.1 vs 3.9-4.4 ms/token
+            # over 48 steps; profiles/r02_decode_transient.md).
+            self.reorder(torch.arange(self.R, device=dev))
 
     # one token for every row: self.tok -> self.logits; device-side position counter advanced at the end
     def _step_impl(self):

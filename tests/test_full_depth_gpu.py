@@ -40,10 +40,10 @@ def test_config2_full_depth_logits_vs_fp32_arithmetic_and_fp16_eager():
         # the product rounds the fp32 frames to fp16 in the patch-embed loader, as the reference's autocast conv does:
         # feed both references the same fp16-rounded frames
         fr16 = frames.half().to(dev)
-        w16 = O.split_state_dict(sd)
+        w16 = O.split_state_dict(sd, dtype=torch.float16, device=dev)          # everything fp16, as demo.py:46
         eager = O.video_prefill(w16, fr16, ids.to(dev), cfg).float()
         del w16
-        w32 = O.split_state_dict({k: (v.float() if v.is_floating_point() else v) for k, v in sd.items()})
+        w32 = O.split_state_dict(sd, dtype=torch.float32, device=dev)
         ref = O.video_prefill(w32, fr16.float(), ids.to(dev), cfg)
         del w32
     e_ours, e_eager = rel_fro(ours, ref), rel_fro(eager, ref)
