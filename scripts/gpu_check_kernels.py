@@ -344,6 +344,13 @@ def build_cases():
     _n(4112, 6144, 1408, 2, epi=ops.EPI_GELU, tile_n=257)
     _n(300, 700, 512, 2, residual=True, tile_n=1024 + 176)
     _n(300, 700, 512, 2, tile_n=65)
+    # folded norm with SWAPPED operands (features on the TMEM lanes; per-token statistics through a shared table)
+    _n(576, 12288, 4096, 1, tile_n=2048 + 192 + 1)
+    _n(576, 22016, 4096, 1, epi=ops.EPI_SWIGLU, tile_n=2048 + 192 + 1)
+    _n(300, 700, 512, 1, residual=True, tile_n=2048 + 96 + 1)
+    _n(300, 700, 512, 2, residual=True, tile_n=2048 + 160 + 1)
+    _n(300, 1000, 512, 2, epi=ops.EPI_GELU, tile_n=2048 + 256 + 1)
+    _n(5, 1024, 4096, 1, tile_n=2048 + 16 + 1)
     for ptile in (257, 1024 + 128 + 1, 1024 + 176 + 1, 1024 + 192 + 1, 1024 + 240 + 1):   # producer tile widths
         _n(576, 1024, 4096, 1, producer_tile=ptile)
         _n(700, 512, 1408, 2, producer_tile=ptile)

@@ -74,9 +74,11 @@ DEVI uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug must trap (-> CUDA error on the host) instead of hanging the GPU.
 // Returns the number of cycles spent waiting (0 if the phase had already completed).
+// returns the cycles spent waiting INCLUDING the first try: mbarrier.try_wait suspends the thread in hardware for a
+// while before it reports failure, so a count that starts after the first failed try misses most of a short wait
 DEVI long long mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return 0;
-  long long t0 = clock64();
+  const long long t0 = clock64();
+  if (mbar_try_wait(bar, parity)) return clock64() - t0;
   while (!mbar_try_wait(bar, parity)) {
     if (clock64() - t0 > 4000000000LL) {  // ~2 s at 2 GHz
       printf("stllm: mbarrier wait timeout (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
@@ -234,6 +236,21 @@ DEVI uint32_t mapa_shared(uint32_t addr, uint32_t cta) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
   return r;
+}
+// Arrivals that only hand a TMEM accumulator stage back to the MMA issuer carry no memory payload: the tcgen05.ld
+// results are in registers (tcgen05.wait::ld) and tcgen05.fence::before_thread_sync orders the async proxy.  The default
+// .release form compiles to MEMBAR.ALL.GPU + ERRBAR at cluster scope, i.e. it waits until every global store of the
+// epilogue has been acknowledged by L2 (6-10 % of the epilogue warps' stall samples, profiles/r02_epilogue.md).
+DEVI void mbar_arrive_relaxed(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+DEVI void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+DEVI float4 lds_f4(uint32_t smem_addr) {
+  float4 f;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w) : "r"(smem_addr));
+  return f;
 }
 DEVI void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");

@@ -201,26 +201,39 @@ DEVI void stg_v8(void* ptr, const uint32_t (&r)[8]) {
 
 // per-thread (= per output row) context of the fused epilogue for one tile
 struct RowCtx {
-  float mu, rstd;         // folded normalisation of this row (mode 0: unused)
+  float mu, rstd;         // folded normalisation of this row (mode 0: mu = 0, rstd = 1)
   float st_sum, st_sq;    // statistics of the values this thread wrote (rs_out)
-  const float2* tab;      // smem: (s_n, b'_n) of the tile's columns (mode 2)
+  uint32_t tab;           // shared-window address of the tile's column table: float2 (s_n, b_n) per accumulator column
+                          // (LayerNorm fold: (s_n, b'_n); plain bias: (0, bias_n)); 0 = no table
 };
+// Everything here is independent of the accumulator: the callers run it BEFORE they wait for the tile's MMAs, so the
+// L2 round trips of the statistics overlap the mainloop instead of sitting between "accumulator ready" and the first
+// store (profiles/r02_epilogue.md: 18 % of the LayerNorm-fold kernel's stall samples were on this loop).
 DEVI void rowctx_begin(RowCtx& rc, const GemmParams& p, int row, bool row_ok) {
   rc.mu = 0.f;
   rc.rstd = 1.f;
   rc.st_sum = 0.f;
   rc.st_sq = 0.f;
+  rc.tab = 0u;
   if (p.norm_mode != 0 && row_ok) {
-    // fixed-order sum of the per-slot partial statistics of this row (written by the producing GEMM)
+    // fixed-order sum of the per-slot partial statistics of this row (written by the producing GEMM).  ALL loads of a
+    // row go out before the first addition (one L2 round trip, ~1.8k cycles under TMA load, instead of one per batch);
+    // the additions keep the slot order.  16 float4 = 64 floats cover K <= 4096 (RMS) / 2048 (LayerNorm) in one pass.
     const float4* sp = reinterpret_cast<const float4*>(p.rs_in + (long long)row * p.rs_in_stride);
+    const int n4 = p.rs_in_stride >> 2;
     float s0 = 0.f, s1 = 0.f;
-    for (int i = 0; i < (p.rs_in_stride >> 2); ++i) {
-      const float4 f = __ldcg(sp + i);
-      if (p.norm_mode == 1) {
-        s1 += (f.x + f.y) + (f.z + f.w);
-      } else {
-        s0 += f.x + f.z;
-        s1 += f.y + f.w;
+    for (int i = 0; i < n4; i += 16) {
+      float4 f[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) f[u] = (i + u < n4) ? __ldcg(sp + i + u) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        if (p.norm_mode == 1) {
+          s1 += (f[u].x + f[u].y) + (f[u].z + f[u].w);
+        } else {
+          s0 += f[u].x + f[u].z;
+          s1 += f[u].y + f[u].w;
+        }
       }
     }
     if (p.norm_mode == 1) {
@@ -230,6 +243,26 @@ DEVI void rowctx_begin(RowCtx& rc, const GemmParams& p, int row, bool row_ok) {
       rc.rstd = rsqrtf(fmaxf(s1 * p.norm_inv_k - rc.mu * rc.mu, 0.f) + p.norm_eps);
     }
   }
+}
+// Column table of one tile -> shared memory (one entry per accumulator column, `ncols` <= 256), by the 256 epilogue
+// threads; also called before the accumulator wait.  Double-buffered per accumulator stage by the callers: the
+// bar.sync below is the only synchronisation needed (a warp is at most one tile ahead of the slowest one).
+DEVI bool needs_col_table(const GemmParams& p) { return p.norm_mode == 2 || p.bias != nullptr; }
+// fetch: this thread's entry (global load issued, not yet consumed); commit: store + barrier.  The row-statistics
+// loads are issued between the two so that all of the tile's scattered L2 reads are in flight together.
+DEVI float2 col_table_fetch(const GemmParams& p, int col0, int ncols) {
+  const int t = threadIdx.x, col = col0 + t;
+  float2 v = make_float2(0.f, 0.f);
+  if (t < ncols && col < p.N) {
+    if (p.norm_mode == 2) v = __ldg(p.col_sb + col);
+    else v.y = __half2float(__ldg(p.bias + col));
+  }
+  return v;
+}
+DEVI void col_table_commit(RowCtx& rc, float2* tab, float2 v, int ncols) {
+  if ((int)threadIdx.x < ncols) tab[threadIdx.x] = v;
+  asm volatile("bar.sync 1, 256;" ::: "memory");
+  rc.tab = smem_u32(tab);
 }
 // `slot`: statistics slot of the columns this thread covered in this tile = 2 * (column tile) + (warp half): every
 // (tile, half) pair writes its own slot, whatever the tile width; the consumer sums ALL slots of the row in slot order.
@@ -245,53 +278,52 @@ DEVI void rowctx_end(const RowCtx& rc, const GemmParams& p, int row, bool row_ok
   }
 }
 
+// number of accumulator columns of a chunk handled by vector accesses: 32 (full chunk), 16 (half chunk: tiles whose width
+// is an odd multiple of 16) or 0 (ragged edge / inactive row: scalar path)
 template <int EPI>
-struct ChunkIn {
-  static constexpr int NC = (EPI == EPI_SWIGLU) ? 16 : 32;   // output columns per 32-column accumulator chunk
-  uint32_t r[32];
-  uint32_t bq[2][8];        // bias: 2 groups of 16 accumulator columns (32 bytes each)
-  uint32_t rq[NC / 16][8];  // residual: groups of 16 output columns
-  int nvec;                 // accumulator columns of this chunk handled by vector accesses: 32, 16 or 0 (scalar path)
-  bool bias_vec, res_vec;
-};
+DEVI int chunk_nvec(bool active, int valid) {
+  int n = !active ? 0 : (valid >= 32 ? 32 : (valid == 16 ? 16 : 0));
+  if (EPI == EPI_SWIGLU && n == 16) n = 0;   // 8 outputs: not worth a vector variant
+  return n;
+}
 
-// `col_end`: first accumulator column (global index) that does NOT belong to this tile / matrix.  A chunk is either
-// full (32 valid columns), a half chunk (exactly 16: tiles whose width is an odd multiple of 16) or ragged (scalar).
+// residual values of one chunk, requested one chunk AHEAD of their use (the first chunk's before the accumulator wait)
 template <int EPI>
-DEVI void chunk_issue(ChunkIn<EPI>& in, const GemmParams& p, uint32_t taddr, int row, bool row_ok, int col0, int col_end) {
-  constexpr int NC = ChunkIn<EPI>::NC;
+struct ResIn {
+  static constexpr int NC = (EPI == EPI_SWIGLU) ? 16 : 32;   // output columns per 32-column accumulator chunk
+  uint32_t q[NC / 16][8];   // groups of 16 output columns
+  bool vec;
+};
+// `col_end`: first accumulator column (global index) that does NOT belong to this tile / matrix
+template <int EPI>
+DEVI void res_issue(ResIn<EPI>& ri, const GemmParams& p, int row, bool row_ok, int col0, int col_end) {
+  constexpr int NC = ResIn<EPI>::NC;
+  ri.vec = false;
+  if (p.residual == nullptr) return;
+  const int nvec = chunk_nvec<EPI>(row_ok && col0 < col_end, col_end - col0);
   const int ocol0 = (EPI == EPI_SWIGLU) ? (col0 >> 1) : col0;
-  const bool active = row_ok && col0 < col_end;
-  tmem_ld_32x32b_x32(taddr, in.r);
-  const int valid = col_end - col0;
-  in.nvec = !active ? 0 : (valid >= 32 ? 32 : (valid == 16 ? 16 : 0));
-  if (EPI == EPI_SWIGLU && in.nvec == 16) in.nvec = 0;   // 8 outputs: not worth a vector variant
-  in.bias_vec = in.nvec > 0 && p.bias != nullptr && ((reinterpret_cast<uintptr_t>(p.bias + col0) & 31) == 0);
-  const __half* rp = active && p.residual != nullptr ? p.residual + (long long)row * p.ldr + ocol0 : nullptr;
-  in.res_vec = rp != nullptr && in.nvec > 0 && ((reinterpret_cast<uintptr_t>(rp) & 31) == 0);
-  if (in.bias_vec) {
-#pragma unroll
-    for (int g = 0; g < 2; ++g)
-      if (g * 16 < in.nvec) ldg_nc_v8(p.bias + col0 + g * 16, in.bq[g]);
-  }
-  if (in.res_vec) {
+  const __half* rp = p.residual + (long long)row * p.ldr + ocol0;
+  ri.vec = nvec > 0 && ((reinterpret_cast<uintptr_t>(rp) & 31) == 0);
+  if (ri.vec) {
 #pragma unroll
     for (int g = 0; g < NC / 16; ++g)
-      if (g * 16 * (32 / NC) < in.nvec) ldg_nc_v8(rp + g * 16, in.rq[g]);
+      if (g * 16 * (32 / NC) < nvec) ldg_nc_v8(rp + g * 16, ri.q[g]);
   }
 }
 
 template <int EPI>
-DEVI void chunk_finish(const ChunkIn<EPI>& in, const GemmParams& p, RowCtx& rc, int row, bool row_ok, int col0, int col_end,
-                       const float* part0, int n_parts, long long part_stride, int chunk_global, int row_in_slot) {
-  constexpr int NC = ChunkIn<EPI>::NC;
+DEVI void chunk_finish(const uint32_t (&r)[32], const ResIn<EPI>& ri, const GemmParams& p, RowCtx& rc, int row, bool row_ok,
+                       int col0, int col_end, const float* part0, int n_parts, long long part_stride, int chunk_global,
+                       int row_in_slot) {
+  constexpr int NC = ResIn<EPI>::NC;
   const int ocol0 = (EPI == EPI_SWIGLU) ? (col0 >> 1) : col0;
   const int ocol_end = (EPI == EPI_SWIGLU) ? (col_end >> 1) : col_end;
   if (!(row_ok && col0 < col_end)) return;
-  const int nvec_out = (EPI == EPI_SWIGLU) ? (in.nvec >> 1) : in.nvec;   // output columns written by vector stores
+  const int nvec = chunk_nvec<EPI>(true, col_end - col0);
+  const int nvec_out = (EPI == EPI_SWIGLU) ? (nvec >> 1) : nvec;   // output columns written by vector stores
   float v[32];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(in.r[j]);
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
   if (part0 != nullptr) {
     for (int pi = 0; pi < n_parts; ++pi) {   // stream-K: partial accumulators of the later k-ranges of this tile
 #pragma unroll
@@ -304,36 +336,29 @@ DEVI void chunk_finish(const ChunkIn<EPI>& in, const GemmParams& p, RowCtx& rc, 
       }
     }
   }
-  if (p.norm_mode == 1) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] *= rc.rstd;
-  } else if (p.norm_mode == 2) {
-    const float4* t4 = reinterpret_cast<const float4*>(rc.tab + chunk_global * 32);   // broadcast LDS.128: 2 columns
+  // folded norm and bias: one broadcast LDS.128 per two columns; entries beyond N are zero
+  if (p.norm_mode == 2) {
+    const uint32_t ta = rc.tab + (uint32_t)chunk_global * 256u;
     const float nmu = -rc.mu;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      const float4 sb = t4[j];
+      const float4 sb = lds_f4(ta + 16u * j);
       v[2 * j] = fmaf(rc.rstd, fmaf(nmu, sb.x, v[2 * j]), sb.y);
       v[2 * j + 1] = fmaf(rc.rstd, fmaf(nmu, sb.z, v[2 * j + 1]), sb.w);
     }
-  }
-  if (p.bias != nullptr) {
-    if (in.bias_vec) {
+  } else {
+    if (p.norm_mode == 1) {
 #pragma unroll
-      for (int g = 0; g < 2; ++g) {
-        if (g * 16 < in.nvec) {
+      for (int j = 0; j < 32; ++j) v[j] *= rc.rstd;
+    }
+    if (rc.tab != 0u) {
+      const uint32_t ta = rc.tab + (uint32_t)chunk_global * 256u;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&in.bq[g][j]));
-            v[g * 16 + 2 * j] += f.x;
-            v[g * 16 + 2 * j + 1] += f.y;
-          }
-        }
+      for (int j = 0; j < 16; ++j) {
+        const float4 sb = lds_f4(ta + 16u * j);
+        v[2 * j] += sb.y;
+        v[2 * j + 1] += sb.w;
       }
-    } else {
-#pragma unroll
-      for (int j = 0; j < 32; ++j)
-        if (col0 + j < col_end) v[j] += __half2float(p.bias[col0 + j]);
     }
   }
   if (EPI == EPI_GELU) {
@@ -351,13 +376,13 @@ DEVI void chunk_finish(const ChunkIn<EPI>& in, const GemmParams& p, RowCtx& rc, 
   }
   if (p.residual != nullptr) {
     const __half* rp = p.residual + (long long)row * p.ldr + ocol0;
-    if (in.res_vec) {
+    if (ri.vec) {
 #pragma unroll
       for (int g = 0; g < NC / 16; ++g) {
         if (g * 16 < nvec_out) {
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&in.rq[g][j]));
+            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&ri.q[g][j]));
             v[g * 16 + 2 * j] += f.x;
             v[g * 16 + 2 * j + 1] += f.y;
           }
@@ -430,10 +455,11 @@ DEVI void dump_store(const uint32_t (&r)[32], float* slot, int chunk_global, int
 //   head of a split tile            -> wait for the contributors' flags, add their partials, fused epilogue
 //   whole tile                      -> fused epilogue
 // `slot_stride_ctas`: distance in CTA slots between consecutive contributors (1 one-CTA, 2 CTA-pair).
+// `res0`: residual values of chunk c_begin, requested by the caller before it waited for the accumulator.
 template <int EPI>
 DEVI void epilogue_segment(const GemmParams& p, RowCtx& rc, uint32_t t_acc, int c_begin, int c_end, int row, bool row_ok,
                            int row_in_slot, int tile_col0, int col_end, bool is_tail, int n_parts,
-                           int slot_stride_ctas, int lane) {
+                           int slot_stride_ctas, int lane, const ResIn<EPI>& res0) {
   if (is_tail) {
     float* slot = p.sk_ws + (long long)blockIdx.x * SLOT_ELEMS;
 #pragma unroll 1
@@ -470,15 +496,20 @@ DEVI void epilogue_segment(const GemmParams& p, RowCtx& rc, uint32_t t_acc, int 
   }
   const float* part0 = n_parts > 0 ? p.sk_ws + (long long)(blockIdx.x + slot_stride_ctas) * SLOT_ELEMS : nullptr;
   const long long pstride = (long long)slot_stride_ctas * SLOT_ELEMS;
-  // one 32-column chunk at a time (a 2-deep software pipeline was measured SLOWER: it needs > 168 registers/thread,
-  // the cap at 320 threads/CTA, and spills; profiles/r01_gemm_ab.md)
+  // one 32-column accumulator chunk at a time (two TMEM chunks in flight need > 168 registers/thread, the cap at 320
+  // threads/CTA, and spill; profiles/r01_gemm_ab.md); the residual of chunk c+1 is requested before chunk c is finished
+  ResIn<EPI> rcur = res0;
 #pragma unroll 1
   for (int c = c_begin; c < c_end; ++c) {
     __syncwarp();
-    ChunkIn<EPI> a;
-    chunk_issue<EPI>(a, p, t_acc + 32 * c, row, row_ok, tile_col0 + 32 * c, col_end);
+    uint32_t ra[32];
+    tmem_ld_32x32b_x32(t_acc + 32 * c, ra);
+    ResIn<EPI> rnxt;
+    rnxt.vec = false;
+    if (c + 1 < c_end) res_issue<EPI>(rnxt, p, row, row_ok, tile_col0 + 32 * (c + 1), col_end);
     tmem_ld_wait();
-    chunk_finish<EPI>(a, p, rc, row, row_ok, tile_col0 + 32 * c, col_end, part0, n_parts, pstride, c, row_in_slot);
+    chunk_finish<EPI>(ra, rcur, p, rc, row, row_ok, tile_col0 + 32 * c, col_end, part0, n_parts, pstride, c, row_in_slot);
+    rcur = rnxt;
   }
   __syncwarp();
   if (n_parts > 0 && lane == 0) {
@@ -510,15 +541,27 @@ DEVI float ldg_half_if(const __half* ptr, bool pred) {
   return __half2float(__ushort_as_half(raw));
 }
 
+// `fsb` = (s_f, b_f) of this thread's feature (LayerNorm fold: (s_n, b'_n); otherwise (0, bias)); `tok_tab`: shared-window
+// address of the (mu, rstd) pairs of this chunk's 32 tokens (folded norm), 0 = none.
 template <int EPI>
-DEVI void chunk_swap(const GemmParams& p, uint32_t taddr, int f, float bias, int tok0, int tok_end, int lane) {
+DEVI void chunk_swap(const GemmParams& p, uint32_t taddr, int f, float2 fsb, uint32_t tok_tab, int tok0, int tok_end, int lane) {
   uint32_t r[32];
   tmem_ld_32x32b_x32(taddr, r);
   tmem_ld_wait();
   float v[32];
+  if (tok_tab != 0u) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const float4 t2 = lds_f4(tok_tab + 16u * j);   // (mu, rstd) of tokens 2j, 2j+1: broadcast
+      v[2 * j] = fmaf(t2.y, fmaf(-t2.x, fsb.x, __uint_as_float(r[2 * j])), fsb.y);
+      v[2 * j + 1] = fmaf(t2.w, fmaf(-t2.z, fsb.x, __uint_as_float(r[2 * j + 1])), fsb.y);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) + fsb.y;
+  }
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
-    v[j] = __uint_as_float(r[j]) + bias;
     if (EPI == EPI_GELU) v[j] = gelu_erf(v[j]);
     if (EPI == EPI_RELU) v[j] = fmaxf(v[j], 0.f);
   }
@@ -738,27 +781,29 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       const uint32_t t_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
       const bool split_head = (kb0 == 0 && kb1 < k_blocks);
       const int n_parts = split_head ? sk_contributors((int)blockIdx.x, (int)gridDim.x, tile, p.sk_tiles, k_blocks) : 0;
+      // accumulator-independent part first: row statistics, column table, residual of the first chunk
+      RowCtx rc;
+      const int col_end = min(p.N, (n_blk + 1) * BN);
+      const bool use_tab = kb0 == 0 && needs_col_table(p);
+      float2 tab_v = make_float2(0.f, 0.f);
+      if (use_tab) tab_v = col_table_fetch(p, n_blk * BN, BN);
+      ResIn<EPI> res0;
+      res0.vec = false;
+      if (kb0 == 0) res_issue<EPI>(res0, p, row, row < p.M, n_blk * BN + 32 * half_idx * CHUNKS_PER_WARP, col_end);
+      rowctx_begin(rc, p, row, row < p.M);
+      if (use_tab) col_table_commit(rc, reinterpret_cast<float2*>(smem + L::TAB_OFFSET) + acc * 256, tab_v, BN);
       {
         const long long w = mbar_wait(&tmem_full_bar[acc], acc_phase);
         if (warp == 0 && lane == 0) atomicAdd(&g_gemm_prof[3], (unsigned long long)w);
       }
       tc_fence_after();
-      RowCtx rc;
-      rowctx_begin(rc, p, row, row < p.M);
-      if (p.norm_mode == 2) {   // (s, b') of this tile's columns -> smem table of this accumulator stage
-        float2* tab = reinterpret_cast<float2*>(smem + L::TAB_OFFSET) + acc * 256;
-        const int t = threadIdx.x, col = n_blk * BN + t;
-        if (t < BN) tab[t] = col < p.N ? __ldg(p.col_sb + col) : make_float2(0.f, 0.f);
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        rc.tab = tab;
-      }
       epilogue_segment<EPI>(p, rc, t_acc, half_idx * CHUNKS_PER_WARP, (half_idx + 1) * CHUNKS_PER_WARP, row, row < p.M,
-                            row_in_tile, n_blk * BN, min(p.N, (n_blk + 1) * BN), kb0 > 0, n_parts, 1, lane);
+                            row_in_tile, n_blk * BN, col_end, kb0 > 0, n_parts, 1, lane, res0);
       if (kb0 == 0) rowctx_end(rc, p, row, row < p.M, n_blk * 2 + half_idx);
       // all TMEM reads of this warp for this segment are done -> release the accumulator stage
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (lane == 0) mbar_arrive_relaxed(&tmem_empty_bar[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -984,6 +1029,38 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
       const uint32_t t_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN2_MAX);
       const bool split_head = (kb0 == 0 && kb1 < k_blocks);
       const int n_parts = split_head ? sk_contributors(cluster_id, num_clusters, tile, p.sk_tiles, k_blocks) : 0;
+      // accumulator-independent part first: row statistics, column table, residual of the first chunk
+      RowCtx rc;
+      ResIn<EPI> res0;
+      res0.vec = false;
+      const int col_end = min(p.N, (b_blk + 1) * bn);
+      float2 fsb = make_float2(0.f, 0.f);   // SWAP: (s_f, b_f) of this thread's feature
+      uint32_t tok_tab = 0u;               // SWAP + folded norm: (mu, rstd) of the tile's tokens, in shared memory
+      if (SWAP) {
+        // lanes = features: one (s, b) pair per thread; columns = tokens: the per-token statistics of a folded norm go
+        // through a shared table, one token per thread (bn <= 256 tokens per tile)
+        if (p.norm_mode == 2) {
+          if (row < p.N) fsb = __ldg(p.col_sb + row);
+        } else {
+          fsb.y = ldg_half_if(p.bias + row, p.bias != nullptr && row < p.N);
+        }
+        if (p.norm_mode != 0 && kb0 == 0) {
+          const int t = threadIdx.x, tok = b_blk * bn + t;
+          RowCtx tc;
+          rowctx_begin(tc, p, tok, t < bn && tok < p.M);
+          float2* tab = reinterpret_cast<float2*>(smem + L::TAB_OFFSET) + acc * 256;
+          if (t < bn) tab[t] = make_float2(tc.mu, tc.rstd);
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+          tok_tab = smem_u32(tab);
+        }
+      } else {
+        const bool use_tab = kb0 == 0 && needs_col_table(p);
+        float2 tab_v = make_float2(0.f, 0.f);
+        if (use_tab) tab_v = col_table_fetch(p, b_blk * bn, bn);
+        if (kb0 == 0) res_issue<EPI>(res0, p, row, row < p.M, b_blk * bn + 32 * c_begin, col_end);
+        rowctx_begin(rc, p, row, row < p.M);
+        if (use_tab) col_table_commit(rc, reinterpret_cast<float2*>(smem + L::TAB_OFFSET) + acc * 256, tab_v, bn);
+      }
       {
         const long long w = mbar_wait(&tmem_full_bar[acc], acc_phase);
         if (warp == 0 && lane == 0) atomicAdd(&g_gemm_prof[3], (unsigned long long)w);
@@ -992,30 +1069,20 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
       if (SWAP) {
         // lanes = features (rows of W), columns = tokens (rows of A)
         const int tok_end = min(p.M, (b_blk + 1) * bn);
-        const float bias = ldg_half_if(p.bias + row, p.bias != nullptr && row < p.N);   // one feature per thread
 #pragma unroll 1
         for (int c = c_begin; c < c_end; ++c) {
           __syncwarp();
-          chunk_swap<EPI>(p, t_acc + 32 * c, row, bias, b_blk * bn + 32 * c, tok_end, lane);
+          chunk_swap<EPI>(p, t_acc + 32 * c, row, fsb, tok_tab != 0u ? tok_tab + 256u * c : 0u, b_blk * bn + 32 * c, tok_end, lane);
         }
       } else {
         // contributors of this CTA's 128 rows are the same-rank CTAs of the following clusters: slot stride 2
-        RowCtx rc;
-        rowctx_begin(rc, p, row, row < p.M);
-        if (p.norm_mode == 2) {   // (s, b') of this tile's columns -> smem table of this accumulator stage
-          float2* tab = reinterpret_cast<float2*>(smem + L::TAB_OFFSET) + acc * 256;
-          const int t = threadIdx.x, col = b_blk * bn + t;
-          if (t < bn) tab[t] = col < p.N ? __ldg(p.col_sb + col) : make_float2(0.f, 0.f);
-          asm volatile("bar.sync 1, 256;" ::: "memory");
-          rc.tab = tab;
-        }
-        epilogue_segment<EPI>(p, rc, t_acc, c_begin, c_end, row, row < p.M, row_in_slot, b_blk * bn,
-                              min(p.N, (b_blk + 1) * bn), kb0 > 0, n_parts, 2, lane);
+        epilogue_segment<EPI>(p, rc, t_acc, c_begin, c_end, row, row < p.M, row_in_slot, b_blk * bn, col_end, kb0 > 0,
+                              n_parts, 2, lane, res0);
         if (kb0 == 0) rowctx_end(rc, p, row, row < p.M, b_blk * 2 + half_idx);
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(acc == 0 ? leader_empty0 : leader_empty1);  // leader's barrier
+      if (lane == 0) mbar_arrive_cluster_relaxed(acc == 0 ? leader_empty0 : leader_empty1);  // leader's barrier
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       ++n_done;
     }
@@ -1387,9 +1454,8 @@ int gemm_impl(const void* A, long long lda, const void* W, long long ldw, void* 
   }
   int allow_sk = 1;
   if (code & 1) { allow_sk = 0; code -= 1; }
-  const bool fused_rows = na.norm_mode != 0 || na.rs_out != nullptr;   // per-row epilogue state: lanes must be tokens
   GemmPlan pl;
-  if (code == 0) pl = plan_gemm(M, N, K, epilogue, !fused_rows, na.rs_out != nullptr);
+  if (code == 0) pl = plan_gemm(M, N, K, epilogue, na.rs_out == nullptr, na.rs_out != nullptr);
   else if (code == 64 || code == 128 || code == 256) pl = GemmPlan{0, code, 0};
   else if (code == 512) pl = GemmPlan{1, 256, 0};
   else if (code > 1024 && code <= 1024 + 256) pl = GemmPlan{1, code - 1024, 0};
@@ -1397,7 +1463,9 @@ int gemm_impl(const void* A, long long lda, const void* W, long long ldw, void* 
   else { stllm_set_last_error("stllm_gemm_f16: unknown tile_n code %d", tile_n); return STLLM_ERR_BAD_ARG; }
   STLLM_CHECK_ARG(pl.bn >= 16 && pl.bn <= 256 && pl.bn % 16 == 0);
   const bool swap = pl.engine == 2;
-  STLLM_CHECK_ARG(!(swap && fused_rows));
+  // a folded norm works in both orientations (per-token statistics through a shared table when swapped); the per-row
+  // statistics OUTPUT needs the token on the TMEM lane
+  STLLM_CHECK_ARG(!(swap && na.rs_out != nullptr));
   // statistics slots: 2 per column tile (one per warp half)
   STLLM_CHECK_ARG(na.rs_out == nullptr || na.rs_out_stride >= na.rs_out_mode * 2 * ((N + pl.bn - 1) / pl.bn));
   // lane operand (128-row boxes) and column operand (bn or bn/2-row boxes)
