@@ -74,6 +74,12 @@ DEVI uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug must trap (-> CUDA error on the host) instead of hanging the GPU.
 // Returns the number of cycles spent waiting (0 if the phase had already completed).
+// hot-loop form: no clock reads, no timeout trap (the MMA issuer shares its scheduler with two epilogue warps; every
+// instruction of its k-block loop delays the next tcgen05.mma when those warps are busy)
+DEVI void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
 // returns the cycles spent waiting INCLUDING the first try: mbarrier.try_wait suspends the thread in hardware for a
 // while before it reports failure, so a count that starts after the first failed try misses most of a short wait
 DEVI long long mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -158,6 +164,12 @@ DEVI uint64_t make_sdesc_k_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// the same descriptor split into its address-dependent low word and its constant high word: the MMA issuers keep the
+// low word of the current pipeline stage in a register and add constants per operand / k-step
+DEVI uint32_t sdesc_lo_k_sw128(uint32_t smem_addr) { return ((smem_addr & 0x3FFFFu) >> 4) | (1u << 16); }
+constexpr uint32_t SDESC_HI_K_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);
+DEVI uint64_t sdesc_join(uint32_t lo) { return ((uint64_t)SDESC_HI_K_SW128 << 32) | (uint64_t)lo; }
+
 // Instruction descriptor for kind::f16: fp16 A/B (K-major both), fp32 D.
 // Bit layout: cute::UMMA::InstrDescriptor (c_format [4,6) | a_format [7,10) | b_format [10,13) |
 // a_major 15 | b_major 16 | N>>3 [17,23) | M>>4 [24,29)).
@@ -177,6 +189,16 @@ DEVI void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[32]) {
         "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
         "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
         "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+// 32 lanes x 16 columns: the unit of the 16-warp epilogue (half the registers of an x32 load)
+DEVI void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
       : "r"(taddr)
       : "memory");
 }

@@ -52,6 +52,7 @@ struct GemmParams {
   int out_f32;    // 0: fp16 output, 1: fp32 output
   int bn;         // CTA-pair engine: accumulator columns per tile (multiple of 16, <= 256), chosen per shape
   int w_prefetch; // 1: the weight operand is static -> its first stages are loaded BEFORE griddepcontrol.wait
+  int prof;       // debug: 1 -> the roles time their mbarrier waits into g_gemm_prof (STLLM_GEMM_PROF=1); 0: lean loops
   int trace;      // debug: 1 + slot (0..3) -> per-CTA phase timestamps into g_gemm_trace[slot] (CTA-pair engine)
   // --- normalisation folded into the GEMM (removes the standalone LayerNorm / RMSNorm launches) ---
   //   consumer side: A holds the UN-normalised rows x, W holds gamma-scaled weights W' = gamma (.) W, and
@@ -706,7 +707,8 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     while (it.next(tile, kb0, kb1)) {
       const int m_blk = tile % p.m_tiles, n_blk = tile / p.m_tiles;
       for (int kb = kb0; kb < kb1; ++kb, ++issued) {
-        w_acc += mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (p.prof) w_acc += mbar_wait(&empty_bar[stage], phase ^ 1);
+        else mbar_wait_spin(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * L::STAGE_BYTES;
         uint8_t* sb = sa + L::A_BYTES;
         if (elect_one()) {
@@ -720,7 +722,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
-    if (lane == 0) atomicAdd(&g_gemm_prof[0], (unsigned long long)w_acc);
+    if (p.prof && lane == 0) atomicAdd(&g_gemm_prof[0], (unsigned long long)w_acc);
   } else if (warp == WARP_MMA) {
     // ===================== MMA issuer =====================
     // Warp-uniform loop, one elected lane issues tcgen05.mma / tcgen05.commit straight from uniform registers: a k-block of
@@ -730,34 +732,38 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
     uint32_t phase = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    // The k-block loop is kept lean (no clock reads or timeout traps unless profiling, descriptors by addition): this
+    // warp shares its scheduler with two epilogue warps, and every instruction here delays the next tcgen05.mma.
     long long w_full = 0, w_acc = 0;
-    const long long t_start = clock64();
+    const bool prof = p.prof != 0;
+    const long long t_start = prof ? clock64() : 0;
+    const uint32_t lo0 = sdesc_lo_k_sw128(smem_u32(smem));   // descriptor low word of stage 0's A tile
+    uint32_t lo = lo0;
     while (it.next(tile, kb0, kb1)) {
-      w_acc += mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+      if (prof) w_acc += mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+      else mbar_wait_spin(&tmem_empty_bar[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
       for (int kb = kb0; kb < kb1; ++kb) {
-        w_full += mbar_wait(&full_bar[stage], phase);
+        if (prof) w_full += mbar_wait(&full_bar[stage], phase);
+        else mbar_wait_spin(&full_bar[stage], phase);
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
-        const uint32_t sb = sa + L::A_BYTES;
         if (elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < BK / 16; ++kk) {
-            const uint64_t da = make_sdesc_k_sw128(sa + kk * 32);
-            const uint64_t db = make_sdesc_k_sw128(sb + kk * 32);
-            umma_f16_ss(d_tmem, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
-          }
+          for (int kk = 0; kk < BK / 16; ++kk)   // +2 per k-step of 16 elements (32 bytes >> 4)
+            umma_f16_ss(d_tmem, sdesc_join(lo + 2 * kk), sdesc_join(lo + (L::A_BYTES >> 4) + 2 * kk), idesc,
+                        (kb > kb0 || kk > 0) ? 1u : 0u);
           umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
         }
         __syncwarp();
-        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        lo += L::STAGE_BYTES >> 4;
+        if (++stage == STAGES) { stage = 0; phase ^= 1; lo = lo0; }
       }
       if (elect_one()) umma_commit(&tmem_full_bar[acc]);  // accumulator complete -> epilogue
       __syncwarp();
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (lane == 0) {
+    if (prof && lane == 0) {
       atomicAdd(&g_gemm_prof[1], (unsigned long long)w_full);
       atomicAdd(&g_gemm_prof[2], (unsigned long long)w_acc);
       if (blockIdx.x == 0) {
@@ -794,7 +800,7 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       if (use_tab) col_table_commit(rc, reinterpret_cast<float2*>(smem + L::TAB_OFFSET) + acc * 256, tab_v, BN);
       {
         const long long w = mbar_wait(&tmem_full_bar[acc], acc_phase);
-        if (warp == 0 && lane == 0) atomicAdd(&g_gemm_prof[3], (unsigned long long)w);
+        if (p.prof && warp == 0 && lane == 0) atomicAdd(&g_gemm_prof[3], (unsigned long long)w);
       }
       tc_fence_after();
       epilogue_segment<EPI>(p, rc, t_acc, half_idx * CHUNKS_PER_WARP, (half_idx + 1) * CHUNKS_PER_WARP, row, row < p.M,
@@ -933,7 +939,8 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
       const int row_a = a_blk * 256 + (int)cta_rank * 128;
       const int row_b = b_blk * bn + (int)cta_rank * (bn / 2);
       for (int kb = kb0; kb < kb1; ++kb, ++issued) {
-        w_acc += mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (p.prof) w_acc += mbar_wait(&empty_bar[stage], phase ^ 1);
+        else mbar_wait_spin(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * L::STAGE_BYTES;
         uint8_t* sb = sa + L::A_BYTES;
         const bool pre = issued < n_pre;   // weight tile of this k-block already requested
@@ -946,7 +953,7 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
         if (++stage == STAGES2) { stage = 0; phase ^= 1; }
       }
     }
-    if (lane == 0) atomicAdd(&g_gemm_prof[0], (unsigned long long)w_acc);
+    if (p.prof && lane == 0) atomicAdd(&g_gemm_prof[0], (unsigned long long)w_acc);
   } else if (warp == WARP_MMA) {
     // ===================== MMA issuer (leader CTA only) =====================
     // warp-uniform loop; the elected lane issues tcgen05.mma.cta_group::2 / multicast commits from uniform registers
@@ -957,35 +964,40 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
       int acc = 0;
       uint32_t acc_phase = 0;
       long long w_full = 0, w_acc = 0;
-      const long long t_start = clock64();
+      const bool prof = p.prof != 0 || p.trace != 0;
+      const long long t_start = prof ? clock64() : 0;
       bool first = true;
       long long c_first = 0, w_full_first = 0;
+      const uint32_t lo0 = sdesc_lo_k_sw128(smem_u32(smem));   // descriptor low word of stage 0's lane-operand tile
+      uint32_t lo = lo0;
       while (it.next(tile, kb0, kb1)) {
-        w_acc += mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        if (prof) w_acc += mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        else mbar_wait_spin(&tmem_empty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN2_MAX);
         for (int kb = kb0; kb < kb1; ++kb) {
-          w_full += mbar_wait(&full_bar[stage], phase);
-          if (first) {
-            if (lane == 0) TRACE(3);
-            first = false;
-            c_first = clock64();
-            w_full_first = w_full;
+          if (prof) {
+            w_full += mbar_wait(&full_bar[stage], phase);
+            if (first) {
+              if (lane == 0) TRACE(3);
+              first = false;
+              c_first = clock64();
+              w_full_first = w_full;
+            }
+          } else {
+            mbar_wait_spin(&full_bar[stage], phase);
           }
           tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
-          const uint32_t sb = sa + L::A_BYTES;
           if (elect_one()) {
 #pragma unroll
-            for (int kk = 0; kk < BK / 16; ++kk) {
-              const uint64_t da = make_sdesc_k_sw128(sa + kk * 32);
-              const uint64_t db = make_sdesc_k_sw128(sb + kk * 32);
-              umma_f16_ss_2sm(d_tmem, da, db, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
-            }
+            for (int kk = 0; kk < BK / 16; ++kk)   // +2 per k-step of 16 elements (32 bytes >> 4)
+              umma_f16_ss_2sm(d_tmem, sdesc_join(lo + 2 * kk), sdesc_join(lo + (L::A_BYTES >> 4) + 2 * kk), idesc,
+                              (kb > kb0 || kk > 0) ? 1u : 0u);
             umma_commit_2sm(&empty_bar[stage], 3);   // frees this smem slot in BOTH CTAs
           }
           __syncwarp();
-          if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+          lo += L::STAGE_BYTES >> 4;
+          if (++stage == STAGES2) { stage = 0; phase ^= 1; lo = lo0; }
         }
         if (elect_one()) umma_commit_2sm(&tmem_full_bar[acc], 3);   // accumulators of both CTAs complete
         __syncwarp();
@@ -998,11 +1010,13 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
           g_gemm_trace[p.trace - 1][blockIdx.x][9] = (unsigned long long)(w_full - w_full_first);
           g_gemm_trace[p.trace - 1][blockIdx.x][10] = (unsigned long long)w_acc;
         }
-        atomicAdd(&g_gemm_prof[1], (unsigned long long)w_full);
-        atomicAdd(&g_gemm_prof[2], (unsigned long long)w_acc);
-        if (blockIdx.x == 0) {
-          atomicAdd(&g_gemm_prof[4], (unsigned long long)(clock64() - t_start));
-          atomicAdd(&g_gemm_prof[5], 1ull);
+        if (p.prof) {
+          atomicAdd(&g_gemm_prof[1], (unsigned long long)w_full);
+          atomicAdd(&g_gemm_prof[2], (unsigned long long)w_acc);
+          if (blockIdx.x == 0) {
+            atomicAdd(&g_gemm_prof[4], (unsigned long long)(clock64() - t_start));
+            atomicAdd(&g_gemm_prof[5], 1ull);
+          }
         }
       }
     }
@@ -1063,7 +1077,7 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
       }
       {
         const long long w = mbar_wait(&tmem_full_bar[acc], acc_phase);
-        if (warp == 0 && lane == 0) atomicAdd(&g_gemm_prof[3], (unsigned long long)w);
+        if (p.prof && warp == 0 && lane == 0) atomicAdd(&g_gemm_prof[3], (unsigned long long)w);
       }
       tc_fence_after();
       if (SWAP) {
@@ -1490,6 +1504,8 @@ int gemm_impl(const void* A, long long lda, const void* W, long long ldw, void* 
   static const int w_prefetch = env_int("STLLM_GEMM_WPREFETCH", 1);
   p.w_prefetch = w_prefetch;
   p.trace = g_trace_on ? 1 + (g_trace_launch++ & 3) : 0;
+  static const int prof_on = env_int("STLLM_GEMM_PROF", 0);
+  p.prof = prof_on;
   p.norm_mode = na.norm_mode;
   p.rs_in = na.rs_in;
   p.col_sb = na.col_sb;
