@@ -542,7 +542,8 @@ def multi_gpu_legs(model, args, dev, rank, world):
                                         f"does not shard, cap ~1.9x")
     except Exception as e:
         out["config4_error"] = f"{type(e).__name__}: {e}"[:300]
-    if world == 8 and os.environ.get("STLLM_BENCH_SWEEP", "1") != "0":
+    # STLLM_BENCH_SWEEP: "0" = never, "force" = at any world size (used to exercise the leg on 2 GPUs), default: 8 GPUs only
+    if (world == 8 or os.environ.get("STLLM_BENCH_SWEEP") == "force") and os.environ.get("STLLM_BENCH_SWEEP", "1") != "0":
         try:
             pts = []
             gbuf = {}

@@ -441,19 +441,59 @@ DEVI void pin_loaded(uint4& a, uint4& b) {
   asm volatile("" : "+r"(a.x), "+r"(a.y), "+r"(a.z), "+r"(a.w), "+r"(b.x), "+r"(b.y), "+r"(b.z), "+r"(b.w));
 }
 
+// ---- CUDA-core path for the <= TAIL_MAX query rows after the last full 128-row tile (ViT: row 257 of 257) ----
+// One CTA per (head, batch).  The head's K and V ([Skv][DH] fp16, 2 x 45 KB for the ViT) are staged in shared memory with
+// one sweep of 16-byte cp.async copies (everything in flight at once: one L2 round trip instead of the ~30 dependent ones of
+// the first version, profiles/r02_attention.md), then q.K^T (thread = key), softmax, P.V ((key group, 8-feature chunk) per
+// thread) run out of shared memory.  Row stride = DH * 2 bytes when that is an odd number of 16-byte chunks (88 -> 11),
+// else one chunk of padding: the 8 threads of an LDS.128 phase then hit 8 different bank groups.
+template <int DH>
+struct TailCfg {
+  static constexpr int NCHUNK = DH / 8;                                   // 16-byte chunks per row
+  static constexpr int RS = (NCHUNK & 1) ? DH * 2 : DH * 2 + 16;          // row stride in bytes
+  __host__ __device__ static int smem_bytes(int Skv, int threads) {
+    const int kg = threads / NCHUNK;
+    return 2 * Skv * RS + (128 + ((Skv + 31) & ~31) + 64 + kg * DH) * 4 + 256;
+  }
+};
+DEVI void cp_async16_tail(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+DEVI uint4 lds_u4(uint32_t a) {
+  uint4 r;
+  asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
+  return r;
+}
+DEVI float lds_f1(uint32_t a) {
+  float r;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r) : "r"(a));
+  return r;
+}
+DEVI void sts_f1(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+
 template <int DH>
 __device__ __forceinline__ void attention_tail_rows(const AttnTcParams& p, uint8_t* smem, int h, int b) {
-  // CUDA-core path for the <= TAIL_MAX query rows after the last full tile.  Latency is what counts (a few hundred CTAs of a
-  // few microseconds each): every thread owns whole keys and requests ALL 16-byte pieces of a key row before it uses the
-  // first (11 loads in flight per key), P V is split over (key group, 8-feature chunk) with 8 loads in flight per thread.
-  constexpr int NCHUNK = DH / 8;                         // 11 (head dim 88) or 16
-  const int nt = (int)blockDim.x, nwarp = nt >> 5;
-  float* sq = reinterpret_cast<float*>(smem);            // [DH] the (pre-scaled, fp16-rounded) query row
-  float* sp = sq + 128;                                  // [Skv] probabilities (unnormalised)
-  float* red = sp + ((p.Skv + 31) & ~31);                // [2][32] reduction scratch
-  float* part = red + 64;                                // [KG][DH] partial outputs
+  constexpr int NCHUNK = TailCfg<DH>::NCHUNK, RS = TailCfg<DH>::RS;
+  const int nt = (int)blockDim.x, nwarp = nt >> 5, t = threadIdx.x;
   const int KG = nt / NCHUNK;                            // key groups of the P V phase
-  const int t = threadIdx.x;
+  // shared-window addresses (the aligned `smem` pointer is generic: explicit ld/st.shared keep ptxas from emitting LD.E)
+  const uint32_t s_k = smem_u32(smem);                   // [Skv][RS] keys
+  const uint32_t s_v = s_k + (uint32_t)(p.Skv * RS);     // [Skv][RS] values
+  const uint32_t s_q = s_v + (uint32_t)(p.Skv * RS);     // [128] floats: the (pre-scaled, fp16-rounded) query row
+  const uint32_t s_p = s_q + 128 * 4;                    // [Skv] probabilities (unnormalised)
+  const uint32_t s_red = s_p + (uint32_t)(((p.Skv + 31) & ~31) * 4);   // [2][32] reduction scratch
+  const uint32_t s_part = s_red + 64 * 4;                // [KG][DH] partial outputs
+  {
+    const char* kb = reinterpret_cast<const char*>(p.k + (long long)b * p.k_sb + (long long)h * DH);
+    const char* vb = reinterpret_cast<const char*>(p.v + (long long)b * p.v_sb + (long long)h * DH);
+    const long long kss = p.k_ss * 2, vss = p.v_ss * 2;
+    for (int i = t; i < p.Skv * NCHUNK; i += nt) {
+      const int key = i / NCHUNK, c = i - key * NCHUNK;
+      cp_async16_tail(s_k + (uint32_t)(key * RS + c * 16), kb + key * kss + c * 16);
+      cp_async16_tail(s_v + (uint32_t)(key * RS + c * 16), vb + key * vss + c * 16);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
   const float sl2 = p.scale * 1.4426950408889634f;
   const int row0 = (p.Sq / TQ) * TQ;
   for (int r = 0; r < p.n_tail; ++r) {
@@ -462,84 +502,74 @@ __device__ __forceinline__ void attention_tail_rows(const AttnTcParams& p, uint8
     if (t < DH) {
       float x = __half2float(qp[t]);
       if (p.q_prescale != 0.f) x = __half2float(__float2half_rn(x * p.q_prescale));
-      sq[t] = x;
+      sts_f1(s_q + 4 * t, x);
     }
+    if (r == 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
+    // ---- scores: thread = key ----
     float mx = -INFINITY;
     for (int key = t; key < p.Skv; key += nt) {
-      const uint4* kp = reinterpret_cast<const uint4*>(p.k + (long long)b * p.k_sb + (long long)key * p.k_ss + (long long)h * DH);
-      uint4 u[NCHUNK];
-#pragma unroll
-      for (int c = 0; c < NCHUNK; ++c) u[c] = ldg_nc_v4_volatile(kp + c);
-#pragma unroll
-      for (int c = 0; c + 1 < NCHUNK; c += 2) pin_loaded(u[c], u[c + 1]);
       float a0 = 0.f, a1 = 0.f;
 #pragma unroll
       for (int c = 0; c < NCHUNK; ++c) {
-        const __half2* hh = reinterpret_cast<const __half2*>(&u[c]);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const float2 f = __half22float2(hh[i]);
-          a0 = fmaf(sq[c * 8 + 2 * i], f.x, a0);
-          a1 = fmaf(sq[c * 8 + 2 * i + 1], f.y, a1);
-        }
+        const uint4 u = lds_u4(s_k + (uint32_t)(key * RS + c * 16));
+        const float4 qa = lds_f4(s_q + c * 32), qb = lds_f4(s_q + c * 32 + 16);   // broadcast
+        const __half2* hh = reinterpret_cast<const __half2*>(&u);
+        const float2 f0 = __half22float2(hh[0]), f1 = __half22float2(hh[1]), f2 = __half22float2(hh[2]), f3 = __half22float2(hh[3]);
+        a0 = fmaf(qa.x, f0.x, a0);
+        a1 = fmaf(qa.y, f0.y, a1);
+        a0 = fmaf(qa.z, f1.x, a0);
+        a1 = fmaf(qa.w, f1.y, a1);
+        a0 = fmaf(qb.x, f2.x, a0);
+        a1 = fmaf(qb.y, f2.y, a1);
+        a0 = fmaf(qb.z, f3.x, a0);
+        a1 = fmaf(qb.w, f3.y, a1);
       }
       const float acc = (a0 + a1) * sl2;
-      sp[key] = acc;
+      sts_f1(s_p + 4 * key, acc);
       mx = fmaxf(mx, acc);
     }
     mx = warp_max(mx);
-    if ((t & 31) == 0) red[t >> 5] = mx;
+    if ((t & 31) == 0) sts_f1(s_red + 4 * (t >> 5), mx);
     __syncthreads();
     mx = -INFINITY;
-    for (int w = 0; w < nwarp; ++w) mx = fmaxf(mx, red[w]);
+    for (int w = 0; w < nwarp; ++w) mx = fmaxf(mx, lds_f1(s_red + 4 * w));
     float sum = 0.f;
     for (int key = t; key < p.Skv; key += nt) {
-      const float e = exp2f(sp[key] - mx);
-      sp[key] = e;
+      const float e = exp2f(lds_f1(s_p + 4 * key) - mx);
+      sts_f1(s_p + 4 * key, e);
       sum += e;
     }
     sum = warp_sum(sum);
-    if ((t & 31) == 0) red[32 + (t >> 5)] = sum;
+    if ((t & 31) == 0) sts_f1(s_red + 4 * (32 + (t >> 5)), sum);
     __syncthreads();
     float total = 0.f;
-    for (int w = 0; w < nwarp; ++w) total += red[32 + w];
+    for (int w = 0; w < nwarp; ++w) total += lds_f1(s_red + 4 * (32 + w));
     const float inv = 1.f / total;
+    // ---- P V: thread = (key group, 8-feature chunk) ----
     if (t < KG * NCHUNK) {
-      const int kg = t / NCHUNK, c = t % NCHUNK;
+      const int kg = t / NCHUNK, c = t - kg * NCHUNK;
       float acc[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-      const __half* vp = p.v + (long long)b * p.v_sb + (long long)h * DH + c * 8;
-      for (int k0 = kg; k0 < p.Skv; k0 += 8 * KG) {
-        uint4 u[8];
+      for (int key = kg; key < p.Skv; key += KG) {
+        const float w = lds_f1(s_p + 4 * key);
+        const uint4 u = lds_u4(s_v + (uint32_t)(key * RS + c * 16));
+        const __half2* hh = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int key = k0 + j * KG;
-          u[j] = ldg_nc_v4_volatile(vp + (long long)(key < p.Skv ? key : kg) * p.v_ss);   // clamped: weight 0 below
-        }
-#pragma unroll
-        for (int j = 0; j < 8; j += 2) pin_loaded(u[j], u[j + 1]);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int key = k0 + j * KG;
-          const float w = key < p.Skv ? sp[key] : 0.f;
-          const __half2* hh = reinterpret_cast<const __half2*>(&u[j]);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2 f = __half22float2(hh[i]);
-            acc[2 * i] = fmaf(w, f.x, acc[2 * i]);
-            acc[2 * i + 1] = fmaf(w, f.y, acc[2 * i + 1]);
-          }
+        for (int i = 0; i < 4; ++i) {
+          const float2 f = __half22float2(hh[i]);
+          acc[2 * i] = fmaf(w, f.x, acc[2 * i]);
+          acc[2 * i + 1] = fmaf(w, f.y, acc[2 * i + 1]);
         }
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) part[kg * DH + c * 8 + i] = acc[i];
+      for (int i = 0; i < 8; ++i) sts_f1(s_part + 4 * (kg * DH + c * 8 + i), acc[i]);
     }
     __syncthreads();
     if (t < DH) {
       float a = 0.f;
-      for (int kg = 0; kg < KG; ++kg) a += part[kg * DH + t];
+      for (int kg = 0; kg < KG; ++kg) a += lds_f1(s_part + 4 * (kg * DH + t));
       p.o[(long long)b * p.o_sb + (long long)qrow * p.o_ss + (long long)h * p.o_sh + t] = __float2half_rn(a * inv);
     }
     __syncthreads();
