@@ -109,11 +109,15 @@ int stllm_attention_f16(const void* q, const void* k, const void* v, void* out, 
  * tcgen05 kernel; 0 = always the mma.sync kernel. */
 int stllm_set_attention_tc(int on);
 
-/* Experimental variants of the ViT-shape tensor-core attention (measured slower than the default, kept for A/B and parity;
- * profiles/r02_attention.md): wide = 128-key tiles with the leftover key / trailing query rows on CUDA cores in one kernel;
- * tail = default kernel on the full 128-row query tiles + a CUDA-core launch for the trailing rows.  -1 = follow the
- * STLLM_ATTN_WIDE / STLLM_ATTN_TAIL environment variables (default off). */
+/* Variants of the ViT-shape tensor-core attention (A/B and parity; profiles/r02_attention.md): wide = 128-key tiles with
+ * the leftover key / trailing query rows on CUDA cores in one kernel (measured slower, default off);
+ * tail: what happens to the query rows after the last full 128-row tile (the ViT's 257th row): 0 = a third tensor-core
+ * tile, 1 = CUDA-core tail CTAs inside the same grid, 2 = a second small launch (default: measured fastest).  -1 = follow
+ * the STLLM_ATTN_WIDE (default 0) / STLLM_ATTN_TAIL (default 2) environment variables. */
 int stllm_set_attention_variant(int wide, int tail);
+/* kernels launched by the most recent stllm_attention_f16 call (1, or 2 when the trailing query rows of the ViT shape
+   went to their own small launch); bookkeeping for launch counts, not a synchronisation point */
+int stllm_attention_last_launches(void);
 
 /* y = LayerNorm(x) with fp32 statistics; gamma/beta fp32.  eva_vit.py:157,163; blip2.py:103-109; Qformer.py:65,
  * 282,366; st_llm.py:39. */

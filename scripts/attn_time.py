@@ -45,8 +45,14 @@ def t_attn(B, H, Sq, Skv, D, causal=False, pre=True, iters=30):
     print(f"TIME attn B={B} H={H} Sq={Sq} Skv={Skv} D={D} causal={int(causal)}: {best:.1f} us ({fl / best / 1e6:.0f} TF)", flush=True)
 
 
-for shape in ((16, 16, 257, 257, 88), (16, 16, 256, 257, 88), (16, 16, 256, 256, 88), (16, 16, 128, 256, 88),
-              (128, 16, 257, 257, 88)):
+from stllm_b200 import _lib  # noqa: E402
+for tail in (0, 1, 2):
+    _lib.load().stllm_set_attention_variant(0, tail)
+    print(f"--- ViT shapes, trailing-row mode {tail} (0: third query tile, 1: tail CTAs in the grid, 2: separate tail launch)")
+    for shape in ((16, 16, 257, 257, 88), (128, 16, 257, 257, 88)):
+        t_attn(*shape)
+_lib.load().stllm_set_attention_variant(-1, -1)
+for shape in ((16, 16, 256, 257, 88), (16, 16, 256, 256, 88), (16, 16, 128, 256, 88)):
     t_attn(*shape)
 t_attn(1, 32, 576, 576, 128, causal=True, pre=False)
 t_attn(8, 32, 576, 576, 128, causal=True, pre=False)

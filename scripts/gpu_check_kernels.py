@@ -240,7 +240,7 @@ def _a(tc, *a, variant=(-1, -1), **kw):
         finally:
             _L.load().stllm_set_attention_tc(1)
             _L.load().stllm_set_attention_variant(-1, -1)
-    vtag = {(-1, -1): "", (1, 0): " wide-tile", (0, 1): " tail-kernel"}[variant]
+    vtag = {(-1, -1): "", (1, 0): " wide-tile", (0, 1): " tail-ctas", (0, 2): " tail-launch"}[variant]
     _case(f"attn tc={tc}{vtag} " + " ".join(str(x) for x in a) + "".join(f" {k}={v}" for k, v in kw.items()), run)
 
 
@@ -370,7 +370,7 @@ def build_cases():
         _a(tc, 1, 32, 2048, 2048, 128, causal=True, packed=True)   # max_position_embeddings
         _a(tc, 3, 16, 257, 257, 88, prescale=True, packed=True)    # odd batch
         _a(tc, 2, 16, 200, 200, 88, prescale=True, packed=True)    # fewer tokens than the ViT (interpolated grids)
-    for variant in ((1, 0), (0, 1)):       # the two default-off ViT attention experiments stay parity-checked
+    for variant in ((1, 0), (0, 1), (0, 2)):   # wide tiles; tail CTAs inside the grid (1) / as a second launch (2)
         _a(1, 2, 16, 257, 257, 88, prescale=True, packed=True, variant=variant)
         _a(1, 16, 16, 257, 257, 88, prescale=True, packed=True, variant=variant)
         _a(1, 2, 3, 257, 257, 88, variant=variant)

@@ -22,6 +22,7 @@ SIGNATURES = {
     "stllm_gemm_debug_trace": [c_int, c_void_p, c_void_p],
     "stllm_set_gemm_streamk": [c_int],
     "stllm_set_attention_variant": [c_int, c_int],
+    "stllm_attention_last_launches": [],
     "stllm_gemm_plan": [c_int, c_int, c_int, c_int, c_ll_p],
     "stllm_set_attention_tc": [c_int],
     "stllm_gemm_f16": [c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int, c_int, c_int, c_void_p, c_void_p, c_ll,

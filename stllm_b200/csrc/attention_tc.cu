@@ -88,6 +88,9 @@ __host__ __device__ constexpr uint32_t make_idesc_f16_bmn(int M, int N) {   // A
 DEVI uint32_t sw_off(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
 
 template <int DH>
+__device__ __forceinline__ void attention_tail_rows(const AttnTcParams& p, uint8_t* smem, int h, int b);   // defined below
+
+template <int DH>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnTcParams p) {
@@ -109,10 +112,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // Trailing query rows (p.n_tail > 0: the ViT's 257th row) get their own CTAs in the SAME grid (blockIdx.y = number of
+  // full tiles): short CUDA-core CTAs that are dispatched between the tensor-core CTAs and fill slots as those retire,
+  // instead of a third 128-row tile per (frame, head) that holds one row and costs a full TMA -> MMA -> softmax chain.
+  if (p.n_tail > 0 && (int)blockIdx.y >= p.Sq / TQ) {
+    pdl_launch_dependents();
+    pdl_wait();
+    attention_tail_rows<DH>(p, smem, (int)blockIdx.x, (int)blockIdx.z);
+    return;
+  }
   // grid = (heads, query tiles, batch): CTAs are dispatched x-fastest, so all heads of one query tile start together.
   // Causal: the LAST query tile has the most key tiles -> dispatch it first (longest-processing-time-first);
   // non-causal: ragged last tile (1 row of 257 in the ViT) goes last and fills the tail of the final wave.
-  const int n_qt = (int)gridDim.y;
+  const int n_qt = (int)gridDim.y - (p.n_tail > 0 ? 1 : 0);
   const int qt = p.causal ? (n_qt - 1 - (int)blockIdx.y) : (int)blockIdx.y;
   const int q0 = qt * TQ, h = blockIdx.x, b = blockIdx.z;
   const int kv_off = p.Skv - p.Sq;
@@ -939,15 +951,18 @@ int make_tmap3(CUtensorMap* tm, const void* ptr, int feat, int S, int B, long lo
 template <int DH>
 int launch_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcParams& p,
               cudaStream_t stream) {
-  constexpr int SMEM = 2 * BLK_BYTES + 8 * KBLK + 128 + 1024;
+  constexpr int SMEM_TC = 2 * BLK_BYTES + 8 * KBLK + 128 + 1024;
+  // with tail CTAs (p.n_tail > 0) every CTA of the grid gets the larger of the two footprints (still two CTAs per SM)
+  const int smem_tail = p.n_tail > 0 ? TailCfg<DH>::smem_bytes(p.Skv, TC_THREADS) + 1024 : 0;
+  const int smem = smem_tail > SMEM_TC ? smem_tail : SMEM_TC;
   auto kern = attention_tc_kernel<DH>;
-  static bool configured = false;
-  if (!configured) {
-    STLLM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    configured = true;
+  static int configured = 0;
+  if (smem > configured) {
+    STLLM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = smem;
   }
-  dim3 grid(p.H, (p.Sq + TQ - 1) / TQ, p.B);
-  STLLM_CHECK_CUDA(stllm_launch(kern, grid, dim3(TC_THREADS), SMEM, stream, tq, tk, tv, p));
+  dim3 grid(p.H, p.n_tail > 0 ? p.Sq / TQ + 1 : (p.Sq + TQ - 1) / TQ, p.B);
+  STLLM_CHECK_CUDA(stllm_launch(kern, grid, dim3(TC_THREADS), smem, stream, tq, tk, tv, p));
   return STLLM_OK;
 }
 
@@ -970,7 +985,11 @@ int launch_tc_wide(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorM
 
 static int g_attn_tc = -1;   // -1: read STLLM_ATTN_TC on first use (default on)
 static int g_attn_wide = -1;  // -1: read STLLM_ATTN_WIDE on first use (default off)
-static int g_attn_tail = -1;  // -1: read STLLM_ATTN_TAIL on first use (default off)
+static int g_attn_tail = -1;  // -1: read STLLM_ATTN_TAIL on first use (default 2: tail launch)
+static int g_attn_last_launches = 1;
+// kernels launched by the most recent attention call of this process (1, or 2 with the trailing-row launch): the host
+// side counts launches per step from it (bench.py gpu_launches)
+extern "C" int stllm_attention_last_launches(void) { return g_attn_last_launches; }
 // experiments kept in the library (profiles/r02_attention.md): wide = 128-key tiles + leftover key / tail rows on CUDA cores
 // in one kernel; tail = round-1 kernel on the full query tiles + a CUDA-core launch for the trailing rows.  -1 = environment.
 extern "C" int stllm_set_attention_variant(int wide, int tail) {
@@ -989,6 +1008,7 @@ int stllm_attention_tc_try(const void* q, const void* k, const void* v, void* ou
                            const long long* qs, const long long* ks, const long long* vs, const long long* os,
                            float scale, float q_prescale, int causal, const void* key_mask, float mask_value,
                            cudaStream_t stream) {
+  g_attn_last_launches = 1;
   if (g_attn_tc < 0) {
     const char* e = getenv("STLLM_ATTN_TC");
     g_attn_tc = (e != nullptr && atoi(e) == 0) ? 0 : 1;
@@ -1023,7 +1043,7 @@ int stllm_attention_tc_try(const void* q, const void* k, const void* v, void* ou
     p.q = (const __half*)q; p.k = (const __half*)k; p.v = (const __half*)v;
     p.q_sb = qs[0]; p.q_ss = qs[1]; p.k_sb = ks[0]; p.k_ss = ks[1]; p.v_sb = vs[0]; p.v_ss = vs[1];
     p.n_left = (Skv % WKV) <= LEFT_MAX ? (Skv % WKV) : 0;
-    p.n_tail = (Sq % TQ) <= TAIL_MAX ? (Sq % TQ) : 0;
+    p.n_tail = ((Sq % TQ) <= TAIL_MAX && TailCfg<88>::smem_bytes(Skv, TC_THREADS) + 1024 <= WIDE_SMEM) ? (Sq % TQ) : 0;
     return launch_tc_wide<88>(tq, tk, tv, p, stream);
   }
   rc = make_tmap3(&tk, k, H * D, Skv, B, ks[1], ks[0], TKV);
@@ -1039,29 +1059,36 @@ int stllm_attention_tc_try(const void* q, const void* k, const void* v, void* ou
   p.q = (const __half*)q; p.k = (const __half*)k; p.v = (const __half*)v;
   p.q_sb = qs[0]; p.q_ss = qs[1]; p.k_sb = ks[0]; p.k_ss = ks[1]; p.v_sb = vs[0]; p.v_ss = vs[1];
   p.n_left = p.n_tail = 0;
-  // ViT shape: the few query rows after the last full tile go to the CUDA-core tail kernel, the tensor-core kernel runs on
-  // the full tiles only (two launches; the tail launch is 256 small CTAs, ~4 us)
-  // OFF by default: the tail launch itself measures ~25 us (ptxas keeps only two of its 16-byte loads in flight per thread,
-  // so its 257 x 176-byte key rows cost ~30 dependent L2 round trips) -- more than the 10 us the third query tile costs.
-  // STLLM_ATTN_TAIL=1 enables it (parity-green: tests/test_kernels_gpu.py attention cases run with both settings).
-  static const int tail_env = [] { const char* e = getenv("STLLM_ATTN_TAIL"); return (e != nullptr && atoi(e) == 1) ? 1 : 0; }();
+  // ViT shape (257 = 2 x 128 + 1): the query rows after the last full tile go to CUDA-core tail CTAs (K/V of the head staged
+  // in shared memory by one cp.async sweep), the tensor-core kernel runs on the full tiles only.  STLLM_ATTN_TAIL /
+  // stllm_set_attention_variant: 0 = third 128-row tile (round 1), 1 = tail CTAs inside the same grid, 2 (default) = a
+  // second small launch.  Measured in the step on one box, three alternating runs each (profiles/r02_attention.md):
+  // 806 / 808 / 816 frames/s; standalone 39.3 / 40.9 / 35.2 us per layer.
+  static const int tail_env = [] { const char* e = getenv("STLLM_ATTN_TAIL"); return e != nullptr ? atoi(e) : 2; }();
   const int tail_ok = g_attn_tail >= 0 ? g_attn_tail : tail_env;
   const int tail = Sq % TQ;
-  if (tail_ok && D == 88 && !causal && key_mask == nullptr && Sq > TQ && tail >= 1 && tail <= TAIL_MAX && Skv <= 8192) {
-    AttnTcParams pm = p;
-    pm.Sq = Sq - tail;
-    rc = launch_tc<88>(tq, tk, tv, pm, stream);
-    if (rc != STLLM_OK) return rc;
-    p.n_tail = tail;
-    auto kern = attention_tail_kernel<88>;
-    const int smem = (128 + ((Skv + 31) & ~31) + 64 + (TAIL_THREADS / 11) * 88) * 4 + 256;
-    static int configured_smem = 0;
-    if (smem > 48 * 1024 && smem > configured_smem) {
-      STLLM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-      configured_smem = smem;
+  // mode 1: tail CTAs inside the tensor-core kernel's grid (one launch); mode 2: a separate tail launch behind it (A/B)
+  const bool tail_fits = TailCfg<88>::smem_bytes(Skv, TC_THREADS) + 1024 <= 112 * 1024;   // two CTAs per SM must still fit
+  if (tail_ok && D == 88 && !causal && key_mask == nullptr && Sq > TQ && tail >= 1 && tail <= TAIL_MAX && tail_fits) {
+    if (tail_ok == 2) {
+      AttnTcParams pm = p;
+      pm.Sq = Sq - tail;
+      rc = launch_tc<88>(tq, tk, tv, pm, stream);
+      if (rc != STLLM_OK) return rc;
+      p.n_tail = tail;
+      auto kern = attention_tail_kernel<88>;
+      const int smem = TailCfg<88>::smem_bytes(Skv, TAIL_THREADS) + 256;
+      static int configured_smem = 0;
+      if (smem > 48 * 1024 && smem > configured_smem) {
+        STLLM_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        configured_smem = smem;
+      }
+      STLLM_CHECK_CUDA(stllm_launch(kern, dim3(H, 1, B), dim3(TAIL_THREADS), smem, stream, p));
+      g_attn_last_launches = 2;
+      return STLLM_OK;
     }
-    STLLM_CHECK_CUDA(stllm_launch(kern, dim3(H, 1, B), dim3(TAIL_THREADS), smem, stream, p));
-    return STLLM_OK;
+    p.n_tail = tail;
+    return launch_tc<88>(tq, tk, tv, p, stream);
   }
   if (D == 88) return launch_tc<88>(tq, tk, tv, p, stream);
   return launch_tc<128>(tq, tk, tv, p, stream);

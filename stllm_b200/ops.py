@@ -182,7 +182,7 @@ def attention(q, k, v, scale, causal=False, key_mask=None, mask_value=-10000.0, 
                                          float(scale), float(q_prescale), 1 if causal else 0, _ptr(key_mask),
                                          float(mask_value), _stream())
     _lib.check(rc, "stllm_attention_f16")
-    launch_count += 1
+    launch_count += _lib.load().stllm_attention_last_launches()
     return out
 
 
