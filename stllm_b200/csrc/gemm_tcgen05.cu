@@ -126,7 +126,8 @@ struct SmemLayout {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
   static constexpr int TAB_OFFSET = BAR_OFFSET + 256;   // 2 x 256 float2: per-column (s, b') of the folded LayerNorm
-  static constexpr int TOTAL = TAB_OFFSET + 4096 + 1024;  // barriers + table + alignment slack
+  static constexpr int EXCH_OFFSET = TAB_OFFSET + 4096;  // 2 x 128 float2: per-row (mu, rstd), column half 0 -> half 1
+  static constexpr int TOTAL = EXCH_OFFSET + 2048 + 1024;  // barriers + table + row exchange + alignment slack
 };
 
 // wait-cycle counters (debug/profiling aid, read by stllm_gemm_debug_counters):
@@ -210,13 +211,13 @@ struct RowCtx {
 // Everything here is independent of the accumulator: the callers run it BEFORE they wait for the tile's MMAs, so the
 // L2 round trips of the statistics overlap the mainloop instead of sitting between "accumulator ready" and the first
 // store (profiles/r02_epilogue.md: 18 % of the LayerNorm-fold kernel's stall samples were on this loop).
-DEVI void rowctx_begin(RowCtx& rc, const GemmParams& p, int row, bool row_ok) {
+DEVI void rowctx_begin(RowCtx& rc, const GemmParams& p, int row, bool row_ok, bool load_stats = true) {
   rc.mu = 0.f;
   rc.rstd = 1.f;
   rc.st_sum = 0.f;
   rc.st_sq = 0.f;
   rc.tab = 0u;
-  if (p.norm_mode != 0 && row_ok) {
+  if (p.norm_mode != 0 && row_ok && load_stats) {
     // fixed-order sum of the per-slot partial statistics of this row (written by the producing GEMM).  ALL loads of a
     // row go out before the first addition (one L2 round trip, ~1.8k cycles under TMA load, instead of one per batch);
     // the additions keep the slot order.  16 float4 = 64 floats cover K <= 4096 (RMS) / 2048 (LayerNorm) in one pass.
@@ -244,6 +245,18 @@ DEVI void rowctx_begin(RowCtx& rc, const GemmParams& p, int row, bool row_ok) {
       rc.rstd = rsqrtf(fmaxf(s1 * p.norm_inv_k - rc.mu * rc.mu, 0.f) + p.norm_eps);
     }
   }
+}
+// The two column halves of a tile are converted by two warps that own the SAME 32 rows: only the half-0 warp reads the
+// row's statistics slots (scattered 16-byte L2 reads: doubling the readers cost 7 us on the ViT q|k|v GEMM), the other
+// picks (mu, rstd) up from shared memory behind the epilogue warps' barrier.
+DEVI void rowctx_share(RowCtx& rc, const GemmParams& p, bool owner, uint32_t cell, bool have_barrier) {
+  if (p.norm_mode == 0) return;
+  if (owner) asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(cell), "f"(rc.mu), "f"(rc.rstd) : "memory");
+  if (!have_barrier) asm volatile("bar.sync 1, 256;" ::: "memory");
+}
+DEVI void rowctx_pickup(RowCtx& rc, const GemmParams& p, bool owner, uint32_t cell) {
+  if (p.norm_mode == 0 || owner) return;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(rc.mu), "=f"(rc.rstd) : "r"(cell));
 }
 // Column table of one tile -> shared memory (one entry per accumulator column, `ncols` <= 256), by the 256 epilogue
 // threads; also called before the accumulator wait.  Double-buffered per accumulator stage by the callers: the
@@ -796,8 +809,12 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
       ResIn<EPI> res0;
       res0.vec = false;
       if (kb0 == 0) res_issue<EPI>(res0, p, row, row < p.M, n_blk * BN + 32 * half_idx * CHUNKS_PER_WARP, col_end);
-      rowctx_begin(rc, p, row, row < p.M);
+      const bool owner = half_idx == 0;
+      const uint32_t cell = smem_u32(smem + L::EXCH_OFFSET) + (uint32_t)((acc * 128 + row_in_tile) * 8);
+      rowctx_begin(rc, p, row, row < p.M, owner);
+      rowctx_share(rc, p, owner, cell, use_tab);
       if (use_tab) col_table_commit(rc, reinterpret_cast<float2*>(smem + L::TAB_OFFSET) + acc * 256, tab_v, BN);
+      rowctx_pickup(rc, p, owner, cell);
       {
         const long long w = mbar_wait(&tmem_full_bar[acc], acc_phase);
         if (p.prof && warp == 0 && lane == 0) atomicAdd(&g_gemm_prof[3], (unsigned long long)w);
@@ -846,7 +863,8 @@ struct SmemLayout2 {
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int BAR_OFFSET = STAGES2 * STAGE_BYTES;
   static constexpr int TAB_OFFSET = BAR_OFFSET + 256;
-  static constexpr int TOTAL = TAB_OFFSET + 4096 + 1024;
+  static constexpr int EXCH_OFFSET = TAB_OFFSET + 4096;
+  static constexpr int TOTAL = EXCH_OFFSET + 2048 + 1024;
 };
 
 template <int EPI, bool SWAP>
@@ -1072,8 +1090,12 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
         float2 tab_v = make_float2(0.f, 0.f);
         if (use_tab) tab_v = col_table_fetch(p, b_blk * bn, bn);
         if (kb0 == 0) res_issue<EPI>(res0, p, row, row < p.M, b_blk * bn + 32 * c_begin, col_end);
-        rowctx_begin(rc, p, row, row < p.M);
+        const bool owner = half_idx == 0;
+        const uint32_t cell = smem_u32(smem + L::EXCH_OFFSET) + (uint32_t)((acc * 128 + row_in_slot) * 8);
+        rowctx_begin(rc, p, row, row < p.M, owner);
+        rowctx_share(rc, p, owner, cell, use_tab);
         if (use_tab) col_table_commit(rc, reinterpret_cast<float2*>(smem + L::TAB_OFFSET) + acc * 256, tab_v, bn);
+        rowctx_pickup(rc, p, owner, cell);
       }
       {
         const long long w = mbar_wait(&tmem_full_bar[acc], acc_phase);
