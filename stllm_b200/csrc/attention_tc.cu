@@ -134,6 +134,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     kv_end = last < kv_end ? last : kv_end;
     if (kv_end < 1) kv_end = 1;
   }
+  // Leftover keys (p.n_left > 0: the ViT's 257th key, Skv = 4 x 64 + 1) never become a tile of their own -- a fifth
+  // TMA -> MMA -> softmax -> MMA round trip for ONE key cost a fifth of the CTA's serial chain.  The softmax threads score
+  // them on CUDA cores during the Q fix-up pass (one DH-long dot product per row and key), open the online softmax with
+  // them and add their weighted values to O in the epilogue (same scheme as attention_tc_wide_kernel).
+  constexpr int LEFT_CAP = 4;                                  // == LEFT_MAX (defined below with the wide kernel)
+  const int n_left = (DH == 88) ? p.n_left : 0;
+  kv_end -= n_left;
+  const int kv_mma = kv_end;
+  __half* s_left_k = reinterpret_cast<__half*>(bars + 16);      // [LEFT_CAP][96] leftover keys
+  __half* s_left_v = s_left_k + LEFT_CAP * 96;                  // [LEFT_CAP][96] leftover values
   const int n_tiles = (kv_end + TKV - 1) / TKV;
   const int col0 = h * DH;
 
@@ -241,23 +251,59 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int r = quad * 32 + lane;                // row inside the tile == TMEM lane
     const int qrow = q0 + r;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-    // ---- Q fix-up: optional fp16 pre-scale (ViT) and zeroing of the padded contraction columns ----
+    // leftover keys / values -> smem (one 16-byte chunk per thread), zero padded to 96 columns
+    if (DH == 88 && n_left > 0) {
+      const int chunks = n_left * 12;
+      for (int i = r; i < 2 * chunks; i += 128) {
+        const int which = i >= chunks, ii = which ? i - chunks : i;
+        const int li = ii / 12, c = ii % 12;
+        const int key = kv_mma + li;
+        uint4 u = make_uint4(0, 0, 0, 0);
+        if (c * 8 < DH) {
+          const __half* src = which ? p.v + (long long)b * p.v_sb + (long long)key * p.v_ss + (long long)h * DH
+                                    : p.k + (long long)b * p.k_sb + (long long)key * p.k_ss + (long long)h * DH;
+          u = __ldg(reinterpret_cast<const uint4*>(src) + c);
+        }
+        *reinterpret_cast<uint4*>((which ? s_left_v : s_left_k) + li * 96 + c * 8) = u;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    // ---- Q fix-up: optional fp16 pre-scale (ViT), zeroing of the padded contraction columns, leftover-key scores ----
     mbar_wait(q_full, 0);
+    float s_left[LEFT_CAP];
+#pragma unroll
+    for (int i = 0; i < LEFT_CAP; ++i) s_left[i] = 0.f;
     if (DH == 88 || p.q_prescale != 0.f) {
 #pragma unroll 1
       for (int c = 0; c < 16; ++c) {               // 16 chunks of 8 columns = 128 contraction columns
         uint4* ptr = reinterpret_cast<uint4*>(sQ + (c >> 3) * BLK_BYTES + sw_off(r, c & 7));
         if (c * 8 >= DH) {
           if (c * 8 < DK) *ptr = make_uint4(0, 0, 0, 0);
-        } else if (p.q_prescale != 0.f) {
+        } else if (p.q_prescale != 0.f || (DH == 88 && n_left > 0)) {
           uint4 u = *ptr;
           __half2* hh = reinterpret_cast<__half2*>(&u);
+          if (p.q_prescale != 0.f) {
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2 f = __half22float2(hh[i]);
-            hh[i] = __floats2half2_rn(f.x * p.q_prescale, f.y * p.q_prescale);
+            for (int i = 0; i < 4; ++i) {
+              const float2 f = __half22float2(hh[i]);
+              hh[i] = __floats2half2_rn(f.x * p.q_prescale, f.y * p.q_prescale);
+            }
+            *ptr = u;
           }
-          *ptr = u;
+          if (DH == 88) {
+#pragma unroll
+            for (int li = 0; li < LEFT_CAP; ++li) {
+              if (li < n_left) {
+                const uint4 kk = *reinterpret_cast<const uint4*>(s_left_k + li * 96 + c * 8);   // broadcast read
+                const __half2* kh = reinterpret_cast<const __half2*>(&kk);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const float2 a = __half22float2(hh[i]), bb = __half22float2(kh[i]);
+                  s_left[li] = fmaf(a.x, bb.x, fmaf(a.y, bb.y, s_left[li]));
+                }
+              }
+            }
+          }
         }
       }
       fence_proxy_async_smem();
@@ -268,7 +314,19 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const float sl2 = p.scale * LOG2E;
     const float mask_l2 = p.mask_value * LOG2E;
     const unsigned char* kmask = p.kmask ? p.kmask + (long long)b * p.Skv : nullptr;
+    // the leftover keys open the online softmax: m = max of their scores, weights w_i = exp2(s_i - m)
     float m_run = -INFINITY, l_run = 0.f;
+    float w_left[LEFT_CAP];
+#pragma unroll
+    for (int i = 0; i < LEFT_CAP; ++i) {
+      s_left[i] *= sl2;
+      if (DH == 88 && i < n_left) m_run = fmaxf(m_run, s_left[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < LEFT_CAP; ++i) {
+      w_left[i] = (DH == 88 && i < n_left) ? exp2f(s_left[i] - m_run) : 0.f;
+      l_run += w_left[i];
+    }
     const bool warp_valid = (q0 + quad * 32) < p.Sq;   // warps whose 32 rows are all beyond Sq do no math at all
     for (int j = 0; j < n_tiles; ++j) {
       const int kbase = j * TKV;
@@ -347,6 +405,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         l_run = l_run * alpha + sum;
         m_run = m_new;
+        if (DH == 88) {
+#pragma unroll
+          for (int i = 0; i < LEFT_CAP; ++i) w_left[i] *= alpha;
+        }
       }
       // ---- previous P V must be complete before O is rescaled and before sP is overwritten ----
       if (j > 0) {
@@ -399,11 +461,29 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         for (int q = 0; q < 4; ++q) {
           const int colq = c + q * 8;
           if (colq < DH) {
+            float f[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = __uint_as_float(o[8 * q + i]);
+            if (DH == 88) {
+#pragma unroll
+              for (int li = 0; li < LEFT_CAP; ++li) {
+                if (li < n_left) {
+                  const uint4 vv = *reinterpret_cast<const uint4*>(s_left_v + li * 96 + colq);
+                  const __half2* vh = reinterpret_cast<const __half2*>(&vv);
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const float2 x = __half22float2(vh[i]);
+                    f[2 * i] = fmaf(w_left[li], x.x, f[2 * i]);
+                    f[2 * i + 1] = fmaf(w_left[li], x.y, f[2 * i + 1]);
+                  }
+                }
+              }
+            }
             uint4 w;
-            w.x = pack_half2(__uint_as_float(o[8 * q + 0]) * inv, __uint_as_float(o[8 * q + 1]) * inv);
-            w.y = pack_half2(__uint_as_float(o[8 * q + 2]) * inv, __uint_as_float(o[8 * q + 3]) * inv);
-            w.z = pack_half2(__uint_as_float(o[8 * q + 4]) * inv, __uint_as_float(o[8 * q + 5]) * inv);
-            w.w = pack_half2(__uint_as_float(o[8 * q + 6]) * inv, __uint_as_float(o[8 * q + 7]) * inv);
+            w.x = pack_half2(f[0] * inv, f[1] * inv);
+            w.y = pack_half2(f[2] * inv, f[3] * inv);
+            w.z = pack_half2(f[4] * inv, f[5] * inv);
+            w.w = pack_half2(f[6] * inv, f[7] * inv);
             *reinterpret_cast<uint4*>(orow + colq) = w;
           }
         }
@@ -951,7 +1031,7 @@ int make_tmap3(CUtensorMap* tm, const void* ptr, int feat, int S, int B, long lo
 template <int DH>
 int launch_tc(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnTcParams& p,
               cudaStream_t stream) {
-  constexpr int SMEM_TC = 2 * BLK_BYTES + 8 * KBLK + 128 + 1024;
+  constexpr int SMEM_TC = 2 * BLK_BYTES + 8 * KBLK + 128 + 2048 + 1024;   // Q | K | V | barriers | leftover keys/values | slack
   // with tail CTAs (p.n_tail > 0) every CTA of the grid gets the larger of the two footprints (still two CTAs per SM)
   const int smem_tail = p.n_tail > 0 ? TailCfg<DH>::smem_bytes(p.Skv, TC_THREADS) + 1024 : 0;
   const int smem = smem_tail > SMEM_TC ? smem_tail : SMEM_TC;
@@ -1059,6 +1139,11 @@ int stllm_attention_tc_try(const void* q, const void* k, const void* v, void* ou
   p.q = (const __half*)q; p.k = (const __half*)k; p.v = (const __half*)v;
   p.q_sb = qs[0]; p.q_ss = qs[1]; p.k_sb = ks[0]; p.k_ss = ks[1]; p.v_sb = vs[0]; p.v_ss = vs[1];
   p.n_left = p.n_tail = 0;
+  // ViT shape (257 keys = 4 x 64 + 1): the key(s) after the last full 64-key tile are scored on CUDA cores by the softmax
+  // threads instead of costing a fifth tile round trip (STLLM_ATTN_LEFT=0 restores the fifth tile)
+  static const int left_env = [] { const char* e = getenv("STLLM_ATTN_LEFT"); return e != nullptr ? atoi(e) : 1; }();
+  if (left_env && D == 88 && !causal && key_mask == nullptr && Skv > TKV && (Skv % TKV) >= 1 && (Skv % TKV) <= LEFT_MAX)
+    p.n_left = Skv % TKV;
   // ViT shape (257 = 2 x 128 + 1): the query rows after the last full tile go to CUDA-core tail CTAs (K/V of the head staged
   // in shared memory by one cp.async sweep), the tensor-core kernel runs on the full tiles only.  STLLM_ATTN_TAIL /
   // stllm_set_attention_variant: 0 = third 128-row tile (round 1), 1 = tail CTAs inside the same grid, 2 (default) = a
