@@ -523,6 +523,12 @@ def multi_gpu_legs(model, args, dev, rank, world):
                 single.capture()
                 ms1 = _timed(single.run, 3, warm=1)
                 res["bit_identical_to_one_gpu"] = bool(torch.equal(single.logits, sharded_logits))
+                # not guaranteed at every world size: the row statistics of the folded LayerNorms are summed per column
+                # tile of the producing GEMM, and the planner's tile width depends on the row count (frames per rank), so
+                # the fp32 partial sums may group differently -> last-bit differences, reported here
+                d = (single.logits.float() - sharded_logits.float())
+                res["max_abs_diff_vs_one_gpu"] = float(d.abs().max())
+                res["rel_fro_diff_vs_one_gpu"] = float(d.norm() / single.logits.float().norm().clamp_min(1e-30))
                 res["one_gpu_ms_per_clip"] = ms1
                 res["speedup_vs_one_gpu"] = ms1 / ms
                 del single
