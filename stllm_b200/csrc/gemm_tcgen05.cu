@@ -856,15 +856,24 @@ gemm_f16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_co
 //     HBM latency overlaps the previous kernel's tail.
 // ================================================================================================
 constexpr int BN2_MAX = 256;
-constexpr int STAGES2 = 6;
+// Pipeline stages of the CTA-pair engine: the stage area is fixed (192 KB), the stage size follows the tile width
+// (16 KB of lane operand + bn/2 rows x 128 B of column operand, a multiple of 1 KB because bn is a multiple of 16), so
+// narrower tiles get deeper pipelines: bn 256..193 -> 6 stages, 192..177 -> 6, 176..145 -> 7, <= 128 -> 8.  The
+// one-tile-per-cluster LLM GEMMs (o_proj, down: bn = 176) are latency-bound on their weight tiles; a stage more in flight
+// is the only latency cover shared memory has left.
+constexpr int STAGES2_MAX = 8;
+constexpr int STAGE_AREA2 = 6 * (BM * BK * 2 + (BN2_MAX / 2) * BK * 2);   // 196608 B
 struct SmemLayout2 {
   static constexpr int A_BYTES = BM * BK * 2;              // 16 KB: this CTA's 128 rows of the lane operand
-  static constexpr int B_BYTES = (BN2_MAX / 2) * BK * 2;   // <= 16 KB: this CTA's half of the column operand tile
-  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFFSET = STAGES2 * STAGE_BYTES;
+  static constexpr int BAR_OFFSET = STAGE_AREA2;
   static constexpr int TAB_OFFSET = BAR_OFFSET + 256;
   static constexpr int EXCH_OFFSET = TAB_OFFSET + 4096;
   static constexpr int TOTAL = EXCH_OFFSET + 2048 + 1024;
+  __host__ __device__ static int stage_bytes(int bn) { return A_BYTES + (bn / 2) * BK * 2; }
+  __host__ __device__ static int stages(int bn) {
+    const int n = STAGE_AREA2 / stage_bytes(bn);
+    return n > STAGES2_MAX ? STAGES2_MAX : n;
+  }
 };
 
 template <int EPI, bool SWAP>
@@ -875,8 +884,8 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
-  uint64_t* empty_bar = full_bar + STAGES2;
-  uint64_t* tmem_full_bar = empty_bar + STAGES2;
+  uint64_t* empty_bar = full_bar + STAGES2_MAX;
+  uint64_t* tmem_full_bar = empty_bar + STAGES2_MAX;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
@@ -892,13 +901,15 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
   const int num_tiles = a_tiles * b_tiles;
   const int k_blocks = (p.K + BK - 1) / BK;
   const int bn = p.bn;
-  const uint32_t stage_tx = 2u * (uint32_t)(L::A_BYTES + (bn / 2) * BK * 2);   // bytes of both CTAs per k-block
+  const int n_stages = L::stages(bn);
+  const int stage_bytes = L::stage_bytes(bn);
+  const uint32_t stage_tx = 2u * (uint32_t)stage_bytes;   // bytes of both CTAs per k-block
   constexpr uint32_t TMEM_COLS = 512;            // 2 accumulator stages x 256 fp32 columns
 
   if (warp == WARP_TMA && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
-    for (int s = 0; s < STAGES2; ++s) {
+    for (int s = 0; s < n_stages; ++s) {
       mbar_init(&full_bar[s], 1);     // leader's copy is the one in use: 1 arrival (leader producer) + tx bytes
       mbar_init(&empty_bar[s], 1);    // one multicast tcgen05.commit
     }
@@ -937,10 +948,10 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
       WorkIter peek = it;
       if (peek.next(tile, kb0, kb1)) {
         decode(tile, a_blk, b_blk);
-        n_pre = (kb1 - kb0 < STAGES2) ? (kb1 - kb0) : STAGES2;
+        n_pre = (kb1 - kb0 < n_stages) ? (kb1 - kb0) : n_stages;
         if (elect_one()) {
           for (int s = 0; s < n_pre; ++s) {
-            uint8_t* sa = smem + s * L::STAGE_BYTES;
+            uint8_t* sa = smem + s * stage_bytes;
             if (is_leader) mbar_arrive_expect_tx(&full_bar[s], stage_tx);
             if (SWAP) tma_load_2d_2sm(&tmA, &full_bar[s], sa, (kb0 + s) * BK, a_blk * 256 + (int)cta_rank * 128, p.hint_a);
             else tma_load_2d_2sm(&tmB, &full_bar[s], sa + L::A_BYTES, (kb0 + s) * BK, b_blk * bn + (int)cta_rank * (bn / 2), p.hint_b);
@@ -959,7 +970,7 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
       for (int kb = kb0; kb < kb1; ++kb, ++issued) {
         if (p.prof) w_acc += mbar_wait(&empty_bar[stage], phase ^ 1);
         else mbar_wait_spin(&empty_bar[stage], phase ^ 1);
-        uint8_t* sa = smem + stage * L::STAGE_BYTES;
+        uint8_t* sa = smem + stage * stage_bytes;
         uint8_t* sb = sa + L::A_BYTES;
         const bool pre = issued < n_pre;   // weight tile of this k-block already requested
         if (elect_one()) {
@@ -968,7 +979,7 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
           if (!(pre && !SWAP)) tma_load_2d_2sm(&tmB, &full_bar[stage], sb, kb * BK, row_b, p.hint_b);
         }
         __syncwarp();
-        if (++stage == STAGES2) { stage = 0; phase ^= 1; }
+        if (++stage == n_stages) { stage = 0; phase ^= 1; }
       }
     }
     if (p.prof && lane == 0) atomicAdd(&g_gemm_prof[0], (unsigned long long)w_acc);
@@ -1014,8 +1025,8 @@ gemm_f16_tcgen05_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __gr
             umma_commit_2sm(&empty_bar[stage], 3);   // frees this smem slot in BOTH CTAs
           }
           __syncwarp();
-          lo += L::STAGE_BYTES >> 4;
-          if (++stage == STAGES2) { stage = 0; phase ^= 1; lo = lo0; }
+          lo += (uint32_t)stage_bytes >> 4;
+          if (++stage == n_stages) { stage = 0; phase ^= 1; lo = lo0; }
         }
         if (elect_one()) umma_commit_2sm(&tmem_full_bar[acc], 3);   // accumulators of both CTAs complete
         __syncwarp();
