@@ -112,21 +112,32 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // Trailing query rows (p.n_tail > 0: the ViT's 257th row) get their own CTAs in the SAME grid (blockIdx.y = number of
-  // full tiles): short CUDA-core CTAs that are dispatched between the tensor-core CTAs and fill slots as those retire,
-  // instead of a third 128-row tile per (frame, head) that holds one row and costs a full TMA -> MMA -> softmax chain.
-  if (p.n_tail > 0 && (int)blockIdx.y >= p.Sq / TQ) {
-    pdl_launch_dependents();
-    pdl_wait();
-    attention_tail_rows<DH>(p, smem, (int)blockIdx.x, (int)blockIdx.z);
-    return;
+  // Trailing query rows (p.n_tail > 0: the ViT's 257th row) can get their own short CUDA-core CTAs in the SAME grid
+  // (trailing-row mode 1) instead of a third 128-row tile per (frame, head) that holds one row and costs a full
+  // TMA -> MMA -> softmax chain.  With tail CTAs the grid is re-indexed linearly: ALL tensor-core CTAs first (same order as without tail CTAs), the
+  // short tail CTAs last, so they are dispatched after the last tensor-core CTA and fill the slots the ragged final wave
+  // leaves free instead of delaying the first wave (interleaved per batch they cost more than they saved).
+  int bx = (int)blockIdx.x, by = (int)blockIdx.y, bz = (int)blockIdx.z;
+  int n_qt = (int)gridDim.y;
+  if (p.n_tail > 0) {
+    n_qt -= 1;
+    const int H = (int)gridDim.x, L = bx + H * (by + (n_qt + 1) * bz), main_total = H * n_qt * (int)gridDim.z;
+    if (L >= main_total) {
+      const int T = L - main_total;
+      pdl_launch_dependents();
+      pdl_wait();
+      attention_tail_rows<DH>(p, smem, T % H, T / H);
+      return;
+    }
+    bx = L % H;
+    by = (L / H) % n_qt;
+    bz = L / (H * n_qt);
   }
   // grid = (heads, query tiles, batch): CTAs are dispatched x-fastest, so all heads of one query tile start together.
   // Causal: the LAST query tile has the most key tiles -> dispatch it first (longest-processing-time-first);
   // non-causal: ragged last tile (1 row of 257 in the ViT) goes last and fills the tail of the final wave.
-  const int n_qt = (int)gridDim.y - (p.n_tail > 0 ? 1 : 0);
-  const int qt = p.causal ? (n_qt - 1 - (int)blockIdx.y) : (int)blockIdx.y;
-  const int q0 = qt * TQ, h = blockIdx.x, b = blockIdx.z;
+  const int qt = p.causal ? (n_qt - 1 - by) : by;
+  const int q0 = qt * TQ, h = bx, b = bz;
   const int kv_off = p.Skv - p.Sq;
   int kv_end = p.Skv;
   if (p.causal) {
