@@ -907,10 +907,10 @@ def main():
                            n_clips=args.batch)
     achieved = gemm_flops / (ms_gemm / 1e3) / 1e12
     # DRAM traffic of the dominant kernel: NOT measured by this run (ncu cannot run inside a timed bench) -- the committed
-    # all-launch capture of one step (profiles/r02_gemm_traffic.json: dram__bytes_read + dram__bytes_write summed over every
+    # all-launch capture of one step (profiles/r02_gemm_traffic_final.json: dram__bytes_read + dram__bytes_write summed over every
     # GEMM launch of a bench step / launches), else round 1's 6-launch sample; `traffic_source` says which
     traffic, traffic_source = None, None
-    for name in ("r02_gemm_traffic.json", "gemm_traffic.json"):
+    for name in ("r02_gemm_traffic_final.json", "r02_gemm_traffic.json", "gemm_traffic.json"):
         tp = os.path.join(ROOT, "profiles", name)
         if os.path.exists(tp):
             with open(tp) as f:
