@@ -81,30 +81,6 @@ def timed_graph(fn, min_ms=60.0):
     return e0.elapsed_time(e1) / n
 
 
-def _unused(fn, min_ms=60.0):
-    fn()
-    torch.cuda.synchronize()
-    g = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(g):
-        fn()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    for _ in range(2):
-        g.replay()
-    e0.record()
-    g.replay()
-    e1.record()
-    torch.cuda.synchronize()
-    one = max(e0.elapsed_time(e1), 1e-3)
-    n = max(3, int(min_ms / one) + 1)
-    e0.record()
-    for _ in range(n):
-        g.replay()
-    e1.record()
-    torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / n
-
-
 def main():
     from stllm_b200 import ops
     from stllm_b200.pipeline import VideoPrefillPipeline, build_model
