@@ -530,20 +530,6 @@ constexpr int LEFT_MAX = 4;
 constexpr int TAIL_MAX = 4;
 constexpr int WIDE_SMEM = 2 * BLK_BYTES + 2 * WKBLK + 2 * WKBLK + 4096 + 1024;   // Q | K (= P) | V | barriers + leftovers
 
-// 16-byte read-only load that ptxas may not sink next to its first use: batches of these are issued back to back, so a
-// thread has all pieces of a key / value row in flight at once (plain __ldg loads were re-serialised two at a time)
-DEVI uint4 ldg_nc_v4_volatile(const void* ptr) {
-  uint4 r;
-  asm volatile("ld.global.nc.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(ptr));
-  return r;
-}
-
-// "use" barrier: the values pass through a volatile asm, so everything computed from them is ordered after it -- and it is
-// ordered after every volatile load before it.  Placed behind a batch of loads it keeps the whole batch in flight.
-DEVI void pin_loaded(uint4& a, uint4& b) {
-  asm volatile("" : "+r"(a.x), "+r"(a.y), "+r"(a.z), "+r"(a.w), "+r"(b.x), "+r"(b.y), "+r"(b.z), "+r"(b.w));
-}
-
 // ---- CUDA-core path for the <= TAIL_MAX query rows after the last full 128-row tile (ViT: row 257 of 257) ----
 // One CTA per (head, batch).  The head's K and V ([Skv][DH] fp16, 2 x 45 KB for the ViT) are staged in shared memory with
 // one sweep of 16-byte cp.async copies (everything in flight at once: one L2 round trip instead of the ~30 dependent ones of
